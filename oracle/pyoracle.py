@@ -1,0 +1,204 @@
+"""ctypes front ends for the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+arm may import this module (see oracle/jda_oracle.c header).
+
+  Oracle  -- our restatement, oracle/libjda_oracle.so (instrumented)
+  RefLib  -- the reference's own c/jda.c, oracle/_ref/libjda_ref.so, reached
+             through the reference's C API (c/jda.h:18-68) and nothing else
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libjda_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libjda_ref.so")
+
+
+def build(quiet=True):
+    """make -C oracle (restatement always; _ref only where /root/reference exists)."""
+    subprocess.run(["make", "-C", HERE, "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+class _Result(C.Structure):
+    # c/jda.h:18-24
+    _fields_ = [("n", C.c_int), ("landmark_n", C.c_int),
+                ("bboxes", C.POINTER(C.c_int)),
+                ("shapes", C.POINTER(C.c_float)),
+                ("scores", C.POINTER(C.c_float))]
+
+
+def _unpack(res, free):
+    n, L = res.n, res.landmark_n
+    if n > 0:
+        boxes = np.ctypeslib.as_array(res.bboxes, shape=(n, 3)).copy()
+        shapes = np.ctypeslib.as_array(res.shapes, shape=(n, 2 * L)).copy()
+        scores = np.ctypeslib.as_array(res.scores, shape=(n,)).copy()
+    else:
+        boxes = np.zeros((0, 3), np.int32)
+        shapes = np.zeros((0, 2 * L), np.float32)
+        scores = np.zeros((0,), np.float32)
+    free(res)
+    return boxes, scores, shapes
+
+
+def _img(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 2
+    return a, a.ctypes.data_as(C.POINTER(C.c_ubyte)), a.shape[1], a.shape[0]
+
+
+class RefLib:
+    """The unmodified reference library, via its public C API only."""
+
+    def __init__(self, path=REF_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = self.lib = C.CDLL(path)
+        for f in ("jdaCascadorCreateDouble", "jdaCascadorCreateFloat"):
+            getattr(L, f).restype = C.c_void_p
+            getattr(L, f).argtypes = [C.c_char_p]
+        L.jdaCascadorSerializeTo.argtypes = [C.c_void_p, C.c_char_p]
+        L.jdaCascadorSerializeTo.restype = None
+        L.jdaCascadorRelease.argtypes = [C.c_void_p]
+        L.jdaCascadorRelease.restype = None
+        L.jdaDetect.restype = _Result
+        L.jdaDetect.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int,
+                                C.c_float, C.c_float, C.c_int, C.c_int, C.c_float]
+        L.jdaResultRelease.argtypes = [_Result]
+        L.jdaResultRelease.restype = None
+
+    def load(self, path, double=True):
+        f = self.lib.jdaCascadorCreateDouble if double else self.lib.jdaCascadorCreateFloat
+        return f(os.fsencode(path))
+
+    def save_f32(self, handle, path):
+        self.lib.jdaCascadorSerializeTo(handle, os.fsencode(path))
+
+    def release(self, handle):
+        self.lib.jdaCascadorRelease(handle)
+
+    def detect(self, handle, img, scale=1.25, step=0.1, min_size=24, max_size=-1, th=0.0):
+        a, p, w, h = _img(img)
+        res = self.lib.jdaDetect(handle, p, w, h, scale, step, min_size, max_size, th)
+        return _unpack(res, self.lib.jdaResultRelease)
+
+
+class Oracle:
+    """Our instrumented restatement."""
+
+    N_STATS = 19
+
+    def __init__(self, path=ORACLE_SO):
+        if not os.path.exists(path):
+            build()
+        L = self.lib = C.CDLL(path)
+        L.jdo_load.restype = C.c_void_p
+        L.jdo_load.argtypes = [C.c_char_p, C.c_int]
+        L.jdo_free.argtypes = [C.c_void_p]
+        L.jdo_free.restype = None
+        L.jdo_save_f32.argtypes = [C.c_void_p, C.c_char_p]
+        L.jdo_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.jdo_dims.restype = None
+        L.jdo_resize.argtypes = [C.POINTER(C.c_ubyte), C.c_int, C.c_int,
+                                 C.POINTER(C.c_ubyte), C.c_int, C.c_int]
+        L.jdo_resize.restype = None
+        L.jdo_levels.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                 C.POINTER(C.c_int), C.c_int]
+        L.jdo_nms.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float),
+                              C.POINTER(C.c_ubyte)]
+        L.jdo_nms.restype = None
+        L.jdo_detect.restype = _Result
+        L.jdo_detect.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int,
+                                 C.c_float, C.c_float, C.c_int, C.c_int, C.c_float]
+        L.jdo_detect_raw.restype = _Result
+        L.jdo_detect_raw.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int,
+                                     C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                     C.POINTER(C.c_longlong)]
+        L.jdo_result_free.argtypes = [_Result]
+        L.jdo_result_free.restype = None
+        L.jdo_trace.restype = C.c_longlong
+        L.jdo_trace.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_float,
+                                C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                C.POINTER(C.c_float), C.POINTER(C.c_ubyte),
+                                C.c_longlong, C.c_longlong]
+        L.jdo_count_windows.restype = C.c_longlong
+        L.jdo_count_windows.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+
+    def load(self, path, double=True):
+        return self.lib.jdo_load(os.fsencode(path), 1 if double else 0)
+
+    def release(self, h):
+        self.lib.jdo_free(h)
+
+    def save_f32(self, h, path):
+        return self.lib.jdo_save_f32(h, os.fsencode(path))
+
+    def dims(self, h):
+        d = (C.c_int * 4)()
+        self.lib.jdo_dims(h, d)
+        return tuple(d)
+
+    def resize(self, img, dw, dh):
+        a, p, w, h = _img(img)
+        out = np.empty((dh, dw), np.uint8)
+        self.lib.jdo_resize(p, w, h, out.ctypes.data_as(C.POINTER(C.c_ubyte)), dw, dh)
+        return out
+
+    def levels(self, w, h, scale=1.25, min_size=24, max_size=-1):
+        buf = (C.c_int * 256)()
+        n = self.lib.jdo_levels(w, h, scale, min_size, max_size, buf, 256)
+        return list(buf[:min(n, 256)])
+
+    def count_windows(self, w, h, scale=1.25, min_size=24, max_size=-1):
+        return int(self.lib.jdo_count_windows(w, h, scale, min_size, max_size))
+
+    def nms(self, boxes, scores):
+        boxes = np.ascontiguousarray(boxes, np.int32)
+        scores = np.ascontiguousarray(scores, np.float32)
+        keep = np.zeros(max(len(scores), 1), np.uint8)
+        self.lib.jdo_nms(len(scores), boxes.ctypes.data_as(C.POINTER(C.c_int)),
+                         scores.ctypes.data_as(C.POINTER(C.c_float)),
+                         keep.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return keep[:len(scores)].astype(bool)
+
+    def detect(self, h, img, scale=1.25, step=0.1, min_size=24, max_size=-1, th=0.0):
+        a, p, w, hh = _img(img)
+        res = self.lib.jdo_detect(h, p, w, hh, scale, step, min_size, max_size, th)
+        return _unpack(res, self.lib.jdo_result_free)
+
+    def detect_raw(self, h, img, scale=1.25, min_size=24, max_size=-1, th=0.0,
+                   t_limit=0, use_th=True):
+        """pre-NMS hits (scan order, normalised shapes) + stats dict."""
+        a, p, w, hh = _img(img)
+        st = (C.c_longlong * self.N_STATS)()
+        res = self.lib.jdo_detect_raw(h, p, w, hh, scale, min_size, max_size, th,
+                                      t_limit, 1 if use_th else 0, st)
+        boxes, scores, shapes = _unpack(res, self.lib.jdo_result_free)
+        stats = {"windows": st[0], "carts": st[1], "ub_reads": st[2],
+                 "stage_survivors": list(st[3:3 + 16])}
+        return boxes, scores, shapes, stats
+
+    def trace(self, h, img, scale=1.25, min_size=24, max_size=-1, t_limit=0, leaf_range=None):
+        """per-window (carts evaluated, exit score) in scan order; optional leaves."""
+        a, p, w, hh = _img(img)
+        nwin = self.count_windows(w, hh, scale, min_size, max_size)
+        tn = np.zeros(max(nwin, 1), np.int32)
+        ts = np.zeros(max(nwin, 1), np.float32)
+        T, K, _, _ = self.dims(h)
+        if leaf_range is not None:
+            w0, w1 = leaf_range
+            lv = np.full((max(w1 - w0, 1), T * K), 255, np.uint8)
+            lp = lv.ctypes.data_as(C.POINTER(C.c_ubyte))
+        else:
+            w0 = w1 = 0
+            lv, lp = None, None
+        n = self.lib.jdo_trace(h, p, w, hh, scale, min_size, max_size, t_limit,
+                               tn.ctypes.data_as(C.POINTER(C.c_int)),
+                               ts.ctypes.data_as(C.POINTER(C.c_float)), lp, w0, w1)
+        assert n == nwin, (n, nwin)
+        return tn[:nwin], ts[:nwin], lv
