@@ -1,0 +1,155 @@
+/*
+ * jda_b200.h -- C ABI of libjda_b200.so, the B200 (sm_100a) implementation of JDA's
+ * sliding-window detect-and-align path.
+ *
+ * Part 1 is the reference's own C API, symbol for symbol (reference c/jda.h:18-68,
+ * implemented there by c/jda.c:443-727).  A program linked against the reference's
+ * libjda can be relinked against libjda_b200.so unchanged.
+ *
+ * Part 2 is additive (reference has no equivalent): many frames per call, frames already
+ * resident in HBM, truncated-cascade / raw-hit output for hard-negative mining
+ * (the Validate loop of src/jda/cascador.cpp:166-211 as used by src/jda/data.cpp:971-1012),
+ * device/stream selection, work counters and kernel timings.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ */
+#ifndef JDA_B200_H_
+#define JDA_B200_H_
+
+#include <stddef.h>
+
+#if defined(_MSC_VER)
+#define JDA_API __declspec(dllexport)
+#else
+#define JDA_API __attribute__((visibility("default")))
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================== Part 1: reference API */
+
+/* replaces c/jda.h:18-24.  bboxes = int[3n] (x, y, size); shapes = float[2*landmark_n*n] in
+ * image pixels; scores = float[n].  The three arrays are malloc'd by the library and owned by
+ * the caller until jdaResultRelease.  Extension: n < 0 signals a CUDA failure (the reference
+ * has no error channel); the arrays are then NULL and jdaB200LastError() says why. */
+typedef struct {
+  int n;
+  int landmark_n;
+  int *bboxes;
+  float *shapes;
+  float *scores;
+} jdaResult;
+
+/* replaces c/jda.c:486-561 / :563-638.  Same file layouts (README.md:84-111), same (float)
+ * narrowing of the double flavour.  Returns NULL on open/short-read failure like the reference,
+ * and additionally on a header this build cannot run (tree_depth != 4).  No CUDA work happens
+ * here: the device is touched on the first detect call. */
+JDA_API void *jdaCascadorCreateDouble(const char *model);
+JDA_API void *jdaCascadorCreateFloat(const char *model);
+
+/* replaces c/jda.c:644-716.  Byte-identical output (float32 flavour, stage field T+1, cart -1). */
+JDA_API void jdaCascadorSerializeTo(void *cascador, const char *model);
+
+/* replaces c/jda.c:718-720.  NULL-safe; also frees device tables, streams and scratch. */
+JDA_API void jdaCascadorRelease(void *cascador);
+
+/* replaces c/jda.c:443-480.  `data`: 8-bit gray, row-major, stride == width, borrowed.
+ * `step` is accepted and ignored exactly as in the reference (c/jda.c:333 shadows it with 0.1).
+ * min_size is clamped up to 24, max_size <= 0 means min(width, height) (c/jda.c:459-460).
+ * scale <= 1 (an endless loop in the reference) returns n = 0.
+ * Re-entrant: calls on one handle from several threads are serialised internally. */
+JDA_API jdaResult jdaDetect(void *cascador, unsigned char *data, int width, int height,
+                            float scale, float step, int min_size, int max_size, float th);
+
+/* replaces c/jda.c:722-727.  NULL-safe. */
+JDA_API void jdaResultRelease(jdaResult result);
+
+/* ========================================================================= Part 2: additive */
+
+enum {
+  JDA_B200_DEVICE_INPUT = 1, /* `frames` is a device pointer (frames resident in HBM)           */
+  JDA_B200_RAW_HITS = 2,     /* no NMS, no relocation: every passing window, scan order,        */
+                             /* shapes window-normalised (what c/jda.c:416-437 collects)        */
+  JDA_B200_NO_FINAL_TH = 4,  /* skip the final score threshold of c/jda.c:414 (mining)          */
+  JDA_B200_NO_TMA = 8,       /* debug: fill shared-memory tiles with plain loads, not TMA       */
+  JDA_B200_NO_STAGE0_SCAN = 16 /* debug: skip the stage-0 scan kernel, run every window through */
+                             /* the generic per-window kernel                                   */
+};
+
+/* One batch of equally sized frames.  Frame f starts at frames + f*frame_stride, rows are
+ * `pitch` bytes apart.  With JDA_B200_DEVICE_INPUT the TMA tile path needs pitch % 16 == 0 and
+ * a 16-byte aligned base (otherwise tiles are filled by plain loads). */
+typedef struct {
+  int n_frames;
+  int width, height;
+  int pitch;
+  size_t frame_stride;
+  float scale;
+  int min_size, max_size;
+  float th;
+  int t_limit; /* 0 = all stages; 1..T = only the first t_limit stages (Validate's current_stage_idx) */
+  int flags;
+} jdaB200Batch;
+
+/* work counters + device timings of the last batch call on this handle */
+typedef struct {
+  long long windows;          /* candidate windows enumerated (c/jda.c:332-339)                */
+  long long stage0_survivors; /* windows that passed all K carts of stage 0                    */
+  long long raw_hits;         /* windows that passed everything (pre-NMS)                      */
+  long long detections;       /* after NMS                                                     */
+  float ms_h2d, ms_resize, ms_scan, ms_cascade, ms_d2h, ms_host; /* CUDA-event / host timings  */
+  int scan_launches, cascade_launches, resize_launches;
+  int n_levels;
+  int levels_smem;            /* levels served from TMA-filled shared-memory tiles             */
+} jdaB200Stats;
+
+/* Detect on n_frames frames.  results[n_frames] are filled like jdaDetect would fill them, one per
+ * frame (release each with jdaResultRelease).  Returns 0, or a negative value on failure
+ * (results then have n = -1). */
+JDA_API int jdaB200DetectBatch(void *cascador, const unsigned char *frames, const jdaB200Batch *batch,
+                               jdaResult *results, jdaB200Stats *stats /* may be NULL */);
+
+/* Bind the handle to a CUDA device (default: device 0 / current at first use) and, optionally, to
+ * a caller-owned cudaStream_t (NULL = the handle's own stream). */
+JDA_API int jdaB200SetDevice(void *cascador, int device);
+JDA_API int jdaB200SetStream(void *cascador, void *cuda_stream);
+
+/* model dimensions: out[0..3] = T, K, landmark_n, tree_depth */
+JDA_API void jdaB200ModelDims(void *cascador, int *out4);
+
+/* last error text of the calling thread ("" if none) */
+JDA_API const char *jdaB200LastError(void);
+
+/* number of visible CUDA devices (0 on a CPU-only box; never fails) */
+JDA_API int jdaB200DeviceCount(void);
+
+/* ---- host-side helpers exported for tests and tools (no device needed) -------------------- */
+
+/* window sizes visited for a (w, h) frame: the loop of c/jda.c:320-332.  Returns the count. */
+JDA_API int jdaB200Levels(int width, int height, float scale, int min_size, int max_size,
+                          int *wins, int cap);
+/* candidate windows for a (w, h) frame (c/jda.c:332-339) */
+JDA_API long long jdaB200CountWindows(int width, int height, float scale, int min_size, int max_size);
+/* the greedy NMS of c/jda.c:237-316: keep[i] = 1 for survivors (scan order preserved) */
+JDA_API void jdaB200Nms(int n, const int *bboxes, const float *scores, unsigned char *keep);
+
+/* ---- per-window trace (tests): scan order, one frame ------------------------------------- */
+/* Runs the full device path on one host frame and records, for every candidate window, the
+ * number of carts evaluated and the score at exit; for windows [leaf_w0, leaf_w1) also the leaf
+ * index of every evaluated cart ([T*K] bytes each, 255 = not evaluated).  Returns the window
+ * count or a negative value. */
+JDA_API long long jdaB200Trace(void *cascador, const unsigned char *frame, int width, int height,
+                               float scale, int min_size, int max_size, int t_limit, int flags,
+                               int *carts_evaluated, float *exit_score, unsigned char *leaves,
+                               long long leaf_w0, long long leaf_w1);
+
+/* Device bilinear down-sample (replaces jdaImageResize, c/jda.c:203-230); host in, host out. */
+JDA_API int jdaB200Resize(void *cascador, const unsigned char *src, int sw, int sh,
+                          unsigned char *dst, int dw, int dh);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JDA_B200_H_ */

@@ -1,0 +1,256 @@
+"""Python front end of libjda_b200.so -- mirrors the reference's C API (c/jda.h:18-68).
+
+    c = Cascador("model.bin", double=True)          # jdaCascadorCreateDouble / ...Float
+    boxes, scores, shapes = c.detect(gray, scale=1.25, step=0.1, min_size=24, max_size=-1, th=0.0)
+    c.save_f32("model_f32.bin")                      # jdaCascadorSerializeTo
+    c.close()                                        # jdaCascadorRelease
+
+plus the additive batch / device-resident / trace entry points of include/jda_b200.h.
+Every call goes through the C ABI with plain pointers; there is no Python or CPU implementation
+of the detect path here -- if the CUDA library is missing or no GPU is visible the call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjda_b200.so")
+
+DEVICE_INPUT, RAW_HITS, NO_FINAL_TH, NO_TMA, NO_STAGE0_SCAN = 1, 2, 4, 8, 16
+
+
+class _Result(C.Structure):
+    _fields_ = [("n", C.c_int), ("landmark_n", C.c_int),
+                ("bboxes", C.POINTER(C.c_int)),
+                ("shapes", C.POINTER(C.c_float)),
+                ("scores", C.POINTER(C.c_float))]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_frames", C.c_int), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_int),
+                ("frame_stride", C.c_size_t), ("scale", C.c_float), ("min_size", C.c_int),
+                ("max_size", C.c_int), ("th", C.c_float), ("t_limit", C.c_int), ("flags", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("windows", C.c_longlong), ("stage0_survivors", C.c_longlong),
+                ("raw_hits", C.c_longlong), ("detections", C.c_longlong),
+                ("ms_h2d", C.c_float), ("ms_resize", C.c_float), ("ms_scan", C.c_float),
+                ("ms_cascade", C.c_float), ("ms_d2h", C.c_float), ("ms_host", C.c_float),
+                ("scan_launches", C.c_int), ("cascade_launches", C.c_int), ("resize_launches", C.c_int),
+                ("n_levels", C.c_int), ("levels_smem", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """dlopen libjda_b200.so (built in-tree by `make -C jda_b200` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: build it with __graft_entry__.build() or `make -C jda_b200`; "
+                           "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, cp, ci, cf = C.c_void_p, C.c_char_p, C.c_int, C.c_float
+    ub = C.POINTER(C.c_ubyte)
+    L.jdaCascadorCreateDouble.restype = vp
+    L.jdaCascadorCreateDouble.argtypes = [cp]
+    L.jdaCascadorCreateFloat.restype = vp
+    L.jdaCascadorCreateFloat.argtypes = [cp]
+    L.jdaCascadorSerializeTo.restype = None
+    L.jdaCascadorSerializeTo.argtypes = [vp, cp]
+    L.jdaCascadorRelease.restype = None
+    L.jdaCascadorRelease.argtypes = [vp]
+    L.jdaDetect.restype = _Result
+    L.jdaDetect.argtypes = [vp, ub, ci, ci, cf, cf, ci, ci, cf]
+    L.jdaResultRelease.restype = None
+    L.jdaResultRelease.argtypes = [_Result]
+    L.jdaB200DetectBatch.restype = ci
+    L.jdaB200DetectBatch.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(_Result), C.POINTER(Stats)]
+    L.jdaB200SetDevice.restype = ci
+    L.jdaB200SetDevice.argtypes = [vp, ci]
+    L.jdaB200SetStream.restype = ci
+    L.jdaB200SetStream.argtypes = [vp, vp]
+    L.jdaB200ModelDims.restype = None
+    L.jdaB200ModelDims.argtypes = [vp, C.POINTER(ci)]
+    L.jdaB200LastError.restype = cp
+    L.jdaB200LastError.argtypes = []
+    L.jdaB200DeviceCount.restype = ci
+    L.jdaB200DeviceCount.argtypes = []
+    L.jdaB200Levels.restype = ci
+    L.jdaB200Levels.argtypes = [ci, ci, cf, ci, ci, C.POINTER(ci), ci]
+    L.jdaB200CountWindows.restype = C.c_longlong
+    L.jdaB200CountWindows.argtypes = [ci, ci, cf, ci, ci]
+    L.jdaB200Nms.restype = None
+    L.jdaB200Nms.argtypes = [ci, C.POINTER(ci), C.POINTER(cf), ub]
+    L.jdaB200Trace.restype = C.c_longlong
+    L.jdaB200Trace.argtypes = [vp, ub, ci, ci, cf, ci, ci, ci, ci, C.POINTER(ci), C.POINTER(cf), ub,
+                               C.c_longlong, C.c_longlong]
+    L.jdaB200Resize.restype = ci
+    L.jdaB200Resize.argtypes = [vp, ub, ci, ci, ub, ci, ci]
+    _lib = L
+    return L
+
+
+EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSerializeTo",
+           "jdaCascadorRelease", "jdaDetect", "jdaResultRelease", "jdaB200DetectBatch",
+           "jdaB200SetDevice", "jdaB200SetStream", "jdaB200ModelDims", "jdaB200LastError",
+           "jdaB200DeviceCount", "jdaB200Levels", "jdaB200CountWindows", "jdaB200Nms",
+           "jdaB200Trace", "jdaB200Resize"]
+
+
+def last_error():
+    return lib().jdaB200LastError().decode()
+
+
+def device_count():
+    return lib().jdaB200DeviceCount()
+
+
+def levels(w, h, scale=1.25, min_size=24, max_size=-1):
+    buf = (C.c_int * 64)()
+    n = lib().jdaB200Levels(w, h, scale, min_size, max_size, buf, 64)
+    return list(buf[:min(n, 64)])
+
+
+def count_windows(w, h, scale=1.25, min_size=24, max_size=-1):
+    return int(lib().jdaB200CountWindows(w, h, scale, min_size, max_size))
+
+
+def nms(boxes, scores):
+    boxes = np.ascontiguousarray(boxes, np.int32)
+    scores = np.ascontiguousarray(scores, np.float32)
+    keep = np.zeros(max(len(scores), 1), np.uint8)
+    lib().jdaB200Nms(len(scores), boxes.ctypes.data_as(C.POINTER(C.c_int)),
+                     scores.ctypes.data_as(C.POINTER(C.c_float)),
+                     keep.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return keep[:len(scores)].astype(bool)
+
+
+def _unpack(res, D=None):
+    L = lib()
+    n, lm = res.n, res.landmark_n
+    if n < 0:
+        raise RuntimeError("jda_b200 detect failed: " + last_error())
+    if n > 0:
+        out = (np.ctypeslib.as_array(res.bboxes, shape=(n, 3)).copy(),
+               np.ctypeslib.as_array(res.scores, shape=(n,)).copy(),
+               np.ctypeslib.as_array(res.shapes, shape=(n, 2 * lm)).copy())
+    else:
+        out = (np.zeros((0, 3), np.int32), np.zeros((0,), np.float32), np.zeros((0, 2 * lm), np.float32))
+    L.jdaResultRelease(res)
+    return out
+
+
+class Cascador:
+    """Handle on one loaded model (jdaCascador of c/jda.c:142-151 + its device copy)."""
+
+    def __init__(self, path, double=True, device=None):
+        L = lib()
+        f = L.jdaCascadorCreateDouble if double else L.jdaCascadorCreateFloat
+        self._h = f(os.fsencode(path))
+        if not self._h:
+            raise RuntimeError("cannot load model %r: %s" % (path, last_error()))
+        if device is not None:
+            if L.jdaB200SetDevice(self._h, int(device)) != 0:
+                raise RuntimeError(last_error())
+        d = (C.c_int * 4)()
+        L.jdaB200ModelDims(self._h, d)
+        self.T, self.K, self.L, self.depth = tuple(d)
+        self.last_stats = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jdaCascadorRelease(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def save_f32(self, path):
+        lib().jdaCascadorSerializeTo(self._h, os.fsencode(path))
+
+    def set_stream(self, cuda_stream_ptr):
+        lib().jdaB200SetStream(self._h, C.c_void_p(cuda_stream_ptr))
+
+    def detect(self, img, scale=1.25, step=0.1, min_size=24, max_size=-1, th=0.0):
+        """jdaDetect: (boxes[n,3] i32, scores[n] f32, shapes[n,2L] f32 in image pixels)."""
+        a = np.ascontiguousarray(img, np.uint8)
+        assert a.ndim == 2
+        res = lib().jdaDetect(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), a.shape[1], a.shape[0],
+                              scale, step, min_size, max_size, th)
+        return _unpack(res)
+
+    def detect_batch(self, frames, scale=1.25, min_size=24, max_size=-1, th=0.0, t_limit=0, flags=0,
+                     device_ptr=None, shape=None, pitch=None, frame_stride=None, unpack=True):
+        """frames: [n,h,w] u8 numpy array (host), or device_ptr + shape=(n,h,w) for frames resident
+        in HBM (any allocator: torch .data_ptr(), cudaMalloc ...).  Returns a list of
+        (boxes, scores, shapes) per frame, or just the detection count when unpack=False."""
+        L = lib()
+        if device_ptr is None:
+            a = np.ascontiguousarray(frames, np.uint8)
+            assert a.ndim == 3
+            n, h, w = a.shape
+            ptr = a.ctypes.data
+            pitch = w if pitch is None else pitch
+            frame_stride = pitch * h if frame_stride is None else frame_stride
+        else:
+            n, h, w = shape
+            ptr = int(device_ptr)
+            pitch = w if pitch is None else pitch
+            frame_stride = pitch * h if frame_stride is None else frame_stride
+            flags |= DEVICE_INPUT
+        b = Batch(n, w, h, pitch, frame_stride, scale, min_size, max_size, th, t_limit, flags)
+        res = (_Result * n)()
+        st = Stats()
+        rc = L.jdaB200DetectBatch(self._h, C.c_void_p(ptr), C.byref(b), res, C.byref(st))
+        self.last_stats = st.as_dict()
+        if rc != 0:
+            raise RuntimeError("jdaB200DetectBatch failed: " + last_error())
+        if unpack:
+            return [_unpack(res[i]) for i in range(n)]
+        tot = 0
+        for i in range(n):
+            tot += res[i].n
+            L.jdaResultRelease(res[i])
+        return tot
+
+    def trace(self, img, scale=1.25, min_size=24, max_size=-1, t_limit=0, flags=0, leaf_range=None):
+        """per-window (carts evaluated, exit score) in scan order + optional leaf indices."""
+        a = np.ascontiguousarray(img, np.uint8)
+        h, w = a.shape
+        nwin = count_windows(w, h, scale, min_size, max_size)
+        tn = np.zeros(max(nwin, 1), np.int32)
+        ts = np.zeros(max(nwin, 1), np.float32)
+        if leaf_range is not None:
+            w0, w1 = leaf_range
+            lv = np.full((max(w1 - w0, 1), self.T * self.K), 255, np.uint8)
+            lp = lv.ctypes.data_as(C.POINTER(C.c_ubyte))
+        else:
+            w0 = w1 = 0
+            lv, lp = None, None
+        n = lib().jdaB200Trace(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, scale, min_size,
+                               max_size, t_limit, flags, tn.ctypes.data_as(C.POINTER(C.c_int)),
+                               ts.ctypes.data_as(C.POINTER(C.c_float)), lp, w0, w1)
+        if n < 0:
+            raise RuntimeError("jdaB200Trace failed: " + last_error())
+        assert n == nwin, (n, nwin)
+        return tn[:nwin], ts[:nwin], lv
+
+    def resize(self, img, dw, dh):
+        a = np.ascontiguousarray(img, np.uint8)
+        out = np.empty((dh, dw), np.uint8)
+        rc = lib().jdaB200Resize(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), a.shape[1], a.shape[0],
+                                 out.ctypes.data_as(C.POINTER(C.c_ubyte)), dw, dh)
+        if rc != 0:
+            raise RuntimeError("jdaB200Resize failed: " + last_error())
+        return out

@@ -1,0 +1,751 @@
+// api.cu -- C ABI of libjda_b200.so (include/jda_b200.h): context, launches, post-processing.
+//
+// Call path of one detect (reference c/jda.c:443-480 -> here):
+//   frames (host: H2D into a 16-byte-pitched device store | device: used in place)
+//   [k1_resize  -> h/q planes, only if the model samples them]        c/jda.c:450-457
+//   k2_scan     -> stage-0 survivors (queue in HBM)                    c/jda.c:332-402, t = 0
+//   k3_cascade  -> raw hits (records in HBM)                           c/jda.c:356-427
+//   D2H of the hit records, sort into scan order, host NMS + relocation c/jda.c:237-316, 465-474
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/jda_b200.h"
+#include "host_model.hpp"
+#include "kernels.cuh"
+
+using namespace jda;
+
+namespace {
+
+thread_local std::string g_err;
+
+void set_err(const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  fprintf(stderr, "[jda_b200] error: %s\n", buf);
+}
+
+#define CU_OK(call)                                                                       \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return false;                                                                       \
+    }                                                                                     \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  bool ensure(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e != cudaSuccess) {
+      set_err("cudaMalloc(%zu) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+      return false;
+    }
+    cap = want;
+    return true;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Geometry {
+  int w = 0, h = 0, min_size = 0, max_size = 0;
+  float scale = 0.f;
+  int n_levels = 0;
+  LevelInfo lv[kMaxLevels];
+  long long windows_per_frame = 0;
+  int table_bytes = 0;  // per level, padded to 128
+  bool valid = false;
+};
+
+struct HitRec {
+  int frame;
+  uint32_t key;
+  int x, y, win;
+  float score;
+  const float *shape;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+struct Context {
+  HostModel m;
+  std::mutex mu;
+  int device = -1;
+  bool inited = false;
+  cudaStream_t own_stream = nullptr, user_stream = nullptr;
+  int sm_count = 148;
+  EncodeTiledFn encode = nullptr;
+  // device model
+  NodeRec *d_nodes = nullptr;
+  float *d_leaf = nullptr;
+  float4 *d_cart = nullptr;
+  float *d_w = nullptr;
+  float *d_mean = nullptr;
+  // geometry + stage-0 tables
+  Geometry geo;
+  DevBuf<uint8_t> d_tables;
+  Stage0Norm *d_norms = nullptr;
+  // scratch
+  DevBuf<uint8_t> d_frames, d_hq, d_trace_leaf;
+  DevBuf<uint2> d_surv;
+  DevBuf<float> d_hits;
+  DevBuf<int> d_trace_n;
+  DevBuf<float> d_trace_s;
+  unsigned *d_counters = nullptr;  // [kMaxLevels] tile counters, [kMaxLevels] surv_count, [+1] hit_count
+  unsigned *h_counters = nullptr;  // pinned mirror
+  std::vector<float> h_hits;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t surv_cap = 0, hit_cap = 0;
+  jdaB200Stats last;
+  int nw = 2;
+  std::vector<short> sched;
+  cudaStream_t stream() const { return user_stream ? user_stream : own_stream; }
+};
+
+constexpr int kCntSurv = kMaxLevels, kCntHit = kMaxLevels + 1, kCntTotal = kMaxLevels + 2;
+
+size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * sizeof(WarpScratch); }
+size_t k3_smem_bytes(int K) { return (size_t)K3_WARPS * (kMaxDim * 4 + ((K + 15) & ~15)); }
+
+bool ctx_init(Context *c) {
+  if (c->inited) {
+    CU_OK(cudaSetDevice(c->device));
+    return true;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("no CUDA device visible: libjda_b200 has no CPU path");
+    return false;
+  }
+  if (c->device < 0) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    c->device = cur;
+  }
+  CU_OK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10) {
+    set_err("device %d is sm_%d%d; this library is built for sm_100a only", c->device, prop.major, prop.minor);
+    return false;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  CU_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  for (auto &e : c->ev) CU_OK(cudaEventCreate(&e));
+  const HostModel &m = c->m;
+  CU_OK(cudaMalloc(&c->d_nodes, m.nodes.size() * sizeof(NodeRec)));
+  CU_OK(cudaMalloc(&c->d_leaf, m.leaf.size() * 4));
+  CU_OK(cudaMalloc(&c->d_cart, m.cart.size() * 4));
+  CU_OK(cudaMalloc(&c->d_w, m.w.size() * 4));
+  CU_OK(cudaMalloc(&c->d_mean, m.mean_shape.size() * 4));
+  CU_OK(cudaMalloc(&c->d_norms, kMaxNorm * sizeof(Stage0Norm)));
+  CU_OK(cudaMemcpy(c->d_nodes, m.nodes.data(), m.nodes.size() * sizeof(NodeRec), cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(c->d_leaf, m.leaf.data(), m.leaf.size() * 4, cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(c->d_cart, m.cart.data(), m.cart.size() * 4, cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(c->d_w, m.w.data(), m.w.size() * 4, cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(c->d_mean, m.mean_shape.data(), m.mean_shape.size() * 4, cudaMemcpyHostToDevice));
+  CU_OK(cudaMalloc(&c->d_counters, kCntTotal * sizeof(unsigned)));
+  CU_OK(cudaMallocHost(&c->h_counters, kCntTotal * sizeof(unsigned)));
+  {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      c->encode = (EncodeTiledFn)fn;
+  }
+  const size_t s2 = k2_smem_bytes((c->m.K * kCartBytes + 127) & ~127);
+  CU_OK(cudaFuncSetAttribute(k2_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  CU_OK(cudaFuncSetAttribute(k2_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  CU_OK(cudaFuncSetAttribute(k2_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  CU_OK(cudaFuncSetAttribute(k2_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  CU_OK(cudaFuncSetAttribute(k2_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  const size_t s3 = k3_smem_bytes(c->m.K);
+  CU_OK(cudaFuncSetAttribute(k3_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
+  CU_OK(cudaFuncSetAttribute(k3_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
+  // tuning knobs (not behaviour): windows per lane and the phase schedule of k2_scan
+  if (const char *e = getenv("JDA_B200_NW")) {
+    int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) c->nw = v;
+  }
+  c->sched.clear();
+  if (const char *e = getenv("JDA_B200_SCHED")) {
+    const char *p = e;
+    while (*p) {
+      int v = (int)strtol(p, (char **)&p, 10);
+      if (v > 0 && v < m.K && (c->sched.empty() || v > c->sched.back()) && c->sched.size() < K2_MAX_SCHED - 1)
+        c->sched.push_back((short)v);
+      while (*p == ',' || *p == ' ') p++;
+    }
+  } else {
+    const int def[] = {4, 8, 12, 16, 24, 32, 48, 64, 96, 128, 160, 192, 256, 320, 384, 448};
+    for (int v : def)
+      if (v < m.K) c->sched.push_back((short)v);
+  }
+  c->sched.push_back((short)m.K);
+  c->inited = true;
+  return true;
+}
+
+void ctx_free(Context *c) {
+  if (c->inited) {
+    cudaSetDevice(c->device);
+    cudaFree(c->d_nodes); cudaFree(c->d_leaf); cudaFree(c->d_cart); cudaFree(c->d_w); cudaFree(c->d_mean);
+    cudaFree(c->d_norms); cudaFree(c->d_counters);
+    cudaFreeHost(c->h_counters);
+    c->d_tables.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
+    c->d_surv.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  }
+  delete c;
+}
+
+// Per-level tile shapes.  A level runs from private shared-memory tiles when a tile of at least
+// 64 windows (with its 16-byte-padded pixel box) fits the per-warp scratch; otherwise its windows
+// read pixels from global memory in "virtual" tiles of 32 x 16 windows.
+void plan_level(LevelInfo &L) {
+  int best_windows = 0;
+  for (int tl = 5; tl >= 3; tl--) {
+    const int tw = 1 << tl;
+    const int bw = (((tw - 1) * L.step + L.win) + 15) & ~15;
+    if (bw > 256) continue;
+    const int bh_max = std::min(256, K2_TILE_BYTES / bw);
+    if (bh_max < L.win) continue;
+    int th = (bh_max - L.win) / L.step + 1;
+    th = std::min(th, K2_LIST_CAP / tw);
+    th = std::min(th, std::max(1, L.ny));
+    const int bh = (th - 1) * L.step + L.win;
+    if ((long long)L.win * bw + L.win >= 65536) continue;  // u16 tile offsets
+    const int windows = std::min(tw, L.nx) * th;
+    if (windows > best_windows) {
+      best_windows = windows;
+      L.tw_log2 = tl; L.th = th; L.box_w = bw; L.box_h = bh;
+    }
+  }
+  if (best_windows >= 64) {
+    L.use_smem = 1;
+  } else {
+    L.use_smem = 0;
+    L.tw_log2 = 5; L.th = K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0;
+  }
+  const int tw = 1 << L.tw_log2;
+  L.ntx = (L.nx + tw - 1) / tw;
+  L.nty = (L.ny + L.th - 1) / L.th;
+}
+
+bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int max_size, bool force_global) {
+  Geometry &g = c->geo;
+  if (g.valid && g.w == w && g.h == h && g.scale == scale && g.min_size == min_size && g.max_size == max_size)
+    return true;
+  g.valid = false;
+  g.w = w; g.h = h; g.scale = scale; g.min_size = min_size; g.max_size = max_size;
+  int wins[kMaxLevels + 1];
+  int n = (w < 24 || h < 24) ? 0 : enumerate_levels(w, h, scale, min_size, max_size, wins, kMaxLevels + 1);
+  if (n > kMaxLevels) {
+    set_err("more than %d pyramid levels (scale too close to 1)", kMaxLevels);
+    return false;
+  }
+  g.n_levels = n;
+  g.table_bytes = (c->m.K * kCartBytes + 127) & ~127;
+  long long base = 0;
+  for (int i = 0; i < n; i++) {
+    LevelInfo &L = g.lv[i];
+    memset(&L, 0, sizeof L);
+    L.win = wins[i];
+    L.step = level_step(L.win);
+    if (L.win >= 2048) { set_err("windows of %d px exceed the 2047 px limit", L.win); return false; }
+    L.nx = (w - L.win) / L.step + 1;
+    L.ny = (h - L.win) / L.step + 1;
+    if (L.nx > 8191 || L.ny > 8191) { set_err("frame too large for 13-bit window indices"); return false; }
+    plan_level(L);
+    L.table_off = i * g.table_bytes;
+    L.win_base = base;
+    base += (long long)L.nx * L.ny;
+  }
+  g.windows_per_frame = base;
+  (void)force_global;
+  if (n > 0 && c->m.stage0_lut_ok) {
+    std::vector<uint8_t> tab((size_t)n * g.table_bytes, 0);
+    Stage0Norm norms[kMaxNorm];
+    memset(norms, 0, sizeof norms);
+    for (int i = 0; i < n; i++)
+      build_stage0_table(c->m, g.lv[i].win, g.lv[i].use_smem ? g.lv[i].box_w : 0,
+                         tab.data() + (size_t)i * g.table_bytes, norms);
+    if (!c->d_tables.ensure(tab.size())) return false;
+    CU_OK(cudaMemcpyAsync(c->d_tables.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, c->stream()));
+    CU_OK(cudaMemcpyAsync(c->d_norms, norms, sizeof norms, cudaMemcpyHostToDevice, c->stream()));
+    CU_OK(cudaStreamSynchronize(c->stream()));
+  }
+  g.valid = true;
+  return true;
+}
+
+struct TraceOut {
+  int *n = nullptr;
+  float *s = nullptr;
+  uint8_t *leaf = nullptr;
+  long long w0 = 0, w1 = 0;
+};
+
+// Runs the device path for one batch; on success `hits` holds the raw hit records sorted into scan
+// order (frame, level, y, x).  `store` keeps the record floats alive.
+bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, std::vector<HitRec> &hits,
+                const TraceOut *trace) {
+  hits.clear();
+  jdaB200Stats &st = c->last;
+  memset(&st, 0, sizeof st);
+  if (b.n_frames <= 0) return true;
+  if (b.width <= 0 || b.height <= 0 || b.pitch < b.width || b.frame_stride < (size_t)b.pitch * (b.height - 1) + b.width) {
+    set_err("bad batch descriptor");
+    return false;
+  }
+  if (!ctx_init(c)) return false;
+  const bool force_global = false;
+  if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, force_global)) return false;
+  const Geometry &g = c->geo;
+  st.n_levels = g.n_levels;
+  st.windows = g.windows_per_frame * b.n_frames;
+  if (g.n_levels == 0) return true;
+  const HostModel &m = c->m;
+  cudaStream_t s = c->stream();
+  const int D = m.D();
+  const int rec_words = kHitHeader + D;
+  const int t_run = (b.t_limit > 0 && b.t_limit < m.T) ? b.t_limit : m.T;
+
+  CU_OK(cudaEventRecord(c->ev[0], s));
+  // ---- frames
+  const uint8_t *d_frames;
+  int pitch;
+  size_t fstride;
+  if (b.flags & JDA_B200_DEVICE_INPUT) {
+    d_frames = frames; pitch = b.pitch; fstride = b.frame_stride;
+  } else {
+    pitch = (b.width + 15) & ~15;
+    fstride = (size_t)pitch * b.height;
+    if (!c->d_frames.ensure(fstride * b.n_frames + 256)) return false;
+    if (b.frame_stride == (size_t)b.pitch * b.height) {
+      CU_OK(cudaMemcpy2DAsync(c->d_frames.p, pitch, frames, b.pitch, b.width, (size_t)b.height * b.n_frames,
+                              cudaMemcpyHostToDevice, s));
+    } else {
+      for (int f = 0; f < b.n_frames; f++)
+        CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * fstride, pitch, frames + f * b.frame_stride, b.pitch,
+                                b.width, b.height, cudaMemcpyHostToDevice, s));
+    }
+    d_frames = c->d_frames.p;
+  }
+  CU_OK(cudaEventRecord(c->ev[1], s));
+
+  // ---- h / q planes (c/jda.c:450-457), only when some node samples them
+  const float r = 1.f / sqrtf(2.f);
+  const int hw = (int)(b.width * r), hh = (int)(b.height * r), qw = b.width / 2, qh = b.height / 2;
+  const size_t hq_stride = (size_t)hw * hh + (size_t)qw * qh;
+  if (m.any_scaled) {
+    if (!c->d_hq.ensure(hq_stride * b.n_frames)) return false;
+    const int big = std::max(hw * hh, qw * qh);
+    for (int f0 = 0; f0 < b.n_frames; f0 += 32768) {  // gridDim.z limit
+      dim3 grid((big + 255) / 256, 2, std::min(32768, b.n_frames - f0));
+      k1_resize<<<grid, 256, 0, s>>>(d_frames + (size_t)f0 * fstride, fstride, pitch, b.width, b.height,
+                                     c->d_hq.p + (size_t)f0 * hq_stride, hq_stride, hw, hh, qw, qh);
+      CU_OK(cudaGetLastError());
+    }
+    st.resize_launches = 1;
+  }
+
+  // ---- trace buffers
+  const bool tracing = trace != nullptr;
+  const long long total_windows = st.windows;
+  int leaf_stride = m.T * m.K;
+  if (tracing) {
+    if (!c->d_trace_n.ensure(total_windows) || !c->d_trace_s.ensure(total_windows)) return false;
+    CU_OK(cudaMemsetAsync(c->d_trace_n.p, 0, total_windows * 4, s));
+    CU_OK(cudaMemsetAsync(c->d_trace_s.p, 0, total_windows * 4, s));
+    if (trace->leaf && trace->w1 > trace->w0) {
+      const size_t nb = (size_t)(trace->w1 - trace->w0) * leaf_stride;
+      if (!c->d_trace_leaf.ensure(nb)) return false;
+      CU_OK(cudaMemsetAsync(c->d_trace_leaf.p, 255, nb, s));
+    }
+  }
+
+  const bool use_scan = m.stage0_lut_ok && !(b.flags & JDA_B200_NO_STAGE0_SCAN);
+  if (c->surv_cap == 0) c->surv_cap = 1 << 16;
+  if (c->hit_cap == 0) c->hit_cap = 1 << 14;
+  c->surv_cap = std::max(c->surv_cap, (size_t)b.n_frames * 1024);
+  c->hit_cap = std::max(c->hit_cap, (size_t)b.n_frames * 128);
+
+  for (int attempt = 0; attempt < 4; attempt++) {
+    if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * rec_words)) return false;
+    CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
+    CU_OK(cudaEventRecord(c->ev[2], s));
+    if (use_scan) {
+      ScanParams P;
+      memset(&P, 0, sizeof P);
+      for (int i = 0; i < g.n_levels; i++) P.lv[i] = g.lv[i];
+      P.frames = d_frames; P.frame_stride = fstride; P.pitch = pitch; P.W = b.width; P.H = b.height;
+      P.n_frames = b.n_frames; P.n_levels = g.n_levels; P.K = m.K; P.table_bytes = g.table_bytes;
+      P.tables = c->d_tables.p; P.norms = c->d_norms; P.tile_counters = c->d_counters;
+      P.surv = c->d_surv.p; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)c->surv_cap;
+      P.windows_per_frame = g.windows_per_frame;
+      P.n_sched = (int)c->sched.size();
+      for (int i = 0; i < P.n_sched; i++) P.sched[i] = c->sched[i];
+      // TMA needs 16-byte aligned base and strides
+      bool tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)d_frames % 16 == 0) &&
+                    pitch % 16 == 0 && fstride % 16 == 0;
+      int n_smem = 0;
+      for (int i = 0; i < g.n_levels && tma_ok; i++) {
+        if (!g.lv[i].use_smem) continue;
+        cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)b.n_frames};
+        cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
+        cuuint32_t box[3] = {(cuuint32_t)g.lv[i].box_w, (cuuint32_t)g.lv[i].box_h, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult cr = c->encode(&P.maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_frames, dims, strides, box,
+                                es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+          set_err("cuTensorMapEncodeTiled failed (%d) for level %d box %dx%d", (int)cr, i, g.lv[i].box_w, g.lv[i].box_h);
+          return false;
+        }
+      }
+      for (int i = 0; i < g.n_levels; i++) n_smem += g.lv[i].use_smem;
+      st.levels_smem = n_smem;
+      P.use_tma = tma_ok ? 1 : 0;
+      if (tracing) {
+        P.trace_n = c->d_trace_n.p; P.trace_s = c->d_trace_s.p;
+        P.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;
+        P.leaf_w0 = trace->w0; P.leaf_w1 = trace->w1; P.leaf_stride = leaf_stride;
+      }
+      const size_t smem = k2_smem_bytes(g.table_bytes);
+      const int grid = c->sm_count;
+      if (tracing) {
+        if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
+        else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
+      } else if (c->nw == 1) {
+        k2_scan<1, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
+      } else if (c->nw == 4) {
+        k2_scan<4, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
+      } else {
+        k2_scan<2, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
+      }
+      CU_OK(cudaGetLastError());
+      st.scan_launches++;
+    }
+    CU_OK(cudaEventRecord(c->ev[3], s));
+    {
+      CascadeParams Q;
+      memset(&Q, 0, sizeof Q);
+      Q.frames = d_frames; Q.frame_stride = fstride; Q.pitch = pitch; Q.W = b.width; Q.H = b.height;
+      Q.hq = m.any_scaled ? c->d_hq.p : nullptr; Q.hq_stride = hq_stride; Q.hw = hw; Q.hh = hh; Q.qw = qw; Q.qh = qh;
+      Q.nodes = c->d_nodes; Q.leaf = c->d_leaf; Q.cart = c->d_cart; Q.w = c->d_w; Q.mean_shape = c->d_mean;
+      Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.t_run = t_run; Q.r = r;
+      Q.n_levels = g.n_levels;
+      for (int i = 0; i < g.n_levels; i++) {
+        Q.lv_win[i] = g.lv[i].win; Q.lv_step[i] = g.lv[i].step; Q.lv_nx[i] = g.lv[i].nx; Q.lv_ny[i] = g.lv[i].ny;
+        Q.lv_base[i] = g.lv[i].win_base;
+      }
+      Q.windows_per_frame = g.windows_per_frame;
+      Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
+      Q.dense = use_scan ? 0 : 1; Q.dense_total = total_windows;
+      Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
+      Q.rec_words = rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
+      if (tracing) {
+        Q.trace_n = c->d_trace_n.p; Q.trace_s = c->d_trace_s.p;
+        Q.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;
+        Q.leaf_w0 = trace->w0; Q.leaf_w1 = trace->w1; Q.leaf_stride = leaf_stride;
+      }
+      const int grid = c->sm_count * 8;
+      const size_t smem = k3_smem_bytes(m.K);
+      if (tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, s>>>(Q);
+      else k3_cascade<false><<<grid, K3_WARPS * 32, smem, s>>>(Q);
+      CU_OK(cudaGetLastError());
+      st.cascade_launches++;
+    }
+    CU_OK(cudaEventRecord(c->ev[4], s));
+    CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaStreamSynchronize(s));
+    const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
+    if (ns > c->surv_cap || nh > c->hit_cap) {  // queues overflowed: grow and run again
+      if (ns > c->surv_cap) c->surv_cap = ns + ns / 4;
+      if (nh > c->hit_cap) c->hit_cap = nh + nh / 4;
+      continue;
+    }
+    st.stage0_survivors = use_scan ? (long long)ns : 0;
+    st.raw_hits = (long long)nh;
+    c->h_hits.resize(nh * rec_words);
+    if (nh) CU_OK(cudaMemcpyAsync(c->h_hits.data(), c->d_hits.p, nh * rec_words * 4, cudaMemcpyDeviceToHost, s));
+    if (tracing) {
+      if (trace->n) CU_OK(cudaMemcpyAsync(trace->n, c->d_trace_n.p, total_windows * 4, cudaMemcpyDeviceToHost, s));
+      if (trace->s) CU_OK(cudaMemcpyAsync(trace->s, c->d_trace_s.p, total_windows * 4, cudaMemcpyDeviceToHost, s));
+      if (trace->leaf && trace->w1 > trace->w0)
+        CU_OK(cudaMemcpyAsync(trace->leaf, c->d_trace_leaf.p, (size_t)(trace->w1 - trace->w0) * leaf_stride,
+                              cudaMemcpyDeviceToHost, s));
+    }
+    CU_OK(cudaEventRecord(c->ev[5], s));
+    CU_OK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&st.ms_h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&st.ms_resize, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&st.ms_d2h, c->ev[4], c->ev[5]);
+    hits.resize(nh);
+    for (size_t i = 0; i < nh; i++) {
+      const float *rec = c->h_hits.data() + i * rec_words;
+      const int *ri = reinterpret_cast<const int *>(rec);
+      hits[i] = HitRec{ri[0], (uint32_t)ri[1], ri[2], ri[3], ri[4], rec[5], rec + kHitHeader};
+    }
+    std::sort(hits.begin(), hits.end(), [](const HitRec &a, const HitRec &b2) {
+      return a.frame != b2.frame ? a.frame < b2.frame : a.key < b2.key;
+    });
+    return true;
+  }
+  set_err("survivor / hit queues kept overflowing");
+  return false;
+}
+
+jdaResult empty_result(int L, int n) {
+  jdaResult r;
+  r.n = n; r.landmark_n = L; r.bboxes = nullptr; r.shapes = nullptr; r.scores = nullptr;
+  return r;
+}
+
+// hits of one frame (scan order) -> jdaResult, c/jda.c:463-474
+jdaResult finish_frame(const HostModel &m, const HitRec *h, int n, bool raw) {
+  const int D = m.D();
+  jdaResult r = empty_result(m.L, 0);
+  // like the reference, the arrays exist even when n == 0
+  r.bboxes = (int *)malloc(sizeof(int) * 3 * (n > 0 ? n : 1));
+  r.scores = (float *)malloc(sizeof(float) * (n > 0 ? n : 1));
+  r.shapes = (float *)malloc(sizeof(float) * D * (n > 0 ? n : 1));
+  if (!r.bboxes || !r.scores || !r.shapes) {
+    free(r.bboxes); free(r.scores); free(r.shapes);
+    return empty_result(m.L, -1);
+  }
+  std::vector<int> box(3 * (size_t)n);
+  std::vector<float> sc(n);
+  for (int i = 0; i < n; i++) {
+    box[3 * i] = h[i].x; box[3 * i + 1] = h[i].y; box[3 * i + 2] = h[i].win;
+    sc[i] = h[i].score;
+  }
+  std::vector<uint8_t> keep(n > 0 ? n : 1, 1);
+  if (!raw) nms(n, box.data(), sc.data(), keep.data());
+  int o = 0;
+  for (int i = 0; i < n; i++) {
+    if (!keep[i]) continue;
+    r.bboxes[3 * o] = h[i].x; r.bboxes[3 * o + 1] = h[i].y; r.bboxes[3 * o + 2] = h[i].win;
+    r.scores[o] = h[i].score;
+    if (raw) memcpy(r.shapes + (size_t)o * D, h[i].shape, sizeof(float) * D);
+    else relocate(h[i].shape, r.shapes + (size_t)o * D, m.L, h[i].x, h[i].y, h[i].win);
+    o++;
+  }
+  r.n = o;
+  return r;
+}
+
+int detect_batch(Context *c, const unsigned char *frames, const jdaB200Batch &b, jdaResult *results,
+                 jdaB200Stats *stats) {
+  std::lock_guard<std::mutex> lock(c->mu);
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  std::vector<HitRec> hits;
+  const bool ok = run_device(c, frames, b, hits, nullptr);
+  if (!ok) {
+    for (int f = 0; f < b.n_frames; f++) results[f] = empty_result(c->m.L, -1);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return -1;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  const bool raw = (b.flags & JDA_B200_RAW_HITS) != 0;
+  size_t i = 0;
+  long long dets = 0;
+  for (int f = 0; f < b.n_frames; f++) {
+    size_t j = i;
+    while (j < hits.size() && hits[j].frame == f) j++;
+    results[f] = finish_frame(c->m, hits.data() + i, (int)(j - i), raw);
+    dets += results[f].n > 0 ? results[f].n : 0;
+    i = j;
+  }
+  c->last.detections = dets;
+  c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = c->last;
+  if (prev_dev >= 0) cudaSetDevice(prev_dev);
+  return 0;
+}
+
+void *create(const char *path, bool dbl) {
+  if (!path) return nullptr;
+  Context *c = new Context();
+  std::string err;
+  if (!load_model(path, dbl, c->m, err)) {
+    g_err = err;
+    delete c;
+    return nullptr;
+  }
+  memset(&c->last, 0, sizeof c->last);
+  return c;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+
+extern "C" {
+
+void *jdaCascadorCreateDouble(const char *model) { return create(model, true); }
+void *jdaCascadorCreateFloat(const char *model) { return create(model, false); }
+
+void jdaCascadorSerializeTo(void *cascador, const char *model) {
+  if (!cascador || !model) return;
+  save_model_f32(static_cast<Context *>(cascador)->m, model);
+}
+
+void jdaCascadorRelease(void *cascador) {
+  if (cascador) ctx_free(static_cast<Context *>(cascador));
+}
+
+jdaResult jdaDetect(void *cascador, unsigned char *data, int width, int height, float scale, float step,
+                    int min_size, int max_size, float th) {
+  (void)step;  // ignored by the reference as well (c/jda.c:333)
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !data) return empty_result(c ? c->m.L : 0, -1);
+  jdaB200Batch b;
+  memset(&b, 0, sizeof b);
+  b.n_frames = 1; b.width = width; b.height = height; b.pitch = width;
+  b.frame_stride = (size_t)width * height;
+  b.scale = scale; b.min_size = min_size; b.max_size = max_size; b.th = th;
+  jdaResult r = empty_result(c->m.L, -1);
+  if (width <= 0 || height <= 0) return finish_frame(c->m, nullptr, 0, false);
+  detect_batch(c, data, b, &r, nullptr);
+  return r;
+}
+
+void jdaResultRelease(jdaResult result) {
+  free(result.bboxes);
+  free(result.shapes);
+  free(result.scores);
+}
+
+int jdaB200DetectBatch(void *cascador, const unsigned char *frames, const jdaB200Batch *batch, jdaResult *results,
+                       jdaB200Stats *stats) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !batch || !results || (!frames && batch->n_frames > 0)) {
+    set_err("null argument");
+    return -2;
+  }
+  return detect_batch(c, frames, *batch, results, stats);
+}
+
+int jdaB200SetDevice(void *cascador, int device) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c) return -2;
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (c->inited && c->device != device) {
+    set_err("device already bound to %d", c->device);
+    return -1;
+  }
+  c->device = device;
+  return 0;
+}
+
+int jdaB200SetStream(void *cascador, void *cuda_stream) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c) return -2;
+  std::lock_guard<std::mutex> lock(c->mu);
+  c->user_stream = static_cast<cudaStream_t>(cuda_stream);
+  return 0;
+}
+
+void jdaB200ModelDims(void *cascador, int *out4) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !out4) return;
+  out4[0] = c->m.T; out4[1] = c->m.K; out4[2] = c->m.L; out4[3] = kDepth;
+}
+
+const char *jdaB200LastError(void) { return g_err.c_str(); }
+
+int jdaB200DeviceCount(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int jdaB200Levels(int width, int height, float scale, int min_size, int max_size, int *wins, int cap) {
+  if (width < 24 || height < 24) return 0;
+  return enumerate_levels(width, height, scale, min_size, max_size, wins, cap);
+}
+
+long long jdaB200CountWindows(int width, int height, float scale, int min_size, int max_size) {
+  return count_windows(width, height, scale, min_size, max_size);
+}
+
+void jdaB200Nms(int n, const int *bboxes, const float *scores, unsigned char *keep) {
+  nms(n, bboxes, scores, keep);
+}
+
+long long jdaB200Trace(void *cascador, const unsigned char *frame, int width, int height, float scale,
+                       int min_size, int max_size, int t_limit, int flags, int *carts_evaluated,
+                       float *exit_score, unsigned char *leaves, long long leaf_w0, long long leaf_w1) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !frame) return -2;
+  std::lock_guard<std::mutex> lock(c->mu);
+  jdaB200Batch b;
+  memset(&b, 0, sizeof b);
+  b.n_frames = 1; b.width = width; b.height = height; b.pitch = width;
+  b.frame_stride = (size_t)width * height;
+  b.scale = scale; b.min_size = min_size; b.max_size = max_size; b.th = 0.f; b.t_limit = t_limit;
+  b.flags = (flags & ~JDA_B200_DEVICE_INPUT) | JDA_B200_NO_FINAL_TH;
+  TraceOut t;
+  t.n = carts_evaluated; t.s = exit_score; t.leaf = leaves; t.w0 = leaf_w0; t.w1 = leaf_w1;
+  std::vector<HitRec> hits;
+  if (!run_device(c, frame, b, hits, &t)) return -1;
+  return c->last.windows;
+}
+
+int jdaB200Resize(void *cascador, const unsigned char *src, int sw, int sh, unsigned char *dst, int dw, int dh) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !src || !dst || sw < 2 || sh < 2 || dw <= 0 || dh <= 0) return -2;
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (!ctx_init(c)) return -1;
+  // k1 produces both planes; ask for the same size twice and read the first
+  DevBuf<uint8_t> in, out;
+  if (!in.ensure((size_t)sw * sh + 16) || !out.ensure((size_t)2 * dw * dh)) return -1;
+  cudaStream_t s = c->stream();
+  bool ok = cudaMemcpyAsync(in.p, src, (size_t)sw * sh, cudaMemcpyHostToDevice, s) == cudaSuccess;
+  dim3 grid((dw * dh + 255) / 256, 1, 1);
+  k1_resize<<<grid, 256, 0, s>>>(in.p, 0, sw, sw, sh, out.p, 0, dw, dh, dw, dh);
+  ok = ok && cudaGetLastError() == cudaSuccess;
+  ok = ok && cudaMemcpyAsync(dst, out.p, (size_t)dw * dh, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+  in.release();
+  out.release();
+  if (!ok) set_err("resize failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return ok ? 0 : -1;
+}
+
+}  // extern "C"

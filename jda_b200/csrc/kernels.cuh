@@ -1,0 +1,571 @@
+// kernels.cuh -- sm_100a kernels of the JDA detect path.
+//
+//   k1_resize    bilinear down-sample to the h (1/sqrt2) and q (1/2) planes     c/jda.c:203-230
+//   k2_scan      stage-0 scan of every candidate window from integer LUTs       c/jda.c:332-402 (t = 0)
+//   k3_cascade   generic per-window cascade + regression gather + emit          c/jda.c:356-427
+//
+// Arithmetic contract: every float expression the reference evaluates is
+// evaluated here with the same operations in the same order, round-to-nearest, no FMA
+// contraction (explicit __fadd_rn/__fmul_rn/__fsub_rn/__fdiv_rn and -fmad=false), float->int by
+// truncation.  Tree traversal and leaf indices are integer-exact; scores and shapes come out
+// bit-identical to the reference's C path.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "host_model.hpp"
+
+namespace jda {
+
+// ------------------------------------------------------------------------------ parameters
+
+struct LevelInfo {
+  int win, step;
+  int nx, ny;           // windows per row / column at this level
+  int tw_log2, th;      // windows per tile: (1 << tw_log2) x th
+  int ntx, nty;         // tiles per frame
+  int box_w, box_h;     // shared-memory tile in pixels (box_w is the tile pitch); global path: 0
+  int use_smem;
+  int table_off;        // byte offset of this level's stage-0 table
+  long long win_base;   // scan-order index of the level's first window inside a frame
+};
+
+constexpr int K2_WARPS = 12;         // warps per scan block (one block per SM)
+constexpr int K2_TILE_BYTES = 8192;  // per-warp pixel tile
+constexpr int K2_LIST_CAP = 512;     // windows per tile (fits u16 ids)
+constexpr int K2_MAX_SCHED = 32;
+
+struct __align__(128) WarpScratch {
+  uint8_t tile[K2_TILE_BYTES];
+  float lscore[K2_LIST_CAP];
+  uint16_t lwid[K2_LIST_CAP];
+  unsigned long long mbar;
+  unsigned char pad[120];
+};
+static_assert(sizeof(WarpScratch) % 128 == 0, "WarpScratch must keep 128-byte alignment");
+
+struct ScanParams {
+  CUtensorMap maps[kMaxLevels];  // one 3-D u8 map per level (box = that level's tile)
+  LevelInfo lv[kMaxLevels];
+  const uint8_t *frames;
+  size_t frame_stride;
+  int pitch, W, H, n_frames;
+  int n_levels, K, table_bytes;
+  const uint8_t *tables;         // n_levels x table_bytes (padded to 128)
+  const Stage0Norm *norms;       // kMaxNorm entries
+  unsigned *tile_counters;       // [n_levels] work-stealing counters
+  uint2 *surv;                   // stage-0 survivors: {frame, level<<26 | yi<<13 | xi}
+  unsigned *surv_count;
+  unsigned surv_cap;
+  long long windows_per_frame;
+  int n_sched;
+  short sched[K2_MAX_SCHED];     // cart index at which each phase ends; last == K
+  int use_tma;
+  // trace (TRACE instantiation only)
+  int *trace_n;
+  float *trace_s;
+  uint8_t *trace_leaf;
+  long long leaf_w0, leaf_w1;
+  int leaf_stride;
+};
+
+struct CascadeParams {
+  const uint8_t *frames;
+  size_t frame_stride;
+  int pitch, W, H;
+  const uint8_t *hq;  // per frame: h plane (hw*hh) then q plane (qw*qh); NULL when no node needs them
+  size_t hq_stride;
+  int hw, hh, qw, qh;
+  const NodeRec *nodes;
+  const float *leaf;
+  const float4 *cart;  // th, mean, std, -
+  const float *w;
+  const float *mean_shape;
+  int T, K, L, t_run;
+  float r;             // 1.f / sqrtf(2.f), computed on the host like c/jda.c:341
+  int n_levels;
+  int lv_win[kMaxLevels], lv_step[kMaxLevels], lv_nx[kMaxLevels], lv_ny[kMaxLevels];
+  long long lv_base[kMaxLevels];
+  long long windows_per_frame;
+  const uint2 *surv;
+  const unsigned *surv_count;
+  unsigned surv_cap;
+  int dense;           // 1: enumerate every window of every frame instead of reading `surv`
+  long long dense_total;
+  float *hits;         // records of rec_words 4-byte words
+  unsigned *hit_count;
+  unsigned hit_cap;
+  int rec_words;
+  float th;
+  int use_th;
+  int *trace_n;
+  float *trace_s;
+  uint8_t *trace_leaf;
+  long long leaf_w0, leaf_w1;
+  int leaf_stride;
+};
+
+constexpr int kHitHeader = 6;  // frame, key, x, y, win, score  -- then 2L shape floats
+
+__host__ __device__ inline uint32_t pack_key(int level, int yi, int xi) {
+  return ((uint32_t)level << 26) | ((uint32_t)yi << 13) | (uint32_t)xi;
+}
+
+#ifdef __CUDACC__
+
+// ------------------------------------------------------------------------------ PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a tile load that never lands (bad descriptor) traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 22)) __trap();
+}
+// 3-D tiled TMA load (x, y, frame) -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int x, int y, int z,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------ k1: resize
+
+// One thread per output pixel; blockIdx.z = frame, blockIdx.y selects the h (0) or q (1) plane.
+// Expression order of c/jda.c:214-226.
+__global__ void k1_resize(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int W, int H,
+                          uint8_t *__restrict__ hq, size_t hq_stride, int hw, int hh, int qw, int qh) {
+  const int plane = blockIdx.y;
+  const int dw = plane ? qw : hw, dh = plane ? qh : hh;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= dw * dh) return;
+  const uint8_t *src = frames + (size_t)blockIdx.z * frame_stride;
+  uint8_t *dst = hq + (size_t)blockIdx.z * hq_stride + (plane ? (size_t)hw * hh : 0);
+  const int i = o / dw, j = o - i * dw;
+  const float xr = __fdiv_rn((float)(W - 1), (float)dw);
+  const float yr = __fdiv_rn((float)(H - 1), (float)dh);
+  const float fx = __fmul_rn(xr, (float)j), fy = __fmul_rn(yr, (float)i);
+  const int x = __float2int_rz(fx), y = __float2int_rz(fy);
+  const float xd = __fsub_rn(fx, (float)x), yd = __fsub_rn(fy, (float)y);
+  const uint8_t *p = src + (size_t)y * pitch + x;
+  const float a = (float)p[0], b = (float)p[1], c = (float)p[pitch], d = (float)p[pitch + 1];
+  const float ix = __fsub_rn(1.f, xd), iy = __fsub_rn(1.f, yd);
+  float v = __fmul_rn(__fmul_rn(a, ix), iy);
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(b, xd), iy));
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(c, ix), yd));
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(d, xd), yd));
+  dst[o] = (uint8_t)__float2int_rz(v);
+}
+
+// ------------------------------------------------------------------------------ k2: stage-0 scan
+//
+// One persistent block per SM.  The block keeps the current level's stage-0 table (K x 96 B) in
+// shared memory; its warps are independent workers that pull tiles of that level from a global
+// counter.  A warp owns a private pixel tile (TMA-filled, box chosen per level so that tile +
+// window list fit its scratch) and walks the carts in phases: inside a phase all lanes evaluate
+// the same cart (uniform table reads), dead lanes are squeezed out between phases by
+// __ballot_sync compaction into an in-place (window id, score) list.  Windows that survive all K
+// carts are appended to the global survivor queue for k3_cascade.
+//
+// Levels whose windows are too large for a private tile read pixels straight from global memory
+// (L1/L2) with the packed-coordinate table format; everything else is identical.
+
+template <bool SMEM>
+struct PixBase;
+template <>
+struct PixBase<true> {
+  uint32_t off;  // byte offset into the block's shared memory
+};
+template <>
+struct PixBase<false> {
+  const uint8_t *ptr;
+};
+
+template <bool SMEM>
+__device__ __forceinline__ int node_test(const uint8_t *smem, uint2 n, const PixBase<SMEM> &b, int pitch) {
+  if constexpr (SMEM) {
+    const int p1 = smem[b.off + (n.x & 0xffffu)];
+    const int p2 = smem[b.off + (n.x >> 16)];
+    return (p1 - p2 <= (int)n.y) ? 1 : 2;
+  } else {
+    const int x1 = n.x & 0x7ff, y1 = (n.x >> 11) & 0x7ff, th = (int)(n.x >> 22) - 256;
+    const int x2 = n.y & 0x7ff, y2 = n.y >> 11;
+    const int p1 = __ldg(b.ptr + y1 * pitch + x1);
+    const int p2 = __ldg(b.ptr + y2 * pitch + x2);
+    return (p1 - p2 <= th) ? 1 : 2;
+  }
+}
+
+template <bool SMEM, int NW, bool TRACE>
+__device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &lv, int li, uint8_t *smem,
+                                          uint32_t norm_off, uint32_t tile_off, float *lscore,
+                                          uint16_t *lwid, int frame, int x0w, int y0w, int cw, int ch,
+                                          int lane) {
+  const int tw_log2 = lv.tw_log2, tw_mask = (1 << tw_log2) - 1;
+  const int step = lv.step;
+  const int pitch = SMEM ? lv.box_w : P.pitch;
+  const uint8_t *gbase = P.frames + (size_t)frame * P.frame_stride +
+                         (size_t)(y0w * step) * P.pitch + (size_t)x0w * step;
+  const Stage0Norm *norms = reinterpret_cast<const Stage0Norm *>(smem + norm_off);
+  const long long gw0 = (long long)frame * P.windows_per_frame + lv.win_base;
+
+  int n = ch << tw_log2;  // dense enumeration; columns >= cw are masked off in phase 0
+  int cart = 0;
+  for (int ph = 0; ph < P.n_sched; ++ph) {
+    const int cend = P.sched[ph];
+    int out = 0;
+    for (int base = 0; base < n; base += 32 * NW) {
+      float score[NW];
+      int wid[NW];
+      bool alive[NW];
+      PixBase<SMEM> pb[NW];
+#pragma unroll
+      for (int j = 0; j < NW; j++) {
+        const int e = base + j * 32 + lane;
+        if (ph == 0) {
+          wid[j] = e;
+          alive[j] = (e < n) && ((e & tw_mask) < cw);
+          score[j] = 0.f;
+        } else {
+          alive[j] = e < n;
+          wid[j] = alive[j] ? (int)lwid[e] : 0;
+          score[j] = alive[j] ? lscore[e] : 0.f;
+        }
+        // dead lanes point at the tile origin: valid memory, one broadcast word
+        const int wx = alive[j] ? (wid[j] & tw_mask) : 0, wy = alive[j] ? (wid[j] >> tw_log2) : 0;
+        if constexpr (SMEM) pb[j].off = tile_off + (uint32_t)(wy * step * pitch + wx * step);
+        else pb[j].ptr = gbase + (size_t)(wy * step) * P.pitch + wx * step;
+      }
+      for (int k = cart; k < cend; ++k) {
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < NW; j++) any |= alive[j];
+        if (!__any_sync(0xffffffffu, any)) break;
+        const uint32_t co = (uint32_t)k * kCartBytes;
+        const uint2 n0 = *reinterpret_cast<const uint2 *>(smem + co);
+        const float cth = *reinterpret_cast<const float *>(smem + co + 88);
+        const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + co + 92);
+        int idx[NW];
+#pragma unroll
+        for (int j = 0; j < NW; j++) idx[j] = node_test<SMEM>(smem, n0, pb[j], pitch);
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+          const uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx[j] * 8);
+          idx[j] = 2 * idx[j] + node_test<SMEM>(smem, nd, pb[j], pitch);
+        }
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+          const uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx[j] * 8);
+          idx[j] = 2 * idx[j] + node_test<SMEM>(smem, nd, pb[j], pitch);
+        }
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+          const int leaf = idx[j] - kNodes;
+          float s = __fadd_rn(score[j], *reinterpret_cast<const float *>(smem + co + 56 + 4 * leaf));
+          if (nflag) {  // warp-uniform: only carts with (mean, std) != (0, 1)
+            const Stage0Norm nm = norms[nflag - 1];
+            s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
+          }
+          if (alive[j]) {
+            score[j] = s;
+            if constexpr (TRACE) {
+              const long long gw = gw0 + (long long)(y0w + (wid[j] >> tw_log2)) * lv.nx + x0w + (wid[j] & tw_mask);
+              if (P.trace_leaf && gw >= P.leaf_w0 && gw < P.leaf_w1)
+                P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + k] = (uint8_t)leaf;
+              if (s < cth) {
+                if (P.trace_n) P.trace_n[gw] = k + 1;
+                if (P.trace_s) P.trace_s[gw] = s;
+              }
+            }
+            if (s < cth) {  // c/jda.c:399
+              alive[j] = false;
+              if constexpr (SMEM) pb[j].off = tile_off;
+              else pb[j].ptr = gbase;
+            }
+          }
+        }
+      }
+      // squeeze survivors to the front of the list (writes never pass the read cursor)
+#pragma unroll
+      for (int j = 0; j < NW; j++) {
+        const unsigned m = __ballot_sync(0xffffffffu, alive[j]);
+        if (alive[j]) {
+          const int pos = out + __popc(m & ((1u << lane) - 1u));
+          lwid[pos] = (uint16_t)wid[j];
+          lscore[pos] = score[j];
+        }
+        out += __popc(m);
+      }
+    }
+    __syncwarp();
+    n = out;
+    cart = cend;
+    if (n == 0) break;
+  }
+  // windows that passed every cart of stage 0
+  for (int base = 0; base < n; base += 32) {
+    const int e = base + lane;
+    const bool v = e < n;
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    unsigned slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(P.surv_count, (unsigned)__popc(m));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (v) {
+      const unsigned slot = slot0 + __popc(m & ((1u << lane) - 1u));
+      const int w = lwid[e];
+      if (slot < P.surv_cap)
+        P.surv[slot] = make_uint2((unsigned)frame, pack_key(li, y0w + (w >> tw_log2), x0w + (w & tw_mask)));
+    }
+  }
+  __syncwarp();
+}
+
+template <int NW, bool TRACE>
+__global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constant__ ScanParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t table_sz = (uint32_t)(P.table_bytes + 127) & ~127u;
+  const uint32_t norm_off = table_sz;
+  const uint32_t ws_off = table_sz + 256u + (uint32_t)warp * (uint32_t)sizeof(WarpScratch);
+  WarpScratch *ws = reinterpret_cast<WarpScratch *>(smem + ws_off);
+  const uint32_t tile_off = ws_off;  // tile is the first member
+  const uint32_t bar = smem_u32(&ws->mbar);
+  const uint32_t tile_s = smem_u32(ws->tile);
+  uint32_t parity = 0;
+
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (int i = threadIdx.x; i < kMaxNorm * 2; i += blockDim.x)
+    reinterpret_cast<float *>(smem + norm_off)[i] = reinterpret_cast<const float *>(P.norms)[i];
+
+  for (int li = P.n_levels - 1; li >= 0; --li) {  // coarse levels first, finest (most tiles) last
+    const LevelInfo &lv = P.lv[li];
+    __syncthreads();
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>(P.tables + lv.table_off);
+      uint4 *dst = reinterpret_cast<uint4 *>(smem);
+      for (int i = threadIdx.x; i < (int)(table_sz / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int tiles_per_frame = lv.ntx * lv.nty;
+    const unsigned total = (unsigned)tiles_per_frame * (unsigned)P.n_frames;
+    const int tw = 1 << lv.tw_log2;
+    for (;;) {
+      unsigned item = 0;
+      if (lane == 0) item = atomicAdd(&P.tile_counters[li], 1u);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= total) break;
+      const int frame = item / tiles_per_frame;
+      const int r = item - frame * tiles_per_frame;
+      const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
+      const int x0w = tx * tw, y0w = ty * lv.th;
+      const int cw = min(tw, lv.nx - x0w), ch = min(lv.th, lv.ny - y0w);
+      if (lv.use_smem) {
+        const int px0 = x0w * lv.step, py0 = y0w * lv.step;
+        if (P.use_tma) {
+          if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)(lv.box_w * lv.box_h));
+            tma_load_3d(tile_s, &P.maps[li], px0, py0, frame, bar);
+          }
+          mbar_wait(bar, parity);
+          parity ^= 1u;
+        } else {
+          const uint8_t *src = P.frames + (size_t)frame * P.frame_stride;
+          for (int i = lane; i < lv.box_w * lv.box_h; i += 32) {
+            const int yy = i / lv.box_w, xx = i - yy * lv.box_w;
+            const int gx = px0 + xx, gy = py0 + yy;
+            ws->tile[i] = (gx < P.W && gy < P.H) ? src[(size_t)gy * P.pitch + gx] : (uint8_t)0;
+          }
+          __syncwarp();
+        }
+        scan_tile<true, NW, TRACE>(P, lv, li, smem, norm_off, tile_off, ws->lscore, ws->lwid, frame, x0w,
+                                   y0w, cw, ch, lane);
+      } else {
+        scan_tile<false, NW, TRACE>(P, lv, li, smem, norm_off, tile_off, ws->lscore, ws->lwid, frame, x0w,
+                                    y0w, cw, ch, lane);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ k3: generic cascade
+//
+// One warp per window.  Within a stage the shape is fixed, so the K tree walks are independent:
+// lanes take 32 consecutive carts at a time (float address arithmetic in the reference's exact
+// order), then the running score is replayed over those 32 carts in cart order (sequential adds
+// and the (score - mean) / std normalisation, early exit at the first score < th), so the reject
+// decision, the exit score and the cart count equal the reference's.  After a completed stage
+// the regression is a leaf-index gather: lane i sums row (8k + leaf_k) of w[t] into shape[i]
+// for k = 0..K-1 in ascending order -- 2L independent chains, each in the reference's order.
+
+constexpr int K3_WARPS = 4;
+
+template <bool TRACE>
+__global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constant__ CascadeParams P) {
+  extern __shared__ __align__(16) uint8_t smem3[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = 2 * P.L;
+  const int per_warp = kMaxDim * 4 + ((P.K + 15) & ~15);
+  float *shape = reinterpret_cast<float *>(smem3 + (size_t)warp * per_warp);
+  uint8_t *leafs = reinterpret_cast<uint8_t *>(shape + kMaxDim);
+
+  const long long total = P.dense ? P.dense_total : (long long)min(*P.surv_count, P.surv_cap);
+  for (long long e = (long long)blockIdx.x * K3_WARPS + warp; e < total; e += (long long)gridDim.x * K3_WARPS) {
+    int frame, level, xi, yi;
+    if (P.dense) {
+      frame = (int)(e / P.windows_per_frame);
+      long long r = e - (long long)frame * P.windows_per_frame;
+      level = 0;
+      while (level + 1 < P.n_levels && r >= P.lv_base[level + 1]) level++;
+      r -= P.lv_base[level];
+      yi = (int)(r / P.lv_nx[level]);
+      xi = (int)(r - (long long)yi * P.lv_nx[level]);
+    } else {
+      const uint2 s = P.surv[e];
+      frame = (int)s.x;
+      level = (int)(s.y >> 26);
+      yi = (int)((s.y >> 13) & 0x1fff);
+      xi = (int)(s.y & 0x1fff);
+    }
+    const int win = P.lv_win[level], step = P.lv_step[level];
+    const int x = xi * step, y = yi * step;
+    const float fwin = (float)win;
+    // view origins, c/jda.c:344-354
+    const int hx = __float2int_rz(__fmul_rn((float)x, P.r)), hy = __float2int_rz(__fmul_rn((float)y, P.r));
+    const int qx = x / 2, qy = y / 2;
+    const uint8_t *po = P.frames + (size_t)frame * P.frame_stride;
+    const uint8_t *ph = P.hq ? P.hq + (size_t)frame * P.hq_stride : nullptr;
+    const uint8_t *pq = P.hq ? ph + (size_t)P.hw * P.hh : nullptr;
+    const long long gw = (long long)frame * P.windows_per_frame + P.lv_base[level] + (long long)yi * P.lv_nx[level] + xi;
+    const bool trace_leaf = TRACE && P.trace_leaf && gw >= P.leaf_w0 && gw < P.leaf_w1;
+
+    __syncwarp();
+    for (int i = lane; i < D; i += 32) shape[i] = P.mean_shape[i];
+    __syncwarp();
+
+    float score = 0.f;
+    int n_eval = 0;
+    bool rejected = false;
+    for (int t = 0; t < P.t_run && !rejected; t++) {
+      for (int kc = 0; kc < P.K && !rejected; kc += 32) {
+        const int k = kc + lane;
+        float ls = 0.f;
+        float4 cp = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (k < P.K) {
+          const size_t c = (size_t)t * P.K + k;
+          const NodeRec *nd = P.nodes + c * kNodes;
+          int idx = 0;
+#pragma unroll
+          for (int lvl = 0; lvl < kDepth - 1; lvl++) {
+            const int4 a = __ldg(reinterpret_cast<const int4 *>(nd + idx));
+            const float4 o = __ldg(reinterpret_cast<const float4 *>(nd + idx) + 1);
+            // a = scale, lm1, lm2, th ; o = o1x, o1y, o2x, o2y   (c/jda.c:371-389)
+            const float x1 = __fadd_rn(shape[a.y], o.x), y1 = __fadd_rn(shape[a.y + 1], o.y);
+            const float x2 = __fadd_rn(shape[a.z], o.z), y2 = __fadd_rn(shape[a.z + 1], o.w);
+            int x1_ = __float2int_rz(__fmul_rn(x1, fwin)), y1_ = __float2int_rz(__fmul_rn(y1, fwin));
+            int x2_ = __float2int_rz(__fmul_rn(x2, fwin)), y2_ = __float2int_rz(__fmul_rn(y2, fwin));
+            x1_ = min(max(x1_, 0), win - 1); y1_ = min(max(y1_, 0), win - 1);
+            x2_ = min(max(x2_, 0), win - 1); y2_ = min(max(y2_, 0), win - 1);
+            int p1, p2;
+            if (a.x == 0) {
+              p1 = __ldg(po + (size_t)(y + y1_) * P.pitch + x + x1_);
+              p2 = __ldg(po + (size_t)(y + y2_) * P.pitch + x + x2_);
+            } else {
+              // h / q views keep w = win (c/jda.c:347,352); linear index like the reference, reads
+              // past the plane buffer (undefined there) are defined as 0 here
+              const uint8_t *pp = (a.x == 1) ? ph : pq;
+              const int pw = (a.x == 1) ? P.hw : P.qw, phh = (a.x == 1) ? P.hh : P.qh;
+              const int bx = (a.x == 1) ? hx : qx, by = (a.x == 1) ? hy : qy;
+              const long long lim = (long long)pw * phh;
+              const long long i1 = (long long)(by + y1_) * pw + bx + x1_;
+              const long long i2 = (long long)(by + y2_) * pw + bx + x2_;
+              p1 = (i1 < lim) ? (int)__ldg(pp + i1) : 0;
+              p2 = (i2 < lim) ? (int)__ldg(pp + i2) : 0;
+            }
+            idx = (p1 - p2 <= a.w) ? 2 * idx + 1 : 2 * idx + 2;
+          }
+          const int lf = idx - kNodes;
+          leafs[k] = (uint8_t)lf;
+          ls = __ldg(P.leaf + c * kLeaves + lf);
+          cp = __ldg(P.cart + c);
+        }
+        // replay the score over this chunk in cart order
+        const int cnt = min(32, P.K - kc);
+        int stop = -1;
+        for (int j = 0; j < cnt; j++) {
+          const float sj = __shfl_sync(0xffffffffu, ls, j);
+          const float thj = __shfl_sync(0xffffffffu, cp.x, j);
+          const float mj = __shfl_sync(0xffffffffu, cp.y, j);
+          const float dj = __shfl_sync(0xffffffffu, cp.z, j);
+          score = __fadd_rn(score, sj);                      // c/jda.c:396
+          score = __fdiv_rn(__fsub_rn(score, mj), dj);       // c/jda.c:397
+          n_eval++;
+          if (score < thj) { stop = j; break; }              // c/jda.c:399
+        }
+        if (TRACE && trace_leaf && k < P.K && (stop < 0 || lane <= stop))
+          P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + (size_t)t * P.K + k] = leafs[k];
+        if (stop >= 0) rejected = true;
+      }
+      if (rejected) break;
+      __syncwarp();
+      // global regression, c/jda.c:403-411
+      const float *wt = P.w + (size_t)t * P.K * kLeaves * D;
+      for (int i = lane; i < D; i += 32) {
+        float acc = shape[i];
+#pragma unroll 8
+        for (int k = 0; k < P.K; k++) acc = __fadd_rn(acc, __ldg(wt + (size_t)(k * kLeaves + leafs[k]) * D + i));
+        shape[i] = acc;
+      }
+      __syncwarp();
+    }
+    if (TRACE) {
+      if (lane == 0) {
+        if (P.trace_n) P.trace_n[gw] = n_eval;
+        if (P.trace_s) P.trace_s[gw] = score;
+      }
+    }
+    if (rejected) continue;
+    if (P.use_th && score < P.th) continue;  // c/jda.c:414
+    unsigned slot = 0;
+    if (lane == 0) slot = atomicAdd(P.hit_count, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < P.hit_cap) {
+      float *rec = P.hits + (size_t)slot * P.rec_words;
+      if (lane == 0) {
+        reinterpret_cast<int *>(rec)[0] = frame;
+        reinterpret_cast<uint32_t *>(rec)[1] = pack_key(level, yi, xi);
+        reinterpret_cast<int *>(rec)[2] = x;
+        reinterpret_cast<int *>(rec)[3] = y;
+        reinterpret_cast<int *>(rec)[4] = win;
+        rec[5] = score;
+      }
+      for (int i = lane; i < D; i += 32) rec[kHitHeader + i] = shape[i];
+    }
+  }
+}
+
+#endif  // __CUDACC__
+}  // namespace jda

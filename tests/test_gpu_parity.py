@@ -1,0 +1,234 @@
+"""Parity of the CUDA path against the oracle and the reference's golden outputs.
+
+Everything goes through the C ABI (jda_b200.api is a ctypes shim over it).  Bar: bit-exact --
+tree traversal, leaf indices, reject positions are integer work; scores and landmarks are the
+same float32 operations in the same order, so they are compared as raw bits (tolerance 0, which is
+inside north_star's 1e-6 relative).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from jda_b200 import api, synth
+from tests.conftest import SHIPPED_F32
+from tests.golden.make_fixtures import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _same(got, want):
+    (b1, s1, p1), (b2, s2, p2) = got, want
+    assert b1.shape == b2.shape, (b1.shape, b2.shape)
+    np.testing.assert_array_equal(b1, b2)
+    np.testing.assert_array_equal(_bits(s1), _bits(s2))
+    np.testing.assert_array_equal(_bits(p1), _bits(p2))
+
+
+@pytest.fixture(scope="module")
+def casc():
+    c = api.Cascador(SHIPPED_F32, double=False)
+    yield c
+    c.close()
+
+
+# ---- the reference's own outputs -------------------------------------------------------------
+
+@pytest.mark.parametrize("case", [c[0] for c in CASES])
+def test_golden_reference_outputs(casc, gold, case):
+    name, mk, kw = next(c for c in CASES if c[0] == case)
+    got = casc.detect(mk(synth), **kw)
+    _same(got, (gold[name + "/boxes"], gold[name + "/scores"], gold[name + "/shapes"]))
+
+
+def test_known_answer_and_landmark_rmse(casc, oracle, oracle_shipped):
+    img = synth.face_canvas()
+    got = casc.detect(img)
+    assert got[0].tolist() == [[396, 308, 110], [63, 21, 213]]
+    want = oracle.detect(oracle_shipped, img)
+    rmse = float(np.sqrt(np.mean((got[2].astype(np.float64) - want[2]) ** 2)))
+    assert rmse == 0.0
+    _same(got, want)
+
+
+# ---- per-window trace: reject position, exit score, every evaluated leaf ------------------------
+
+TRACE_FRAMES = {
+    "noise": lambda: synth.noise_frame(0),
+    "blur": lambda: synth.blur_frame(1),
+    "faces": lambda: synth.face_canvas(),
+    "odd_size": lambda: synth.facemix_frame(4, 451, 333),
+}
+
+
+@pytest.mark.parametrize("flags", [0, api.NO_TMA], ids=["tma", "plain_loads"])
+@pytest.mark.parametrize("frame", list(TRACE_FRAMES))
+def test_trace_matches_oracle(casc, oracle, oracle_shipped, frame, flags):
+    img = TRACE_FRAMES[frame]()
+    nwin = api.count_windows(img.shape[1], img.shape[0])
+    # leaves for three slices of the scan: first windows, the middle, the coarse levels at the end
+    for rng in [(0, 3000), (nwin // 2, nwin // 2 + 3000), (nwin - 3000, nwin)]:
+        tn, ts, lv = casc.trace(img, flags=flags, leaf_range=rng)
+        on, os_, olv = oracle.trace(oracle_shipped, img, leaf_range=rng)
+        np.testing.assert_array_equal(tn, on)           # carts evaluated = reject (stage, cart)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+        np.testing.assert_array_equal(lv, olv)
+
+
+def test_trace_generic_kernel_only(casc, oracle, oracle_shipped):
+    """stage-0 scan switched off: every window through k3_cascade."""
+    img = synth.face_canvas()[:240, :320].copy()
+    tn, ts, lv = casc.trace(img, flags=api.NO_STAGE0_SCAN, leaf_range=(0, 4000))
+    on, os_, olv = oracle.trace(oracle_shipped, img, leaf_range=(0, 4000))
+    np.testing.assert_array_equal(tn, on)
+    np.testing.assert_array_equal(_bits(ts), _bits(os_))
+    np.testing.assert_array_equal(lv, olv)
+
+
+@pytest.mark.parametrize("nw", ["1", "2", "4"])
+def test_windows_per_lane_variants(oracle, oracle_shipped, nw):
+    os.environ["JDA_B200_NW"] = nw
+    try:
+        c = api.Cascador(SHIPPED_F32, double=False)
+        img = synth.facemix_frame(9)
+        _same(c.detect(img, th=-1.0), oracle.detect(oracle_shipped, img, th=-1.0))
+        raw = c.detect_batch(img[None], th=0.0, flags=api.RAW_HITS | api.NO_FINAL_TH)[0]
+        ob, osc, osh, st = oracle.detect_raw(oracle_shipped, img, use_th=False)
+        _same(raw, (ob, osc, osh))
+        assert c.last_stats["stage0_survivors"] == st["stage_survivors"][0]
+        c.close()
+    finally:
+        del os.environ["JDA_B200_NW"]
+
+
+# ---- synthetic models: deep survivors, normalised scores, scaled (h/q) nodes --------------------
+
+SYN = [
+    dict(seed=1, mode="passall", scales=(0,)),
+    dict(seed=2, mode="reject", scales=(0,)),
+    dict(seed=3, mode="reject", scales=(0, 1, 2), coord_max=0.45),
+    dict(seed=4, mode="passall", scales=(0, 1, 2), coord_max=0.45),
+    dict(seed=5, mode="reject", scales=(0,), norm_every=7),      # > 32 normalised carts: generic path
+]
+
+
+@pytest.mark.parametrize("cfg", SYN, ids=lambda c: "seed%d" % c["seed"])
+def test_synthetic_models(oracle, tmp_path, cfg):
+    path = synth.write_model(str(tmp_path / "syn.model"), **cfg)
+    c = api.Cascador(path, double=True)
+    ho = oracle.load(path, True)
+    frames = [synth.blur_frame(9, 96, 80), synth.noise_frame(5, 70, 61)]
+    if cfg["mode"] == "reject":
+        frames.append(synth.blur_frame(10, 320, 240))
+    for img in frames:
+        for kw in (dict(scale=1.25, min_size=24, max_size=-1, th=-1e30),
+                   dict(scale=1.3, min_size=30, max_size=60, th=0.5)):
+            _same(c.detect(img, **kw), oracle.detect(ho, img, **kw))
+        tn, ts, lv = c.trace(img, leaf_range=(0, 500))
+        on, os_, olv = oracle.trace(ho, img, leaf_range=(0, 500))
+        np.testing.assert_array_equal(tn, on)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+        np.testing.assert_array_equal(lv, olv)
+    c.close(); oracle.release(ho)
+
+
+def test_against_reference_library_directly(reflib, tmp_path):
+    path = synth.write_model(str(tmp_path / "syn.model"), seed=21, mode="reject")
+    c = api.Cascador(path, double=True)
+    hr = reflib.load(path, True)
+    for img in (synth.blur_frame(31, 200, 160), synth.facemix_frame(32, 333, 250)):
+        _same(c.detect(img, th=-1e30), reflib.detect(hr, img, th=-1e30))
+    c.close(); reflib.release(hr)
+
+
+def test_resize_planes_byte_identical(casc, oracle):
+    img = synth.facemix_frame(2)
+    r = np.float32(1.0) / np.sqrt(np.float32(2.0))
+    for dw, dh in [(int(np.float32(640) * r), int(np.float32(480) * r)), (320, 240), (101, 77)]:
+        np.testing.assert_array_equal(casc.resize(img, dw, dh), oracle.resize(img, dw, dh))
+
+
+# ---- batch / device-resident / mining entry points --------------------------------------------------
+
+def test_batch_equals_per_frame(casc, oracle, oracle_shipped):
+    frames = synth.make_frames("mix", 9, seed0=40)
+    res = casc.detect_batch(frames, max_size=192, th=-0.5)
+    assert casc.last_stats["windows"] == 9 * 169236
+    for f in range(9):
+        _same(res[f], oracle.detect(oracle_shipped, frames[f], max_size=192, th=-0.5))
+
+
+def test_device_resident_frames(casc):
+    import torch
+    frames = synth.make_frames("facemix", 6, seed0=60)
+    host = casc.detect_batch(frames, max_size=192, th=-0.5)
+    d = torch.from_numpy(frames).cuda()
+    torch.cuda.synchronize()
+    dev = casc.detect_batch(None, device_ptr=d.data_ptr(), shape=tuple(d.shape), max_size=192, th=-0.5)
+    for a, b in zip(host, dev):
+        _same(a, b)
+    # odd pitch: TMA not applicable, plain-load path must give the same answer
+    fr = synth.make_frames("facemix", 3, 451, 333, seed0=70)
+    host = casc.detect_batch(fr, th=-0.5)
+    d = torch.from_numpy(fr).cuda()
+    torch.cuda.synchronize()
+    dev = casc.detect_batch(None, device_ptr=d.data_ptr(), shape=tuple(d.shape), th=-0.5)
+    for a, b in zip(host, dev):
+        _same(a, b)
+
+
+@pytest.mark.parametrize("t_limit", [1, 2, 5])
+def test_mining_mode_truncated_cascade(casc, oracle, oracle_shipped, t_limit):
+    """Validate()'s partial cascade (src/jda/cascador.cpp:178-197): first t stages, every survivor
+    emitted with its score and window-normalised shape, no NMS."""
+    img = synth.face_canvas()
+    got = casc.detect_batch(img[None], t_limit=t_limit, flags=api.RAW_HITS | api.NO_FINAL_TH)[0]
+    ob, osc, osh, st = oracle.detect_raw(oracle_shipped, img, t_limit=t_limit, use_th=False)
+    assert len(osc) == st["stage_survivors"][t_limit - 1] > 0
+    _same(got, (ob, osc, osh))
+
+
+# ---- edges ------------------------------------------------------------------------------------
+
+def test_edge_cases(casc, oracle, oracle_shipped):
+    tiny = synth.blur_frame(2, 30, 27)
+    for img, kw in [(tiny, dict(th=-5.0)),
+                    (synth.blur_frame(3, 24, 24), dict(th=-1e30)),      # exactly one window
+                    (synth.blur_frame(3, 23, 64), dict()),               # too small: no windows
+                    (synth.noise_frame(1, 100, 100), dict(scale=1.0)),   # reference would never return
+                    (synth.noise_frame(1, 100, 100), dict(min_size=90, max_size=50)),
+                    (synth.face_canvas(), dict(scale=2.0, th=-1.0)),
+                    (synth.face_canvas(), dict(scale=1.07, min_size=150, th=-1.0))]:
+        _same(casc.detect(img, **kw), oracle.detect(oracle_shipped, img, **kw))
+    assert casc.detect(synth.blur_frame(3, 23, 64))[0].shape == (0, 3)
+
+
+# ---- full-size, size-independent properties -------------------------------------------------------
+
+def test_full_size_batch_properties(casc, oracle, oracle_shipped):
+    """BASELINE config 2 shape (VGA, 3-octave) on a 96-frame slice: window count is exact, the run is
+    idempotent, batch order does not matter, and sampled frames equal the oracle."""
+    frames = synth.make_frames("mix", 96, seed0=1000)
+    a = casc.detect_batch(frames, max_size=192, th=0.0)
+    st = dict(casc.last_stats)
+    assert st["windows"] == 96 * 169236 and st["n_levels"] == 10
+    b = casc.detect_batch(frames, max_size=192, th=0.0)
+    for x, y in zip(a, b):
+        _same(x, y)
+    perm = np.random.default_rng(0).permutation(96)
+    c = casc.detect_batch(frames[perm], max_size=192, th=0.0)
+    for i, p in enumerate(perm):
+        _same(c[i], a[p])
+    s0 = 0
+    for f in (0, 1, 2, 50):
+        _same(a[f], oracle.detect(oracle_shipped, frames[f], max_size=192, th=0.0))
+    raw = casc.detect_batch(frames[:4], max_size=192, flags=api.RAW_HITS | api.NO_FINAL_TH)
+    for f in range(4):
+        ob, osc, osh, ost = oracle.detect_raw(oracle_shipped, frames[f], max_size=192, use_th=False)
+        _same(raw[f], (ob, osc, osh))
+        s0 += ost["stage_survivors"][0]
+    assert casc.last_stats["stage0_survivors"] == s0

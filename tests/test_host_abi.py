@@ -1,0 +1,99 @@
+"""CPU-side checks of libjda_b200.so: it loads, exports the whole C ABI, and its host logic
+(model files, level enumeration, NMS) agrees with the oracle.  No compute calls need a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from jda_b200 import api, synth
+from tests.conftest import ROOT, SHIPPED_F32
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "jda_b200.h")).read()
+    declared = re.findall(r"JDA_API\s+[\w\s\*]+?\b(jda\w+)\s*\(", hdr)
+    assert len(declared) >= 17 and set(declared) == set(api.EXPORTS)
+    L = ctypes.CDLL(api.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    # the six symbols of the reference's c/jda.h are all there under their real names
+    for name in ("jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSerializeTo",
+                 "jdaCascadorRelease", "jdaDetect", "jdaResultRelease"):
+        assert name in declared
+
+
+def test_result_struct_layout_matches_reference_header():
+    import ctypes
+    # c/jda.h:18-24: two ints + three pointers = 32 bytes on LP64
+    assert ctypes.sizeof(api._Result) == 32
+    assert api._Result.bboxes.offset == 8 and api._Result.shapes.offset == 16 and api._Result.scores.offset == 24
+
+
+def test_model_roundtrip_bytes(tmp_path):
+    c = api.Cascador(SHIPPED_F32, double=False)
+    assert (c.T, c.K, c.L, c.depth) == (5, 540, 27, 4)
+    out = tmp_path / "rt.model"
+    c.save_f32(str(out))
+    assert out.read_bytes() == open(SHIPPED_F32, "rb").read()
+    # double flavour -> same in-memory model -> same float file
+    wide = synth.widen_f32_model(SHIPPED_F32, str(tmp_path / "wide.model"))
+    c2 = api.Cascador(wide, double=True)
+    out2 = tmp_path / "rt2.model"
+    c2.save_f32(str(out2))
+    assert out2.read_bytes() == out.read_bytes()
+    c.close(); c2.close()
+
+
+def test_synthetic_model_serialiser_matches_oracle(oracle, tmp_path):
+    path = synth.write_model(str(tmp_path / "s.model"), seed=11, scales=(0, 1, 2), coord_max=0.45)
+    c = api.Cascador(path, double=True)
+    h = oracle.load(path, True)
+    a, b = tmp_path / "a", tmp_path / "b"
+    c.save_f32(str(a)); oracle.save_f32(h, str(b))
+    assert a.read_bytes() == b.read_bytes()
+    c.close(); oracle.release(h)
+
+
+def test_bad_models_are_rejected(tmp_path):
+    with pytest.raises(RuntimeError):
+        api.Cascador(str(tmp_path / "missing.model"))
+    p = tmp_path / "short.model"
+    p.write_bytes(open(SHIPPED_F32, "rb").read()[:100000])
+    with pytest.raises(RuntimeError):
+        api.Cascador(str(p), double=False)
+    q = tmp_path / "depth5.model"
+    b = bytearray(open(SHIPPED_F32, "rb").read())
+    b[16:20] = (5).to_bytes(4, "little")
+    q.write_bytes(bytes(b))
+    with pytest.raises(RuntimeError):
+        api.Cascador(str(q), double=False)
+
+
+@pytest.mark.parametrize("w,h,scale,mn,mx", [(640, 480, 1.25, 24, -1), (640, 480, 1.25, 24, 192),
+                                              (640, 480, 1.2, 24, -1), (640, 480, 1.25, 40, -1),
+                                              (1920, 1080, 1.25, 24, 768), (450, 333, 1.15, 28, 200),
+                                              (30, 27, 1.25, 24, -1), (23, 100, 1.25, 24, -1),
+                                              (640, 480, 1.0, 24, -1), (640, 480, 0.9, 24, -1),
+                                              (640, 480, 1.5, 100, 50), (24, 24, 1.25, 24, -1)])
+def test_levels_and_window_counts_match_oracle(oracle, w, h, scale, mn, mx):
+    assert api.levels(w, h, scale, mn, mx) == (oracle.levels(w, h, scale, mn, mx) if min(w, h) >= 24 else [])
+    assert api.count_windows(w, h, scale, mn, mx) == oracle.count_windows(w, h, scale, mn, mx)
+
+
+def test_nms_matches_oracle_on_random_boxes(oracle):
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 17, 300):
+        boxes = np.stack([rng.integers(0, 200, n), rng.integers(0, 200, n), rng.integers(24, 120, n)], 1).astype(np.int32)
+        scores = rng.normal(0, 1, n).astype(np.float32)
+        scores[rng.integers(0, max(n, 1), n // 3)] = 0.5   # ties exercise the strict-< exchange sort
+        np.testing.assert_array_equal(api.nms(boxes, scores), oracle.nms(boxes, scores))
+
+
+@pytest.mark.skipif(api.device_count() > 0, reason="a GPU is visible")
+def test_detect_without_gpu_fails_loudly():
+    c = api.Cascador(SHIPPED_F32, double=False)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        c.detect(synth.noise_frame(0, 64, 48))
+    c.close()
