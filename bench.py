@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- candidate windows/sec of the JDA detect path on the VGA 3-octave pyramid.
+
+    python bench.py --gpus N --steps K --warmup W              (ours; N>1 under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K ...    (the reference's own c/jda.c on host cores)
+
+A step = one pass of the hot path (jdaB200DetectBatch: scan + cascade + hit read-back + host NMS)
+over one batch of B synthetic 640x480 frames per GPU, args (scale 1.25, min 24, max 192, th 0.0):
+BASELINE.json configs[1], 169,236 candidate windows per frame.  K steps x B frames ~ the config's
+10k frames (K=20, B=512).  The batch (157 MB) is larger than L2 (126 MB) and two different batches
+alternate between steps.
+
+value : whole-job windows/s with the frames already resident in HBM (device pointers in).
+e2e   : same metric through the reference-facing call with HOST frames (pinned): H2D of every frame
+        and D2H of the hit records happen inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+MODEL = os.path.join(ROOT, "tests", "golden", "jda_shipped_f32.model")
+W, H = 640, 480
+ARGS = dict(scale=1.25, min_size=24, max_size=192, th=0.0)
+WINDOWS_PER_FRAME = 169236
+METRIC = "candidate windows/sec, VGA 3-octave pyramid (scale 1.25, min 24, max 192), full cascade"
+
+
+def frame_pool(n_distinct, dist, seed0):
+    from jda_b200 import synth
+    return synth.make_frames(dist, n_distinct, W, H, seed0=seed0)
+
+
+def tile_batch(pool, batch, shift):
+    idx = (np.arange(batch) + shift) % len(pool)
+    return np.ascontiguousarray(pool[idx])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.05:
+                    sm.append(float(f[0]))
+                    for nm, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def work_stats(pool_sample):
+    """avg carts / window and survivors for the algorithmic-bytes figure (oracle = checker only)."""
+    from oracle import pyoracle
+    o = pyoracle.Oracle()
+    h = o.load(MODEL, double=False)
+    carts = wins = stages = 0
+    for img in pool_sample:
+        _, _, _, st = o.detect_raw(h, img, scale=ARGS["scale"], min_size=ARGS["min_size"],
+                                   max_size=ARGS["max_size"], th=ARGS["th"])
+        carts += st["carts"]
+        wins += st["windows"]
+        stages += sum(st["stage_survivors"])
+    o.release(h)
+    return carts / wins, stages / wins
+
+
+def cpu_reference_run(frames, threads, use_ref=True):
+    """The reference's own jdaDetect (oracle/_ref) -- or the oracle port -- on `threads` host threads,
+    one shared read-only cascador (the function is re-entrant).  Returns seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    kind = "port"
+    if use_ref and os.path.exists(pyoracle.REF_SO):
+        lib = pyoracle.RefLib()
+        h = lib.load(MODEL, double=False)
+        kind = "reference"
+    else:
+        lib = pyoracle.Oracle()
+        h = lib.load(MODEL, double=False)
+
+    def one(i):
+        lib.detect(h, frames[i], ARGS["scale"], 0.1, ARGS["min_size"], ARGS["max_size"], ARGS["th"])
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, range(len(frames))))
+    dt = time.perf_counter() - t0
+    lib.release(h)
+    return dt, kind
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = max(8, min(cores, 64))
+    pool = frame_pool(n, a.dist, 0)
+    for _ in range(a.warmup):
+        cpu_reference_run(pool[:max(2, n // 4)], cores)
+    tot = 0.0
+    kind = "port"
+    for _ in range(a.steps):
+        dt, kind = cpu_reference_run(pool, cores)
+        tot += dt
+    val = a.steps * n * WINDOWS_PER_FRAME / tot
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": a.gpus,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+           "config": {"workload": "vga_3oct_%s" % a.dist, "frames_per_step": n, "frame": [W, H], **ARGS},
+           "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": kind,
+                            "sample": "%d %s VGA frames per step, %d threads over jdaDetect" % (n, a.dist, cores)},
+           "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--dist", default="mix", choices=["mix", "noise", "blur6", "facemix"])
+    ap.add_argument("--distinct", type=int, default=96, help="distinct synthetic frames tiled into a batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    import torch
+    from jda_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the detect path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    c = api.Cascador(MODEL, double=False, device=local)
+    stream = torch.cuda.current_stream()
+    c.set_stream(stream.cuda_stream)
+
+    B = a.batch
+    pool = frame_pool(a.distinct, a.dist, 100000 * rank)
+    host = [torch.from_numpy(tile_batch(pool, B, s)).pin_memory() for s in (0, 37)]
+    dev = [h.cuda(non_blocking=False) for h in host]
+    torch.cuda.synchronize()
+
+    from jda_b200 import shard
+
+    def gather_records(res):
+        """the one exchange step of the path: NCCL all-gather of the fixed-stride detection records
+        (frame, x, y, size, score, 54 landmark floats) so every rank holds the job-wide table."""
+        if not dist_on:
+            return None
+        rec = shard.pack_records(res, frame0=rank * B, landmark_n=c.L)
+        return shard.all_gather_records(rec, device="cuda")
+
+    def step_resident(i):
+        d = dev[i & 1]
+        res = c.detect_batch(None, device_ptr=d.data_ptr(), shape=(B, H, W), **ARGS)
+        gather_records(res)
+        return c.last_stats
+
+    def step_e2e(i):
+        hbuf = host[i & 1].numpy()
+        res = c.detect_batch(hbuf, **ARGS)
+        gather_records(res)
+        return c.last_stats
+
+    def timed(step_fn, steps, warmup, sample_clocks=False):
+        for i in range(warmup):
+            step_fn(i)
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if sample_clocks else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        acc = {"ms_scan": 0.0, "ms_cascade": 0.0, "ms_h2d": 0.0, "ms_d2h": 0.0, "ms_host": 0.0,
+               "raw_hits": 0, "stage0_survivors": 0, "detections": 0, "launches": 0}
+        for i in range(steps):
+            st = step_fn(i)
+            for k in ("ms_scan", "ms_cascade", "ms_h2d", "ms_d2h", "ms_host", "raw_hits", "stage0_survivors",
+                      "detections"):
+                acc[k] += st[k]
+            acc["launches"] += st["scan_launches"] + st["cascade_launches"] + st["resize_launches"]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if dist_on:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        clocks = sampler.stop(t0, t1) if sampler else None
+        return ms, acc, clocks
+
+    ms, acc, clocks = timed(step_resident, a.steps, a.warmup, sample_clocks=True)
+    total_windows = a.steps * B * WINDOWS_PER_FRAME * world
+    value = total_windows / (ms * 1e-3)
+
+    e2e_steps = max(3, a.steps // 2)
+    ms_e, acc_e, _ = timed(step_e2e, e2e_steps, 2)
+    e2e_value = e2e_steps * B * WINDOWS_PER_FRAME * world / (ms_e * 1e-3)
+    rec_bytes = (6 + 2 * c.L) * 4
+    d2h = int(acc_e["raw_hits"] / e2e_steps) * rec_bytes + 22 * 4
+
+    out = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+           "config": {"workload": "vga_3oct_%s" % a.dist, "frames_per_step_per_gpu": B, "frame": [W, H],
+                      "windows_per_frame": WINDOWS_PER_FRAME, **ARGS, "distinct_frames": a.distinct,
+                      "l2": "inputs larger than L2 (157 MB batch, two batches alternate)",
+                      "model": "shipped T=5 K=540 L=27 (tests/golden/jda_shipped_f32.model)",
+                      "parallelism": "frames sharded, %d rank(s), NCCL all-gather of detections" % world},
+           "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": B * W * H,
+                   "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps},
+           "gpu_launches": acc["launches"], "clocks": clocks,
+           "kernel_ms_per_step": {"k2_scan": acc["ms_scan"] / a.steps, "k3_cascade": acc["ms_cascade"] / a.steps,
+                                  "d2h": acc["ms_d2h"] / a.steps, "host_nms": acc["ms_host"] / a.steps},
+           "per_step": {"stage0_survivors": acc["stage0_survivors"] / a.steps, "raw_hits": acc["raw_hits"] / a.steps,
+                        "detections": acc["detections"] / a.steps}}
+
+    if rank == 0:
+        # roofline of the dominant kernel (k2_scan): SURVEY.md 8(d) figure (A), logical bytes touched
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        carts_pw, stages_pw = work_stats(pool[:6])
+        bytes_pw = 118.0 * carts_pw + 216.0      # per window inside k2 (stage 0); survivors' stages are k3's
+        k2_s = acc["ms_scan"] / a.steps * 1e-3
+        achieved = B * WINDOWS_PER_FRAME * bytes_pw / k2_s / 1e9
+        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": None, "kernel": "k2_scan",
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                           "note": "logical (algorithmic touched) bytes: 118 B x carts/window + 216 B; data is "
+                                   "served from shared memory/L2 so frac may exceed 1; compulsory DRAM is "
+                                   "~1.8 B/window (see DESIGN.md)",
+                           "carts_per_window": carts_pw, "algorithmic_bytes_per_window": bytes_pw,
+                           "k2_windows_per_s": B * WINDOWS_PER_FRAME / k2_s}
+        if not a.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = max(8, min(cores, 48))
+            dt, kind = cpu_reference_run(pool[:n], cores)
+            out["cpu_baseline"] = {"value": n * WINDOWS_PER_FRAME / dt, "unit": "windows/s", "cores": cores,
+                                   "kind": kind, "sample": "%d %s VGA frames, %d threads over jdaDetect (%.1f s)"
+                                   % (n, a.dist, cores, dt)}
+    if not a.no_breakdown and not dist_on:
+        # the three SURVEY.md 8(d) distributions separately (short runs, resident frames)
+        by = {}
+        for d in ("noise", "blur6", "facemix"):
+            p = frame_pool(32, d, 5000)
+            t = torch.from_numpy(tile_batch(p, B, 0)).cuda()
+            torch.cuda.synchronize()
+
+            def fn(i, t=t):
+                c.detect_batch(None, device_ptr=t.data_ptr(), shape=(B, H, W), unpack=False, **ARGS)
+                return c.last_stats
+            m, ac, _ = timed(fn, 5, 2)
+            by[d] = {"windows_per_s": 5 * B * WINDOWS_PER_FRAME / (m * 1e-3), "k2_ms": ac["ms_scan"] / 5,
+                     "k3_ms": ac["ms_cascade"] / 5}
+            del t
+        out["by_distribution"] = by
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    c.close()
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,66 @@
+"""Multi-GPU plumbing of the detect path: frames shard across ranks in contiguous
+blocks, the model is replicated, and the only exchange is one all-gather of fixed-stride detection
+records per batch so that every rank ends with the identical job-wide detection table.
+
+The reference has no distributed code; the record carries exactly what its jdaResult holds per
+face (c/jda.h:18-24): bbox (x, y, size), score, 2*L landmark floats -- plus the global frame id.
+
+Works on any torch.distributed backend: NCCL with CUDA tensors on the B200 box (NVLink/NVSwitch),
+gloo with CPU tensors in the CPU tests.
+"""
+import numpy as np
+
+HEADER = 5  # frame, x, y, size, score
+
+
+def shard_range(n_frames, rank, world):
+    """contiguous block of frames owned by `rank`: frame i -> rank floor(i * world / n)."""
+    lo = (n_frames * rank + world - 1) // world
+    hi = (n_frames * (rank + 1) + world - 1) // world
+    return lo, hi
+
+
+def pack_records(results, frame0=0, landmark_n=27):
+    """list of (boxes, scores, shapes) per local frame -> [n, 5 + 2L] float32 records.
+    Integers up to 2^24 (frame ids, pixel coordinates) are exact in float32."""
+    D = 2 * landmark_n
+    n = sum(len(r[1]) for r in results)
+    rec = np.zeros((n, HEADER + D), np.float32)
+    o = 0
+    for f, (boxes, scores, shapes) in enumerate(results):
+        k = len(scores)
+        if k:
+            rec[o:o + k, 0] = frame0 + f
+            rec[o:o + k, 1:4] = boxes
+            rec[o:o + k, 4] = scores
+            rec[o:o + k, HEADER:] = shapes
+            o += k
+    return rec
+
+
+def unpack_records(rec):
+    """records -> (frame ids, boxes i32, scores, shapes)."""
+    return (rec[:, 0].astype(np.int64), rec[:, 1:4].astype(np.int32), rec[:, 4].copy(),
+            rec[:, HEADER:].copy())
+
+
+def all_gather_records(rec, device=None, group=None):
+    """One count all-gather + one padded record all-gather.  Returns the job-wide table ordered by
+    (rank, local order) = global frame order for contiguous sharding.  Collective: every rank calls."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    cnt = torch.tensor([rec.shape[0]], dtype=torch.int64, device=dev)
+    cnts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnts, cnt, group=group)
+    cnts_h = cnts.cpu().numpy()
+    mx = max(int(cnts_h.max()), 1)
+    width = rec.shape[1]
+    mine = torch.zeros((mx, width), dtype=torch.float32, device=dev)
+    if rec.shape[0]:
+        mine[:rec.shape[0]] = torch.from_numpy(rec).to(dev)
+    allr = torch.empty((world * mx, width), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(allr, mine, group=group)
+    allr = allr.cpu().numpy().reshape(world, mx, width)
+    return np.concatenate([allr[r, :int(cnts_h[r])] for r in range(world)], axis=0)
