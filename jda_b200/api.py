@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjda_b200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("JDA_B200_LIB", "libjda_b200.so"))
 
 DEVICE_INPUT, RAW_HITS, NO_FINAL_TH, NO_TMA, NO_STAGE0_SCAN = 1, 2, 4, 8, 16
 

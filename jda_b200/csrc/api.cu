@@ -124,6 +124,7 @@ struct Context {
   size_t surv_cap = 0, hit_cap = 0;
   jdaB200Stats last;
   int nw = 2;
+  int stragglers = 1;
   std::vector<short> sched;
   cudaStream_t stream() const { return user_stream ? user_stream : own_stream; }
 };
@@ -185,6 +186,7 @@ bool ctx_init(Context *c) {
   CU_OK(cudaFuncSetAttribute(k2_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  CU_OK(cudaFuncSetAttribute(k2_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   const size_t s3 = k3_smem_bytes(c->m.K);
   CU_OK(cudaFuncSetAttribute(k3_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   CU_OK(cudaFuncSetAttribute(k3_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
@@ -193,6 +195,7 @@ bool ctx_init(Context *c) {
     int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) c->nw = v;
   }
+  if (const char *e = getenv("JDA_B200_STRAGGLERS")) c->stragglers = atoi(e) ? 1 : 0;
   c->sched.clear();
   if (const char *e = getenv("JDA_B200_SCHED")) {
     const char *p = e;
@@ -229,7 +232,10 @@ void ctx_free(Context *c) {
 // Per-level tile shapes.  A level runs from private shared-memory tiles when a tile of at least
 // 64 windows (with its 16-byte-padded pixel box) fits the per-warp scratch; otherwise its windows
 // read pixels from global memory in "virtual" tiles of 32 x 16 windows.
+int g_min_tile_windows = 64;
+
 void plan_level(LevelInfo &L) {
+  if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
   int best_windows = 0;
   for (int tl = 5; tl >= 3; tl--) {
     const int tw = 1 << tl;
@@ -248,7 +254,7 @@ void plan_level(LevelInfo &L) {
       L.tw_log2 = tl; L.th = th; L.box_w = bw; L.box_h = bh;
     }
   }
-  if (best_windows >= 64) {
+  if (best_windows >= g_min_tile_windows) {
     L.use_smem = 1;
   } else {
     L.use_smem = 0;
@@ -434,6 +440,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       for (int i = 0; i < g.n_levels; i++) n_smem += g.lv[i].use_smem;
       st.levels_smem = n_smem;
       P.use_tma = tma_ok ? 1 : 0;
+      P.stragglers = c->stragglers;
       if (tracing) {
         P.trace_n = c->d_trace_n.p; P.trace_s = c->d_trace_s.p;
         P.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;
@@ -443,6 +450,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       const int grid = c->sm_count;
       if (tracing) {
         if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
+        else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
         else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
       } else if (c->nw == 1) {
         k2_scan<1, false><<<grid, K2_WARPS * 32, smem, s>>>(P);

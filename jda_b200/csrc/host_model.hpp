@@ -209,14 +209,15 @@ inline long long count_windows(int w, int h, float scale, int min_size, int max_
 // c/jda.c:373-389 depend only on the node and the window size: they are folded, bit-exactly
 // (same float add, float mul, truncation, clamp), into integers per (level, node).
 //
-// Cart record, 96 bytes:
+// Cart record, 104 bytes (26 words: consecutive carts land in different banks for the lane = cart
+// reads of straggler mode):
 //   [0..56)   7 nodes x {u32 a, i32 b}
 //                tile format  : a = off1 | off2 << 16  (byte offsets inside the smem tile), b = th
 //                packed format: a = x1 | y1 << 11 | (th + 256) << 22, b = x2 | y2 << 11  (win < 2048)
 //   [56..88)  8 leaf scores (f32)
 //   [88]      cart threshold (f32)
 //   [92]      0, or 1 + index into the norm table when (mean, std) != (0, 1)
-constexpr int kCartBytes = 96;
+constexpr int kCartBytes = 104;
 
 struct Stage0Norm { float mean, std; };
 

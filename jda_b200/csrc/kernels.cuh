@@ -31,8 +31,14 @@ struct LevelInfo {
   long long win_base;   // scan-order index of the level's first window inside a frame
 };
 
-constexpr int K2_WARPS = 12;         // warps per scan block (one block per SM)
-constexpr int K2_TILE_BYTES = 8192;  // per-warp pixel tile
+#ifndef JDA_K2_WARPS
+#define JDA_K2_WARPS 12
+#endif
+#ifndef JDA_K2_TILE_BYTES
+#define JDA_K2_TILE_BYTES 8192
+#endif
+constexpr int K2_WARPS = JDA_K2_WARPS;            // warps per scan block (one block per SM)
+constexpr int K2_TILE_BYTES = JDA_K2_TILE_BYTES;  // per-warp pixel tile
 constexpr int K2_LIST_CAP = 512;     // windows per tile (fits u16 ids)
 constexpr int K2_MAX_SCHED = 32;
 
@@ -62,6 +68,7 @@ struct ScanParams {
   int n_sched;
   short sched[K2_MAX_SCHED];     // cart index at which each phase ends; last == K
   int use_tma;
+  int stragglers;                // 1: finish nearly empty tiles in cart-parallel straggler mode
   // trace (TRACE instantiation only)
   int *trace_n;
   float *trace_s;
@@ -219,111 +226,248 @@ __device__ __forceinline__ int node_test(const uint8_t *smem, uint2 n, const Pix
   }
 }
 
+// Everything scan_tile's helpers need about the current tile.
+struct TileCtx {
+  const ScanParams *P;
+  const LevelInfo *lv;
+  uint8_t *smem;
+  const Stage0Norm *norms;
+  float *lscore;
+  uint16_t *lwid;
+  const uint8_t *gbase;  // global address of the tile's first pixel
+  long long gw0;         // scan-order index of the level's first window in this frame (trace)
+  uint32_t tile_off;     // shared-memory byte offset of the tile
+  int tw_log2, tw_mask, step, pitch;
+  int x0w, y0w, cw;
+  int lane;
+};
+
+template <bool SMEM>
+__device__ __forceinline__ PixBase<SMEM> window_base(const TileCtx &c, int wid, bool alive) {
+  // dead lanes point at the tile origin: valid memory, one broadcast word
+  const int wx = alive ? (wid & c.tw_mask) : 0, wy = alive ? (wid >> c.tw_log2) : 0;
+  PixBase<SMEM> b;
+  if constexpr (SMEM) b.off = c.tile_off + (uint32_t)(wy * c.step * c.pitch + wx * c.step);
+  else b.ptr = c.gbase + (size_t)(wy * c.step) * c.P->pitch + wx * c.step;
+  return b;
+}
+
+__device__ __forceinline__ long long trace_index(const TileCtx &c, int wid) {
+  return c.gw0 + (long long)(c.y0w + (wid >> c.tw_log2)) * c.lv->nx + c.x0w + (wid & c.tw_mask);
+}
+
+// One group of 32*NWG list entries through carts [cart, cend): every lane walks the same cart
+// (uniform table reads), NWG windows per lane interleaved level by level for ILP.  Survivors are
+// squeezed to the front of the in-place list at `out` (writes never pass the read cursor).
+template <bool SMEM, int NWG, bool TRACE>
+__device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, int n, int cart, int cend,
+                                           int &out) {
+  const uint8_t *smem = c.smem;
+  const int lane = c.lane;
+  float score[NWG];
+  int wid[NWG];
+  bool alive[NWG];
+  PixBase<SMEM> pb[NWG];
+#pragma unroll
+  for (int j = 0; j < NWG; j++) {
+    const int e = base + j * 32 + lane;
+    if (ph == 0) {
+      wid[j] = e;
+      alive[j] = (e < n) && ((e & c.tw_mask) < c.cw);
+      score[j] = 0.f;
+    } else {
+      alive[j] = e < n;
+      wid[j] = alive[j] ? (int)c.lwid[e] : 0;
+      score[j] = alive[j] ? c.lscore[e] : 0.f;
+    }
+    pb[j] = window_base<SMEM>(c, wid[j], alive[j]);
+  }
+  for (int k = cart; k < cend; ++k) {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < NWG; j++) any |= alive[j];
+    if (!__any_sync(0xffffffffu, any)) break;
+    const uint32_t co = (uint32_t)k * kCartBytes;
+    const uint2 n0 = *reinterpret_cast<const uint2 *>(smem + co);
+    const float cth = *reinterpret_cast<const float *>(smem + co + 88);
+    const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + co + 92);
+    int idx[NWG];
+#pragma unroll
+    for (int j = 0; j < NWG; j++) idx[j] = node_test<SMEM>(smem, n0, pb[j], c.pitch);
+#pragma unroll
+    for (int j = 0; j < NWG; j++) {
+      const uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx[j] * 8);
+      idx[j] = 2 * idx[j] + node_test<SMEM>(smem, nd, pb[j], c.pitch);
+    }
+#pragma unroll
+    for (int j = 0; j < NWG; j++) {
+      const uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx[j] * 8);
+      idx[j] = 2 * idx[j] + node_test<SMEM>(smem, nd, pb[j], c.pitch);
+    }
+#pragma unroll
+    for (int j = 0; j < NWG; j++) {
+      const int leaf = idx[j] - kNodes;
+      float s = __fadd_rn(score[j], *reinterpret_cast<const float *>(smem + co + 56 + 4 * leaf));
+      if (nflag) {  // warp-uniform: only carts with (mean, std) != (0, 1)
+        const Stage0Norm nm = c.norms[nflag - 1];
+        s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
+      }
+      if (alive[j]) {
+        score[j] = s;
+        if constexpr (TRACE) {
+          const ScanParams &P = *c.P;
+          const long long gw = trace_index(c, wid[j]);
+          if (P.trace_leaf && gw >= P.leaf_w0 && gw < P.leaf_w1)
+            P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + k] = (uint8_t)leaf;
+          if (s < cth) {
+            if (P.trace_n) P.trace_n[gw] = k + 1;
+            if (P.trace_s) P.trace_s[gw] = s;
+          }
+        }
+        if (s < cth) {  // c/jda.c:399
+          alive[j] = false;
+          pb[j] = window_base<SMEM>(c, 0, false);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NWG; j++) {
+    const unsigned m = __ballot_sync(0xffffffffu, alive[j]);
+    if (alive[j]) {
+      const int pos = out + __popc(m & ((1u << lane) - 1u));
+      c.lwid[pos] = (uint16_t)wid[j];
+      c.lscore[pos] = score[j];
+    }
+    out += __popc(m);
+  }
+}
+
+// Straggler mode.  Once a tile is down to n <= K2_STRAGGLERS windows the parallel axis flips: for
+// each remaining window the 32 lanes walk 32 CONSECUTIVE CARTS (the shape is the constant mean
+// shape in stage 0, so the carts of a window are independent), park the 32 leaf scores in shared
+// memory, and then the running scores are replayed cart by cart with lane = window -- the same
+// sequential adds / compares as the reference, so reject cart and score bits are unchanged.  A tail
+// that would take hundreds of nearly empty warp iterations becomes a few dense chunk steps.
+// On return the list holds the windows that passed every cart; n is updated.
+constexpr int K2_STRAGGLERS = 15;
+constexpr int K2_LS_STRIDE = 33;  // conflict-free both for the lane = cart writes and lane = window reads
+static_assert(K2_STRAGGLERS * K2_LS_STRIDE <= K2_LIST_CAP, "leaf-score scratch reuses the score list");
+
+template <bool SMEM, bool TRACE>
+__device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int cart) {
+  const ScanParams &P = *c.P;
+  const uint8_t *smem = c.smem;
+  const int lane = c.lane, K = P.K;
+  bool alive = lane < n;
+  const int wid = alive ? (int)c.lwid[lane] : 0;
+  float score = alive ? c.lscore[lane] : 0.f;
+  __syncwarp();  // the score list is reused as ls[window][cart] from here on
+  float *ls = c.lscore;
+  [[maybe_unused]] uint8_t lf[K2_STRAGGLERS];
+  for (int k0 = cart; k0 < K; k0 += 32) {
+    unsigned live = __ballot_sync(0xffffffffu, alive);
+    if (!live) break;
+    const int k = min(k0 + lane, K - 1);
+    const uint32_t co = (uint32_t)k * kCartBytes;
+    const uint2 n0 = *reinterpret_cast<const uint2 *>(smem + co);
+    for (unsigned rest = live; rest; rest &= rest - 1) {
+      const int w = __ffs(rest) - 1;
+      const PixBase<SMEM> pb = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, w), true);
+      int idx = node_test<SMEM>(smem, n0, pb, c.pitch);
+      uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx * 8);
+      idx = 2 * idx + node_test<SMEM>(smem, nd, pb, c.pitch);
+      nd = *reinterpret_cast<const uint2 *>(smem + co + idx * 8);
+      idx = 2 * idx + node_test<SMEM>(smem, nd, pb, c.pitch);
+      const int leaf = idx - kNodes;
+      ls[w * K2_LS_STRIDE + lane] = *reinterpret_cast<const float *>(smem + co + 56 + 4 * leaf);
+      if constexpr (TRACE) lf[w] = (uint8_t)leaf;
+    }
+    __syncwarp();
+    const int cnt = min(32, K - k0);
+    [[maybe_unused]] int died_at = alive ? cnt : -1;  // chunk-local cart after which this lane's window stopped
+    for (int j = 0; j < cnt; j++) {
+      const uint32_t cj = (uint32_t)(k0 + j) * kCartBytes;
+      const float cth = *reinterpret_cast<const float *>(smem + cj + 88);
+      const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + cj + 92);
+      float s = __fadd_rn(score, ls[lane * K2_LS_STRIDE + j]);
+      if (nflag) {
+        const Stage0Norm nm = c.norms[nflag - 1];
+        s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
+      }
+      if (alive) {
+        score = s;
+        if (s < cth) {  // c/jda.c:399
+          alive = false;
+          if constexpr (TRACE) {
+            died_at = j;
+            const long long gw = trace_index(c, wid);
+            if (P.trace_n) P.trace_n[gw] = k0 + j + 1;
+            if (P.trace_s) P.trace_s[gw] = s;
+          }
+        }
+      }
+      if (!__any_sync(0xffffffffu, alive)) break;
+    }
+    if constexpr (TRACE) {
+      // leaves of the carts the reference would have evaluated: up to and including the rejecting one
+      if (P.trace_leaf) {
+        for (unsigned rest = live; rest; rest &= rest - 1) {
+          const int w = __ffs(rest) - 1;
+          const int dw = __shfl_sync(0xffffffffu, died_at, w);
+          const long long gw = trace_index(c, __shfl_sync(0xffffffffu, wid, w));
+          if (gw >= P.leaf_w0 && gw < P.leaf_w1 && k0 + lane < K && lane <= min(dw, cnt - 1))
+            P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + k0 + lane] = lf[w];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // compact the windows that passed every cart back into the list
+  const unsigned m = __ballot_sync(0xffffffffu, alive);
+  __syncwarp();
+  if (alive) c.lwid[__popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
+  n = __popc(m);
+  __syncwarp();
+}
+
 template <bool SMEM, int NW, bool TRACE>
 __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &lv, int li, uint8_t *smem,
                                           uint32_t norm_off, uint32_t tile_off, float *lscore,
                                           uint16_t *lwid, int frame, int x0w, int y0w, int cw, int ch,
                                           int lane) {
-  const int tw_log2 = lv.tw_log2, tw_mask = (1 << tw_log2) - 1;
-  const int step = lv.step;
-  const int pitch = SMEM ? lv.box_w : P.pitch;
-  const uint8_t *gbase = P.frames + (size_t)frame * P.frame_stride +
-                         (size_t)(y0w * step) * P.pitch + (size_t)x0w * step;
-  const Stage0Norm *norms = reinterpret_cast<const Stage0Norm *>(smem + norm_off);
-  const long long gw0 = (long long)frame * P.windows_per_frame + lv.win_base;
+  TileCtx c;
+  c.P = &P; c.lv = &lv; c.smem = smem;
+  c.norms = reinterpret_cast<const Stage0Norm *>(smem + norm_off);
+  c.lscore = lscore; c.lwid = lwid;
+  c.tw_log2 = lv.tw_log2; c.tw_mask = (1 << lv.tw_log2) - 1; c.step = lv.step;
+  c.pitch = SMEM ? lv.box_w : P.pitch;
+  c.gbase = P.frames + (size_t)frame * P.frame_stride + (size_t)(y0w * lv.step) * P.pitch + (size_t)x0w * lv.step;
+  c.gw0 = (long long)frame * P.windows_per_frame + lv.win_base;
+  c.tile_off = tile_off; c.x0w = x0w; c.y0w = y0w; c.cw = cw; c.lane = lane;
 
-  int n = ch << tw_log2;  // dense enumeration; columns >= cw are masked off in phase 0
+  int n = ch << c.tw_log2;  // dense enumeration; columns >= cw are masked off in phase 0
   int cart = 0;
   for (int ph = 0; ph < P.n_sched; ++ph) {
     const int cend = P.sched[ph];
-    int out = 0;
-    for (int base = 0; base < n; base += 32 * NW) {
-      float score[NW];
-      int wid[NW];
-      bool alive[NW];
-      PixBase<SMEM> pb[NW];
-#pragma unroll
-      for (int j = 0; j < NW; j++) {
-        const int e = base + j * 32 + lane;
-        if (ph == 0) {
-          wid[j] = e;
-          alive[j] = (e < n) && ((e & tw_mask) < cw);
-          score[j] = 0.f;
-        } else {
-          alive[j] = e < n;
-          wid[j] = alive[j] ? (int)lwid[e] : 0;
-          score[j] = alive[j] ? lscore[e] : 0.f;
-        }
-        // dead lanes point at the tile origin: valid memory, one broadcast word
-        const int wx = alive[j] ? (wid[j] & tw_mask) : 0, wy = alive[j] ? (wid[j] >> tw_log2) : 0;
-        if constexpr (SMEM) pb[j].off = tile_off + (uint32_t)(wy * step * pitch + wx * step);
-        else pb[j].ptr = gbase + (size_t)(wy * step) * P.pitch + wx * step;
-      }
-      for (int k = cart; k < cend; ++k) {
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < NW; j++) any |= alive[j];
-        if (!__any_sync(0xffffffffu, any)) break;
-        const uint32_t co = (uint32_t)k * kCartBytes;
-        const uint2 n0 = *reinterpret_cast<const uint2 *>(smem + co);
-        const float cth = *reinterpret_cast<const float *>(smem + co + 88);
-        const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + co + 92);
-        int idx[NW];
-#pragma unroll
-        for (int j = 0; j < NW; j++) idx[j] = node_test<SMEM>(smem, n0, pb[j], pitch);
-#pragma unroll
-        for (int j = 0; j < NW; j++) {
-          const uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx[j] * 8);
-          idx[j] = 2 * idx[j] + node_test<SMEM>(smem, nd, pb[j], pitch);
-        }
-#pragma unroll
-        for (int j = 0; j < NW; j++) {
-          const uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx[j] * 8);
-          idx[j] = 2 * idx[j] + node_test<SMEM>(smem, nd, pb[j], pitch);
-        }
-#pragma unroll
-        for (int j = 0; j < NW; j++) {
-          const int leaf = idx[j] - kNodes;
-          float s = __fadd_rn(score[j], *reinterpret_cast<const float *>(smem + co + 56 + 4 * leaf));
-          if (nflag) {  // warp-uniform: only carts with (mean, std) != (0, 1)
-            const Stage0Norm nm = norms[nflag - 1];
-            s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
-          }
-          if (alive[j]) {
-            score[j] = s;
-            if constexpr (TRACE) {
-              const long long gw = gw0 + (long long)(y0w + (wid[j] >> tw_log2)) * lv.nx + x0w + (wid[j] & tw_mask);
-              if (P.trace_leaf && gw >= P.leaf_w0 && gw < P.leaf_w1)
-                P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + k] = (uint8_t)leaf;
-              if (s < cth) {
-                if (P.trace_n) P.trace_n[gw] = k + 1;
-                if (P.trace_s) P.trace_s[gw] = s;
-              }
-            }
-            if (s < cth) {  // c/jda.c:399
-              alive[j] = false;
-              if constexpr (SMEM) pb[j].off = tile_off;
-              else pb[j].ptr = gbase;
-            }
-          }
-        }
-      }
-      // squeeze survivors to the front of the list (writes never pass the read cursor)
-#pragma unroll
-      for (int j = 0; j < NW; j++) {
-        const unsigned m = __ballot_sync(0xffffffffu, alive[j]);
-        if (alive[j]) {
-          const int pos = out + __popc(m & ((1u << lane) - 1u));
-          lwid[pos] = (uint16_t)wid[j];
-          lscore[pos] = score[j];
-        }
-        out += __popc(m);
-      }
+    int out = 0, base = 0;
+    // full groups of NW packets, then the remainder with as few packets as it needs
+    for (; n - base >= 32 * NW; base += 32 * NW) scan_group<SMEM, NW, TRACE>(c, ph, base, n, cart, cend, out);
+    if constexpr (NW >= 4) {
+      if (n - base > 64) { scan_group<SMEM, 4, TRACE>(c, ph, base, n, cart, cend, out); base = n; }
     }
+    if constexpr (NW >= 2) {
+      if (n - base > 32) { scan_group<SMEM, 2, TRACE>(c, ph, base, n, cart, cend, out); base = n; }
+    }
+    if (n - base > 0) scan_group<SMEM, 1, TRACE>(c, ph, base, n, cart, cend, out);
     __syncwarp();
     n = out;
     cart = cend;
     if (n == 0) break;
+    if (n <= K2_STRAGGLERS && cart < P.K && P.stragglers) {
+      straggler_tail<SMEM, TRACE>(c, n, cart);
+      break;
+    }
   }
   // windows that passed every cart of stage 0
   for (int base = 0; base < n; base += 32) {
@@ -337,7 +481,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
       const unsigned slot = slot0 + __popc(m & ((1u << lane) - 1u));
       const int w = lwid[e];
       if (slot < P.surv_cap)
-        P.surv[slot] = make_uint2((unsigned)frame, pack_key(li, y0w + (w >> tw_log2), x0w + (w & tw_mask)));
+        P.surv[slot] = make_uint2((unsigned)frame, pack_key(li, y0w + (w >> c.tw_log2), x0w + (w & c.tw_mask)));
     }
   }
   __syncwarp();

@@ -89,9 +89,12 @@ def test_trace_generic_kernel_only(casc, oracle, oracle_shipped):
     np.testing.assert_array_equal(lv, olv)
 
 
+@pytest.mark.parametrize("stragglers", ["1", "0"])
 @pytest.mark.parametrize("nw", ["1", "2", "4"])
-def test_windows_per_lane_variants(oracle, oracle_shipped, nw):
+def test_scan_kernel_variants(oracle, oracle_shipped, nw, stragglers):
+    """windows per lane (ILP width) and straggler mode on/off are scheduling choices only."""
     os.environ["JDA_B200_NW"] = nw
+    os.environ["JDA_B200_STRAGGLERS"] = stragglers
     try:
         c = api.Cascador(SHIPPED_F32, double=False)
         img = synth.facemix_frame(9)
@@ -100,9 +103,18 @@ def test_windows_per_lane_variants(oracle, oracle_shipped, nw):
         ob, osc, osh, st = oracle.detect_raw(oracle_shipped, img, use_th=False)
         _same(raw, (ob, osc, osh))
         assert c.last_stats["stage0_survivors"] == st["stage_survivors"][0]
+        for im in (img, synth.noise_frame(3, 200, 150)):
+            nwin = api.count_windows(im.shape[1], im.shape[0])
+            rng = (max(0, nwin - 6000), nwin)
+            tn, ts, lv = c.trace(im, leaf_range=rng)
+            on, os_, olv = oracle.trace(oracle_shipped, im, leaf_range=rng)
+            np.testing.assert_array_equal(tn, on)
+            np.testing.assert_array_equal(_bits(ts), _bits(os_))
+            np.testing.assert_array_equal(lv, olv)
         c.close()
     finally:
         del os.environ["JDA_B200_NW"]
+        del os.environ["JDA_B200_STRAGGLERS"]
 
 
 # ---- synthetic models: deep survivors, normalised scores, scaled (h/q) nodes --------------------
