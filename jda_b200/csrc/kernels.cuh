@@ -364,6 +364,7 @@ __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int car
   float score = alive ? c.lscore[lane] : 0.f;
   __syncwarp();  // the score list is reused as ls[window][cart] from here on
   float *ls = c.lscore;
+  const int lrow = (lane < K2_STRAGGLERS ? lane : 0) * K2_LS_STRIDE;
   [[maybe_unused]] uint8_t lf[K2_STRAGGLERS];
   for (int k0 = cart; k0 < K; k0 += 32) {
     unsigned live = __ballot_sync(0xffffffffu, alive);
@@ -390,7 +391,7 @@ __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int car
       const uint32_t cj = (uint32_t)(k0 + j) * kCartBytes;
       const float cth = *reinterpret_cast<const float *>(smem + cj + 88);
       const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + cj + 92);
-      float s = __fadd_rn(score, ls[lane * K2_LS_STRIDE + j]);
+      float s = __fadd_rn(score, ls[lrow + j]);  // lanes past the stragglers re-read row 0 (in bounds)
       if (nflag) {
         const Stage0Norm nm = c.norms[nflag - 1];
         s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
