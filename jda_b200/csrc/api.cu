@@ -113,7 +113,9 @@ struct Context {
   Stage0Norm *d_norms = nullptr;
   // scratch
   DevBuf<uint8_t> d_frames, d_hq, d_trace_leaf;
-  DevBuf<uint2> d_surv;
+  DevBuf<uint4> d_surv;
+  DevBuf<float> d_shape0;
+  DevBuf<uint8_t> d_tables_packed;
   DevBuf<float> d_hits;
   DevBuf<int> d_trace_n;
   DevBuf<float> d_trace_s;
@@ -123,7 +125,7 @@ struct Context {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t surv_cap = 0, hit_cap = 0;
   jdaB200Stats last;
-  int nw = 2;
+  int nw = 4;
   int stragglers = 1;
   std::vector<short> sched;
   cudaStream_t stream() const { return user_stream ? user_stream : own_stream; }
@@ -132,6 +134,9 @@ struct Context {
 constexpr int kCntSurv = kMaxLevels, kCntHit = kMaxLevels + 1, kCntTotal = kMaxLevels + 2;
 
 size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * sizeof(WarpScratch); }
+size_t k3s_smem_bytes(int K, int D) {
+  return (size_t)K3S_COHORT * ((K + 15) & ~15) + (size_t)2 * K3S_CHUNK * kLeaves * D * 4;
+}
 size_t k3_smem_bytes(int K) { return (size_t)K3_WARPS * (kMaxDim * 4 + ((K + 15) & ~15)); }
 
 bool ctx_init(Context *c) {
@@ -187,6 +192,8 @@ bool ctx_init(Context *c) {
   CU_OK(cudaFuncSetAttribute(k2_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  CU_OK(cudaFuncSetAttribute(k3_stage0, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)k3s_smem_bytes(c->m.K, c->m.D())));
   const size_t s3 = k3_smem_bytes(c->m.K);
   CU_OK(cudaFuncSetAttribute(k3_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   CU_OK(cudaFuncSetAttribute(k3_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
@@ -222,7 +229,7 @@ void ctx_free(Context *c) {
     cudaFree(c->d_norms); cudaFree(c->d_counters);
     cudaFreeHost(c->h_counters);
     c->d_tables.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
-    c->d_surv.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
+    c->d_surv.release(); c->d_shape0.release(); c->d_tables_packed.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
   }
@@ -305,6 +312,12 @@ bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int ma
                          tab.data() + (size_t)i * g.table_bytes, norms);
     if (!c->d_tables.ensure(tab.size())) return false;
     CU_OK(cudaMemcpyAsync(c->d_tables.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, c->stream()));
+    // the same tables in packed-coordinate form for every level: k3_stage0 reads pixels from global memory
+    std::vector<uint8_t> tabp((size_t)n * g.table_bytes, 0);
+    Stage0Norm norms2[kMaxNorm];
+    for (int i = 0; i < n; i++) build_stage0_table(c->m, g.lv[i].win, 0, tabp.data() + (size_t)i * g.table_bytes, norms2);
+    if (!c->d_tables_packed.ensure(tabp.size())) return false;
+    CU_OK(cudaMemcpyAsync(c->d_tables_packed.p, tabp.data(), tabp.size(), cudaMemcpyHostToDevice, c->stream()));
     CU_OK(cudaMemcpyAsync(c->d_norms, norms, sizeof norms, cudaMemcpyHostToDevice, c->stream()));
     CU_OK(cudaStreamSynchronize(c->stream()));
   }
@@ -406,6 +419,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
 
   for (int attempt = 0; attempt < 4; attempt++) {
     if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * rec_words)) return false;
+    if (use_scan && !c->d_shape0.ensure(c->surv_cap * D)) return false;
     CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
     CU_OK(cudaEventRecord(c->ev[2], s));
     if (use_scan) {
@@ -463,6 +477,19 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       st.scan_launches++;
     }
     CU_OK(cudaEventRecord(c->ev[3], s));
+    if (use_scan) {  // stage 0 of the survivors: leaves + regression gather, cohort-staged
+      Stage0Params S;
+      memset(&S, 0, sizeof S);
+      S.frames = d_frames; S.frame_stride = fstride; S.pitch = pitch;
+      S.tables_packed = c->d_tables_packed.p; S.table_bytes = g.table_bytes;
+      S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
+      for (int i = 0; i < g.n_levels; i++) S.lv_step[i] = g.lv[i].step;
+      S.surv = c->d_surv.p; S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)c->surv_cap;
+      S.out_shape = c->d_shape0.p;
+      k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), s>>>(S);
+      CU_OK(cudaGetLastError());
+      st.cascade_launches++;
+    }
     {
       CascadeParams Q;
       memset(&Q, 0, sizeof Q);
@@ -478,6 +505,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       Q.windows_per_frame = g.windows_per_frame;
       Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
       Q.dense = use_scan ? 0 : 1; Q.dense_total = total_windows;
+      Q.t_start = use_scan ? 1 : 0; Q.init_shape = use_scan ? c->d_shape0.p : nullptr;
       Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
       Q.rec_words = rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
       if (tracing) {

@@ -61,7 +61,7 @@ struct ScanParams {
   const uint8_t *tables;         // n_levels x table_bytes (padded to 128)
   const Stage0Norm *norms;       // kMaxNorm entries
   unsigned *tile_counters;       // [n_levels] work-stealing counters
-  uint2 *surv;                   // stage-0 survivors: {frame, level<<26 | yi<<13 | xi}
+  uint4 *surv;                   // stage-0 survivors: {frame, level<<26 | yi<<13 | xi, score bits, 0}
   unsigned *surv_count;
   unsigned surv_cap;
   long long windows_per_frame;
@@ -95,9 +95,11 @@ struct CascadeParams {
   int lv_win[kMaxLevels], lv_step[kMaxLevels], lv_nx[kMaxLevels], lv_ny[kMaxLevels];
   long long lv_base[kMaxLevels];
   long long windows_per_frame;
-  const uint2 *surv;
+  const uint4 *surv;
   const unsigned *surv_count;
   unsigned surv_cap;
+  const float *init_shape;  // [surv_cap][2L] shapes after stage 0 (from k3_stage0) when t_start == 1
+  int t_start;              // 0: start from the mean shape; 1: stage 0 already done for every queue entry
   int dense;           // 1: enumerate every window of every frame instead of reading `surv`
   long long dense_total;
   float *hits;         // records of rec_words 4-byte words
@@ -427,7 +429,10 @@ __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int car
   // compact the windows that passed every cart back into the list
   const unsigned m = __ballot_sync(0xffffffffu, alive);
   __syncwarp();
-  if (alive) c.lwid[__popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
+  if (alive) {
+    c.lwid[__popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
+    c.lscore[__popc(m & ((1u << lane) - 1u))] = score;  // the leaf-score scratch is free again
+  }
   n = __popc(m);
   __syncwarp();
 }
@@ -482,7 +487,8 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
       const unsigned slot = slot0 + __popc(m & ((1u << lane) - 1u));
       const int w = lwid[e];
       if (slot < P.surv_cap)
-        P.surv[slot] = make_uint2((unsigned)frame, pack_key(li, y0w + (w >> c.tw_log2), x0w + (w & c.tw_mask)));
+        P.surv[slot] = make_uint4((unsigned)frame, pack_key(li, y0w + (w >> c.tw_log2), x0w + (w & c.tw_mask)),
+                                  __float_as_uint(lscore[e]), 0u);
     }
   }
   __syncwarp();
@@ -580,6 +586,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
   const long long total = P.dense ? P.dense_total : (long long)min(*P.surv_count, P.surv_cap);
   for (long long e = (long long)blockIdx.x * K3_WARPS + warp; e < total; e += (long long)gridDim.x * K3_WARPS) {
     int frame, level, xi, yi;
+    float score0 = 0.f;
     if (P.dense) {
       frame = (int)(e / P.windows_per_frame);
       long long r = e - (long long)frame * P.windows_per_frame;
@@ -589,8 +596,9 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
       yi = (int)(r / P.lv_nx[level]);
       xi = (int)(r - (long long)yi * P.lv_nx[level]);
     } else {
-      const uint2 s = P.surv[e];
+      const uint4 s = P.surv[e];
       frame = (int)s.x;
+      score0 = __uint_as_float(s.z);
       level = (int)(s.y >> 26);
       yi = (int)((s.y >> 13) & 0x1fff);
       xi = (int)(s.y & 0x1fff);
@@ -608,13 +616,14 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
     const bool trace_leaf = TRACE && P.trace_leaf && gw >= P.leaf_w0 && gw < P.leaf_w1;
 
     __syncwarp();
-    for (int i = lane; i < D; i += 32) shape[i] = P.mean_shape[i];
+    const bool resumed = !P.dense && P.t_start > 0;
+    for (int i = lane; i < D; i += 32) shape[i] = resumed ? P.init_shape[(size_t)e * D + i] : P.mean_shape[i];
     __syncwarp();
 
-    float score = 0.f;
-    int n_eval = 0;
+    float score = resumed ? score0 : 0.f;
+    int n_eval = resumed ? P.t_start * P.K : 0;
     bool rejected = false;
-    for (int t = 0; t < P.t_run && !rejected; t++) {
+    for (int t = resumed ? P.t_start : 0; t < P.t_run && !rejected; t++) {
       for (int kc = 0; kc < P.K && !rejected; kc += 32) {
         const int k = kc + lane;
         float ls = 0.f;
@@ -708,6 +717,135 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
         rec[5] = score;
       }
       for (int i = lane; i < D; i += 32) rec[kHitHeader + i] = shape[i];
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------ k3_stage0
+//
+// Stage 0 for the survivors of k2_scan: they are known to pass every cart of the stage and k2 has
+// their exit score, so only two things are left -- the K leaf indices and the regression gather
+//   shape = mean_shape + sum_k w[0][8k + leaf_k]        (k ascending, c/jda.c:403-411).
+// Leaves come from the packed stage-0 LUT of the window's level (integer offsets, L1-resident).
+// The gather is the expensive part: 8K rows x 2L floats stream from L2 per survivor if done naively
+// (that made k3_cascade L2-bound in profiles/r1_v1).  Here a block takes a cohort of 32 survivors and
+// stages w[0] through shared memory 8 carts (64 rows) at a time with cp.async double buffering, so
+// each byte of w[0] is fetched once per cohort instead of once per survivor.
+constexpr int K3S_WARPS = 8;
+constexpr int K3S_PER_WARP = 4;
+constexpr int K3S_COHORT = K3S_WARPS * K3S_PER_WARP;
+constexpr int K3S_CHUNK = 8;  // carts staged per step
+
+struct Stage0Params {
+  const uint8_t *frames;
+  size_t frame_stride;
+  int pitch;
+  const uint8_t *tables_packed;  // [n_levels][table_bytes], packed-coordinate format
+  int table_bytes;
+  const float *w0;               // w[0]: [8K][2L]
+  const float *mean_shape;
+  int K, L;
+  int lv_step[kMaxLevels];
+  const uint4 *surv;
+  const unsigned *surv_count;
+  unsigned surv_cap;
+  float *out_shape;              // [surv_cap][2L]
+};
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constant__ Stage0Params P) {
+  extern __shared__ __align__(16) uint8_t smem0[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = 2 * P.L, K = P.K;
+  const int kpad = (K + 15) & ~15;
+  const int chunk_floats = K3S_CHUNK * kLeaves * D;
+  uint8_t *leaves = smem0;                                                   // [cohort][kpad]
+  float *rows = reinterpret_cast<float *>(smem0 + (size_t)K3S_COHORT * kpad);  // [2][chunk_floats]
+  const int total = (int)min(*P.surv_count, P.surv_cap);
+  const int n_chunks = (K + K3S_CHUNK - 1) / K3S_CHUNK;
+
+  for (int c0 = blockIdx.x * K3S_COHORT; c0 < total; c0 += gridDim.x * K3S_COHORT) {
+    // ---- leaves of my K3S_PER_WARP survivors
+    for (int s = 0; s < K3S_PER_WARP; s++) {
+      const int e = c0 + warp * K3S_PER_WARP + s;
+      if (e >= total) break;
+      const uint4 q = P.surv[e];
+      const int level = (int)(q.y >> 26), yi = (int)((q.y >> 13) & 0x1fff), xi = (int)(q.y & 0x1fff);
+      const int step = P.lv_step[level];
+      PixBase<false> pb;
+      pb.ptr = P.frames + (size_t)q.x * P.frame_stride + (size_t)(yi * step) * P.pitch + (size_t)xi * step;
+      const uint8_t *tab = P.tables_packed + (size_t)level * P.table_bytes;
+      uint8_t *lf = leaves + (size_t)(warp * K3S_PER_WARP + s) * kpad;
+      for (int k = lane; k < K; k += 32) {
+        const uint2 *nd = reinterpret_cast<const uint2 *>(tab + (size_t)k * kCartBytes);
+        int idx = node_test<false>(nullptr, __ldg(nd), pb, P.pitch);
+        idx = 2 * idx + node_test<false>(nullptr, __ldg(nd + idx), pb, P.pitch);
+        idx = 2 * idx + node_test<false>(nullptr, __ldg(nd + idx), pb, P.pitch);
+        lf[k] = (uint8_t)(idx - kNodes);
+      }
+    }
+    // ---- regression gather over staged chunks of w[0]
+    float2 acc[K3S_PER_WARP][2];
+#pragma unroll
+    for (int s = 0; s < K3S_PER_WARP; s++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int p = lane + 32 * h;
+        acc[s][h] = (2 * p + 1 < D) ? make_float2(P.mean_shape[2 * p], P.mean_shape[2 * p + 1]) : make_float2(0.f, 0.f);
+      }
+    auto stage = [&](int ci, int buf) {
+      const int carts = min(K3S_CHUNK, K - ci * K3S_CHUNK);
+      const int n16 = carts * kLeaves * D / 4;  // 16-byte pieces
+      const float4 *src = reinterpret_cast<const float4 *>(P.w0 + (size_t)ci * chunk_floats);
+      float4 *dst = reinterpret_cast<float4 *>(rows + (size_t)buf * chunk_floats);
+      for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async16(dst + i, src + i);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, 0);
+    for (int ci = 0; ci < n_chunks; ci++) {
+      if (ci + 1 < n_chunks) {
+        stage(ci + 1, (ci + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();  // chunk ci landed for everyone (and, first time round, the leaves are written)
+      const float *rb = rows + (size_t)(ci & 1) * chunk_floats;
+      const int carts = min(K3S_CHUNK, K - ci * K3S_CHUNK);
+      for (int cl = 0; cl < carts; cl++) {
+        const int k = ci * K3S_CHUNK + cl;
+#pragma unroll
+        for (int s = 0; s < K3S_PER_WARP; s++) {
+          if (c0 + warp * K3S_PER_WARP + s >= total) continue;  // no survivor in this seat: its leaves are stale
+          const int leaf = leaves[(size_t)(warp * K3S_PER_WARP + s) * kpad + k];
+          const float2 *row = reinterpret_cast<const float2 *>(rb + (size_t)(cl * kLeaves + leaf) * D);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int p = lane + 32 * h;
+            if (2 * p + 1 < D) {
+              const float2 v = row[p];
+              acc[s][h].x = __fadd_rn(acc[s][h].x, v.x);
+              acc[s][h].y = __fadd_rn(acc[s][h].y, v.y);
+            }
+          }
+        }
+      }
+      __syncthreads();  // everyone is done with buffer ci & 1 before it is refilled
+    }
+#pragma unroll
+    for (int s = 0; s < K3S_PER_WARP; s++) {
+      const int e = c0 + warp * K3S_PER_WARP + s;
+      if (e < total) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int p = lane + 32 * h;
+          if (2 * p + 1 < D) reinterpret_cast<float2 *>(P.out_shape + (size_t)e * D)[p] = acc[s][h];
+        }
+      }
     }
   }
 }
