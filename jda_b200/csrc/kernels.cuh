@@ -294,6 +294,7 @@ __device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, i
     const float cth = *reinterpret_cast<const float *>(smem + co + 88);
     const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + co + 92);
     int idx[NWG];
+    float s[NWG];
 #pragma unroll
     for (int j = 0; j < NWG; j++) idx[j] = node_test<SMEM>(smem, n0, pb[j], c.pitch);
 #pragma unroll
@@ -306,31 +307,36 @@ __device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, i
       const uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx[j] * 8);
       idx[j] = 2 * idx[j] + node_test<SMEM>(smem, nd, pb[j], c.pitch);
     }
+    // leaf = idx - 7; leaf scores start at byte 56 of the cart record
 #pragma unroll
-    for (int j = 0; j < NWG; j++) {
-      const int leaf = idx[j] - kNodes;
-      float s = __fadd_rn(score[j], *reinterpret_cast<const float *>(smem + co + 56 + 4 * leaf));
-      if (nflag) {  // warp-uniform: only carts with (mean, std) != (0, 1)
-        const Stage0Norm nm = c.norms[nflag - 1];
-        s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
-      }
-      if (alive[j]) {
-        score[j] = s;
-        if constexpr (TRACE) {
-          const ScanParams &P = *c.P;
+    for (int j = 0; j < NWG; j++)
+      s[j] = __fadd_rn(score[j], *reinterpret_cast<const float *>(smem + co + (56 - 4 * kNodes) + 4 * idx[j]));
+    if (nflag) {  // warp-uniform and rare: only carts with (mean, std) != (0, 1)
+      const Stage0Norm nm = c.norms[nflag - 1];
+#pragma unroll
+      for (int j = 0; j < NWG; j++) s[j] = __fdiv_rn(__fsub_rn(s[j], nm.mean), nm.std);
+    }
+    if constexpr (TRACE) {
+      const ScanParams &P = *c.P;
+#pragma unroll
+      for (int j = 0; j < NWG; j++) {
+        if (alive[j]) {
           const long long gw = trace_index(c, wid[j]);
           if (P.trace_leaf && gw >= P.leaf_w0 && gw < P.leaf_w1)
-            P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + k] = (uint8_t)leaf;
-          if (s < cth) {
+            P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + k] = (uint8_t)(idx[j] - kNodes);
+          if (s[j] < cth) {
             if (P.trace_n) P.trace_n[gw] = k + 1;
-            if (P.trace_s) P.trace_s[gw] = s;
+            if (P.trace_s) P.trace_s[gw] = s[j];
           }
         }
-        if (s < cth) {  // c/jda.c:399
-          alive[j] = false;
-          pb[j] = window_base<SMEM>(c, 0, false);
-        }
       }
+    }
+    // c/jda.c:399 -- branch-free: a rejected lane keeps walking its (valid) window until the phase ends,
+    // its score is never read again
+#pragma unroll
+    for (int j = 0; j < NWG; j++) {
+      score[j] = s[j];
+      alive[j] = alive[j] && !(s[j] < cth);
     }
   }
 #pragma unroll
@@ -675,7 +681,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
           const float mj = __shfl_sync(0xffffffffu, cp.y, j);
           const float dj = __shfl_sync(0xffffffffu, cp.z, j);
           score = __fadd_rn(score, sj);                      // c/jda.c:396
-          score = __fdiv_rn(__fsub_rn(score, mj), dj);       // c/jda.c:397
+          // c/jda.c:397; (score - 0) / 1 is score exactly, so the divide only runs where it matters
+          if (mj != 0.f || dj != 1.f) score = __fdiv_rn(__fsub_rn(score, mj), dj);
           n_eval++;
           if (score < thj) { stop = j; break; }              // c/jda.c:399
         }
@@ -769,23 +776,36 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
   const int n_chunks = (K + K3S_CHUNK - 1) / K3S_CHUNK;
 
   for (int c0 = blockIdx.x * K3S_COHORT; c0 < total; c0 += gridDim.x * K3S_COHORT) {
-    // ---- leaves of my K3S_PER_WARP survivors
-    for (int s = 0; s < K3S_PER_WARP; s++) {
-      const int e = c0 + warp * K3S_PER_WARP + s;
-      if (e >= total) break;
-      const uint4 q = P.surv[e];
-      const int level = (int)(q.y >> 26), yi = (int)((q.y >> 13) & 0x1fff), xi = (int)(q.y & 0x1fff);
-      const int step = P.lv_step[level];
-      PixBase<false> pb;
-      pb.ptr = P.frames + (size_t)q.x * P.frame_stride + (size_t)(yi * step) * P.pitch + (size_t)xi * step;
-      const uint8_t *tab = P.tables_packed + (size_t)level * P.table_bytes;
-      uint8_t *lf = leaves + (size_t)(warp * K3S_PER_WARP + s) * kpad;
+    // ---- leaves of my K3S_PER_WARP survivors: the walks are interleaved (independent load chains)
+    {
+      PixBase<false> pb[K3S_PER_WARP];
+      const uint8_t *tab[K3S_PER_WARP];
+      bool ok[K3S_PER_WARP];
+#pragma unroll
+      for (int s = 0; s < K3S_PER_WARP; s++) {
+        const int e = c0 + warp * K3S_PER_WARP + s;
+        ok[s] = e < total;
+        const uint4 q = P.surv[ok[s] ? e : c0];
+        const int level = (int)(q.y >> 26), yi = (int)((q.y >> 13) & 0x1fff), xi = (int)(q.y & 0x1fff);
+        const int step = P.lv_step[level];
+        pb[s].ptr = P.frames + (size_t)q.x * P.frame_stride + (size_t)(yi * step) * P.pitch + (size_t)xi * step;
+        tab[s] = P.tables_packed + (size_t)level * P.table_bytes;
+      }
       for (int k = lane; k < K; k += 32) {
-        const uint2 *nd = reinterpret_cast<const uint2 *>(tab + (size_t)k * kCartBytes);
-        int idx = node_test<false>(nullptr, __ldg(nd), pb, P.pitch);
-        idx = 2 * idx + node_test<false>(nullptr, __ldg(nd + idx), pb, P.pitch);
-        idx = 2 * idx + node_test<false>(nullptr, __ldg(nd + idx), pb, P.pitch);
-        lf[k] = (uint8_t)(idx - kNodes);
+        int idx[K3S_PER_WARP];
+        const uint2 *nd[K3S_PER_WARP];
+#pragma unroll
+        for (int s = 0; s < K3S_PER_WARP; s++) {
+          nd[s] = reinterpret_cast<const uint2 *>(tab[s] + (size_t)k * kCartBytes);
+          idx[s] = node_test<false>(nullptr, __ldg(nd[s]), pb[s], P.pitch);
+        }
+#pragma unroll
+        for (int s = 0; s < K3S_PER_WARP; s++) idx[s] = 2 * idx[s] + node_test<false>(nullptr, __ldg(nd[s] + idx[s]), pb[s], P.pitch);
+#pragma unroll
+        for (int s = 0; s < K3S_PER_WARP; s++) idx[s] = 2 * idx[s] + node_test<false>(nullptr, __ldg(nd[s] + idx[s]), pb[s], P.pitch);
+#pragma unroll
+        for (int s = 0; s < K3S_PER_WARP; s++)
+          if (ok[s]) leaves[(size_t)(warp * K3S_PER_WARP + s) * kpad + k] = (uint8_t)(idx[s] - kNodes);
       }
     }
     // ---- regression gather over staged chunks of w[0]

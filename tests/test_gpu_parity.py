@@ -62,6 +62,8 @@ TRACE_FRAMES = {
     "blur": lambda: synth.blur_frame(1),
     "faces": lambda: synth.face_canvas(),
     "odd_size": lambda: synth.facemix_frame(4, 451, 333),
+    "narrow": lambda: synth.facemix_frame(6, 60, 300),      # few windows per row: 8-wide tiles
+    "wide": lambda: synth.facemix_frame(8, 400, 64),
 }
 
 
