@@ -135,6 +135,11 @@ JDA_API long long jdaB200CountWindows(int width, int height, float scale, int mi
 /* the greedy NMS of c/jda.c:237-316: keep[i] = 1 for survivors (scan order preserved) */
 JDA_API void jdaB200Nms(int n, const int *bboxes, const float *scores, unsigned char *keep);
 
+/* The scan kernel's tile plan for a (w, h) frame, one text line per pyramid level:
+ * "win step nx ny tw th box_w box_h smem windows".  Returns the number of levels (host only). */
+JDA_API int jdaB200DescribePlan(int width, int height, float scale, int min_size, int max_size,
+                                char *buf, int cap);
+
 /* ---- per-window trace (tests): scan order, one frame ------------------------------------- */
 /* Runs the full device path on one host frame and records, for every candidate window, the
  * number of carts evaluated and the score at exit; for windows [leaf_w0, leaf_w1) also the leaf

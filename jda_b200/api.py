@@ -87,6 +87,8 @@ def lib():
     L.jdaB200Levels.argtypes = [ci, ci, cf, ci, ci, C.POINTER(ci), ci]
     L.jdaB200CountWindows.restype = C.c_longlong
     L.jdaB200CountWindows.argtypes = [ci, ci, cf, ci, ci]
+    L.jdaB200DescribePlan.restype = ci
+    L.jdaB200DescribePlan.argtypes = [ci, ci, cf, ci, ci, C.c_char_p, ci]
     L.jdaB200Nms.restype = None
     L.jdaB200Nms.argtypes = [ci, C.POINTER(ci), C.POINTER(cf), ub]
     L.jdaB200Trace.restype = C.c_longlong
@@ -102,7 +104,7 @@ EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSeri
            "jdaCascadorRelease", "jdaDetect", "jdaResultRelease", "jdaB200DetectBatch",
            "jdaB200SetDevice", "jdaB200SetStream", "jdaB200ModelDims", "jdaB200LastError",
            "jdaB200DeviceCount", "jdaB200Levels", "jdaB200CountWindows", "jdaB200Nms",
-           "jdaB200Trace", "jdaB200Resize"]
+           "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan"]
 
 
 def last_error():
@@ -121,6 +123,14 @@ def levels(w, h, scale=1.25, min_size=24, max_size=-1):
 
 def count_windows(w, h, scale=1.25, min_size=24, max_size=-1):
     return int(lib().jdaB200CountWindows(w, h, scale, min_size, max_size))
+
+
+def describe_plan(w, h, scale=1.25, min_size=24, max_size=-1):
+    """scan-kernel tile plan: list of dicts per level (host only)."""
+    buf = C.create_string_buffer(4096)
+    lib().jdaB200DescribePlan(w, h, scale, min_size, max_size, buf, 4096)
+    keys = ["win", "step", "nx", "ny", "tw", "th", "box_w", "box_h", "smem", "windows"]
+    return [dict(zip(keys, map(int, ln.split()))) for ln in buf.value.decode().splitlines()]
 
 
 def nms(boxes, scores):

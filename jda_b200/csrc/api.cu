@@ -236,32 +236,83 @@ void ctx_free(Context *c) {
   delete c;
 }
 
-// Per-level tile shapes.  A level runs from private shared-memory tiles when a tile of at least
-// 64 windows (with its 16-byte-padded pixel box) fits the per-warp scratch; otherwise its windows
-// read pixels from global memory in "virtual" tiles of 32 x 16 windows.
-int g_min_tile_windows = 64;
+// Expected shared-memory wavefronts of one pixel read (1 = conflict free) for packets of 32 survivors
+// drawn in row-major order from a tw x th tile at a few survival densities.  Bank = (byte address / 4)
+// mod 32; lanes on the same word broadcast, lanes on different words of one bank serialise.  The tile
+// pitch decides how the rows of a tile fold onto the 32 banks (tools/sim_banks.py has the long version).
+double estimate_wavefronts(int win, int step, int tw, int th, int pitch) {
+  uint32_t rng = 12345u;
+  auto next = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+  const double dens[3] = {0.7, 0.4, 0.2};
+  double tot = 0;
+  int cnt = 0;
+  for (double rho : dens) {
+    for (int trial = 0; trial < 12; trial++) {
+      int base[32], nb = 0;
+      int start = (int)(next() % (uint32_t)(tw * th));
+      for (int i = 0; i < tw * th && nb < 32; i++) {
+        const int w = (start + i) % (tw * th);
+        if ((next() & 0xffff) < (uint32_t)(rho * 65536)) base[nb++] = (w / tw) * step * pitch + (w % tw) * step;
+      }
+      if (nb < 8) continue;
+      for (int o = 0; o < 4; o++) {
+        const int off = (int)(next() % (uint32_t)win) * pitch + (int)(next() % (uint32_t)win);
+        int worst = 0;
+        for (int bnk = 0; bnk < 32; bnk++) {
+          int words[32], nw = 0;
+          for (int l = 0; l < nb; l++) {
+            const int wd = (base[l] + off) >> 2;
+            if ((wd & 31) != bnk) continue;
+            bool seen = false;
+            for (int q = 0; q < nw; q++) seen |= (words[q] == wd);
+            if (!seen) words[nw++] = wd;
+          }
+          worst = std::max(worst, nw);
+        }
+        tot += worst;
+        cnt++;
+      }
+    }
+  }
+  return cnt ? tot / cnt : 1.0;
+}
 
+int g_min_tile_windows = 64;
+int g_tune_pitch = 1;
+
+// Per-level tile shapes.  A level runs from private shared-memory tiles when a tile of at least
+// 64 windows (with its 16-byte-granular pixel box) fits the per-warp scratch; otherwise its windows
+// read pixels from global memory in "virtual" tiles of 32 x 16 windows.  Among the shapes that fit,
+// the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
+// pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
 void plan_level(LevelInfo &L) {
   if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
+  if (const char *e = getenv("JDA_B200_TUNE_PITCH")) g_tune_pitch = atoi(e);
+  double best_cost = 1e30;
   int best_windows = 0;
   for (int tl = 5; tl >= 3; tl--) {
     const int tw = 1 << tl;
-    const int bw = (((tw - 1) * L.step + L.win) + 15) & ~15;
-    if (bw > 256) continue;
-    const int bh_max = std::min(256, K2_TILE_BYTES / bw);
-    if (bh_max < L.win) continue;
-    int th = (bh_max - L.win) / L.step + 1;
-    th = std::min(th, K2_LIST_CAP / tw);
-    th = std::min(th, std::max(1, L.ny));
-    const int bh = (th - 1) * L.step + L.win;
-    if ((long long)L.win * bw + L.win >= 65536) continue;  // u16 tile offsets
-    const int windows = std::min(tw, L.nx) * th;
-    if (windows > best_windows) {
-      best_windows = windows;
-      L.tw_log2 = tl; L.th = th; L.box_w = bw; L.box_h = bh;
+    const int bw0 = (((tw - 1) * L.step + L.win) + 15) & ~15;
+    for (int bw = bw0; bw <= std::min(256, bw0 + (g_tune_pitch ? 80 : 0)); bw += 16) {
+      const int bh_max = std::min(256, K2_TILE_BYTES / bw);
+      if (bh_max < L.win) continue;
+      int th = (bh_max - L.win) / L.step + 1;
+      th = std::min(th, K2_LIST_CAP / tw);
+      th = std::min(th, std::max(1, L.ny));
+      const int bh = (th - 1) * L.step + L.win;
+      if ((long long)L.win * bw + L.win >= 65536) continue;  // u16 tile offsets
+      const int windows = std::min(tw, L.nx) * th;
+      if (windows < g_min_tile_windows) continue;
+      const double wf = g_tune_pitch ? estimate_wavefronts(L.win, L.step, tw, th, bw) : 1.0;
+      const double cost = (4.0 + 6.0 * wf) * (1.0 + 40.0 / windows);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_windows = windows;
+        L.tw_log2 = tl; L.th = th; L.box_w = bw; L.box_h = bh;
+      }
     }
   }
-  if (best_windows >= g_min_tile_windows) {
+  if (best_windows > 0) {
     L.use_smem = 1;
   } else {
     L.use_smem = 0;
@@ -738,6 +789,25 @@ int jdaB200Levels(int width, int height, float scale, int min_size, int max_size
 
 long long jdaB200CountWindows(int width, int height, float scale, int min_size, int max_size) {
   return count_windows(width, height, scale, min_size, max_size);
+}
+
+int jdaB200DescribePlan(int width, int height, float scale, int min_size, int max_size, char *buf, int cap) {
+  int wins[kMaxLevels + 1];
+  int n = (width < 24 || height < 24) ? 0 : enumerate_levels(width, height, scale, min_size, max_size, wins, kMaxLevels + 1);
+  n = std::min(n, kMaxLevels);
+  int o = 0;
+  if (buf && cap > 0) buf[0] = 0;
+  for (int i = 0; i < n; i++) {
+    LevelInfo L;
+    memset(&L, 0, sizeof L);
+    L.win = wins[i]; L.step = level_step(L.win);
+    L.nx = (width - L.win) / L.step + 1; L.ny = (height - L.win) / L.step + 1;
+    plan_level(L);
+    if (buf && o < cap)
+      o += snprintf(buf + o, cap - o, "%d %d %d %d %d %d %d %d %d %d\n", L.win, L.step, L.nx, L.ny, 1 << L.tw_log2,
+                    L.th, L.box_w, L.box_h, L.use_smem, (1 << L.tw_log2) * L.th);
+  }
+  return n;
 }
 
 void jdaB200Nms(int n, const int *bboxes, const float *scores, unsigned char *keep) {

@@ -463,12 +463,17 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
   for (int ph = 0; ph < P.n_sched; ++ph) {
     const int cend = P.sched[ph];
     int out = 0, base = 0;
-    // full groups of NW packets, then the remainder with as few packets as it needs
-    for (; n - base >= 32 * NW; base += 32 * NW) scan_group<SMEM, NW, TRACE>(c, ph, base, n, cart, cend, out);
-    if constexpr (NW >= 4) {
+    // full groups of NWM packets, then the remainder with as few packets as it needs.  The global-memory
+    // levels run twice as wide: their pixel reads are L2-latency bound, not shared-memory bound.
+    constexpr int NWM = (SMEM || TRACE || NW > 4) ? NW : 2 * NW;
+    for (; n - base >= 32 * NWM; base += 32 * NWM) scan_group<SMEM, NWM, TRACE>(c, ph, base, n, cart, cend, out);
+    if constexpr (NWM >= 8) {
+      if (n - base > 128) { scan_group<SMEM, 8, TRACE>(c, ph, base, n, cart, cend, out); base = n; }
+    }
+    if constexpr (NWM >= 4) {
       if (n - base > 64) { scan_group<SMEM, 4, TRACE>(c, ph, base, n, cart, cend, out); base = n; }
     }
-    if constexpr (NW >= 2) {
+    if constexpr (NWM >= 2) {
       if (n - base > 32) { scan_group<SMEM, 2, TRACE>(c, ph, base, n, cart, cend, out); base = n; }
     }
     if (n - base > 0) scan_group<SMEM, 1, TRACE>(c, ph, base, n, cart, cend, out);

@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
     import ctypes
     hdr = open(os.path.join(ROOT, "include", "jda_b200.h")).read()
     declared = re.findall(r"JDA_API\s+[\w\s\*]+?\b(jda\w+)\s*\(", hdr)
-    assert len(declared) >= 17 and set(declared) == set(api.EXPORTS)
+    assert len(declared) >= 18 and set(declared) == set(api.EXPORTS)
     L = ctypes.CDLL(api.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
@@ -97,3 +97,20 @@ def test_detect_without_gpu_fails_loudly():
     with pytest.raises(RuntimeError, match="no CUDA device"):
         c.detect(synth.noise_frame(0, 64, 48))
     c.close()
+
+
+@pytest.mark.parametrize("w,h,mx", [(640, 480, 192), (640, 480, -1), (1920, 1080, 768), (60, 300, -1), (451, 333, -1)])
+def test_tile_plan_invariants(w, h, mx):
+    """every planned shared-memory tile fits the per-warp scratch and TMA's box rules"""
+    plan = api.describe_plan(w, h, 1.25, 24, mx)
+    assert [p["win"] for p in plan] == api.levels(w, h, 1.25, 24, mx)
+    for p in plan:
+        assert p["step"] == int(np.float32(p["win"]) * np.float32(0.1))
+        assert p["tw"] * p["th"] <= 512 and p["tw"] in (8, 16, 32)
+        if p["smem"]:
+            assert p["box_w"] % 16 == 0 and p["box_w"] <= 256 and p["box_h"] <= 256
+            assert p["box_w"] * p["box_h"] <= 8192
+            assert p["box_w"] >= (p["tw"] - 1) * p["step"] + p["win"]
+            assert p["box_h"] == (p["th"] - 1) * p["step"] + p["win"]
+            assert (p["win"] - 1) * p["box_w"] + p["win"] - 1 < 65536
+    assert any(p["smem"] for p in plan)
