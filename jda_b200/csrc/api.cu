@@ -278,7 +278,7 @@ double estimate_wavefronts(int win, int step, int tw, int th, int pitch) {
 }
 
 int g_min_tile_windows = 64;
-int g_tune_pitch = 1;
+int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflict model (measured: no gain, r1)
 
 // Per-level tile shapes.  A level runs from private shared-memory tiles when a tile of at least
 // 64 windows (with its 16-byte-granular pixel box) fits the per-warp scratch; otherwise its windows
@@ -303,8 +303,9 @@ void plan_level(LevelInfo &L) {
       if ((long long)L.win * bw + L.win >= 65536) continue;  // u16 tile offsets
       const int windows = std::min(tw, L.nx) * th;
       if (windows < g_min_tile_windows) continue;
-      const double wf = g_tune_pitch ? estimate_wavefronts(L.win, L.step, tw, th, bw) : 1.0;
-      const double cost = (4.0 + 6.0 * wf) * (1.0 + 40.0 / windows);
+      // default: most windows per tile, wider tiles on ties; tuned: modelled wavefronts x tail factor
+      const double cost = g_tune_pitch ? (4.0 + 6.0 * estimate_wavefronts(L.win, L.step, tw, th, bw)) * (1.0 + 40.0 / windows)
+                                       : -(double)windows;
       if (cost < best_cost) {
         best_cost = cost;
         best_windows = windows;

@@ -34,6 +34,9 @@ struct LevelInfo {
 #ifndef JDA_K2_WARPS
 #define JDA_K2_WARPS 12
 #endif
+#ifndef JDA_K2_GLOBAL_WIDE
+#define JDA_K2_GLOBAL_WIDE 1
+#endif
 #ifndef JDA_K2_TILE_BYTES
 #define JDA_K2_TILE_BYTES 8192
 #endif
@@ -465,7 +468,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
     int out = 0, base = 0;
     // full groups of NWM packets, then the remainder with as few packets as it needs.  The global-memory
     // levels run twice as wide: their pixel reads are L2-latency bound, not shared-memory bound.
-    constexpr int NWM = (SMEM || TRACE || NW > 4) ? NW : 2 * NW;
+    constexpr int NWM = (SMEM || TRACE || NW > 4 || !JDA_K2_GLOBAL_WIDE) ? NW : 2 * NW;
     for (; n - base >= 32 * NWM; base += 32 * NWM) scan_group<SMEM, NWM, TRACE>(c, ph, base, n, cart, cend, out);
     if constexpr (NWM >= 8) {
       if (n - base > 128) { scan_group<SMEM, 8, TRACE>(c, ph, base, n, cart, cend, out); base = n; }
