@@ -111,6 +111,9 @@ typedef struct {
 JDA_API int jdaB200DetectBatch(void *cascador, const unsigned char *frames, const jdaB200Batch *batch,
                                jdaResult *results, jdaB200Stats *stats /* may be NULL */);
 
+/* jdaResultRelease for a whole array of results (one call instead of n). */
+JDA_API void jdaB200ResultsRelease(jdaResult *results, int n);
+
 /* Bind the handle to a CUDA device (default: device 0 / current at first use) and, optionally, to
  * a caller-owned cudaStream_t (NULL = the handle's own stream). */
 JDA_API int jdaB200SetDevice(void *cascador, int device);

@@ -73,6 +73,8 @@ def lib():
     L.jdaResultRelease.argtypes = [_Result]
     L.jdaB200DetectBatch.restype = ci
     L.jdaB200DetectBatch.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(_Result), C.POINTER(Stats)]
+    L.jdaB200ResultsRelease.restype = None
+    L.jdaB200ResultsRelease.argtypes = [C.POINTER(_Result), ci]
     L.jdaB200SetDevice.restype = ci
     L.jdaB200SetDevice.argtypes = [vp, ci]
     L.jdaB200SetStream.restype = ci
@@ -104,7 +106,7 @@ EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSeri
            "jdaCascadorRelease", "jdaDetect", "jdaResultRelease", "jdaB200DetectBatch",
            "jdaB200SetDevice", "jdaB200SetStream", "jdaB200ModelDims", "jdaB200LastError",
            "jdaB200DeviceCount", "jdaB200Levels", "jdaB200CountWindows", "jdaB200Nms",
-           "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan"]
+           "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan", "jdaB200ResultsRelease"]
 
 
 def last_error():
@@ -226,13 +228,23 @@ class Cascador:
         self.last_stats = st.as_dict()
         if rc != 0:
             raise RuntimeError("jdaB200DetectBatch failed: " + last_error())
-        if unpack:
-            return [_unpack(res[i]) for i in range(n)]
-        tot = 0
+        lm = self.L
+        if not unpack:
+            tot = sum(res[i].n for i in range(n))
+            L.jdaB200ResultsRelease(res, n)
+            return tot
+        empty = (np.zeros((0, 3), np.int32), np.zeros((0,), np.float32), np.zeros((0, 2 * lm), np.float32))
+        out = []
         for i in range(n):
-            tot += res[i].n
-            L.jdaResultRelease(res[i])
-        return tot
+            k = res[i].n
+            if k > 0:
+                out.append((np.ctypeslib.as_array(res[i].bboxes, shape=(k, 3)).copy(),
+                            np.ctypeslib.as_array(res[i].scores, shape=(k,)).copy(),
+                            np.ctypeslib.as_array(res[i].shapes, shape=(k, 2 * lm)).copy()))
+            else:
+                out.append(empty)
+        L.jdaB200ResultsRelease(res, n)
+        return out
 
     def trace(self, img, scale=1.25, min_size=24, max_size=-1, t_limit=0, flags=0, leaf_range=None):
         """per-window (carts evaluated, exit score) in scan order + optional leaf indices."""

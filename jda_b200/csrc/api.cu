@@ -292,7 +292,10 @@ void plan_level(LevelInfo &L) {
   int best_windows = 0;
   for (int tl = 5; tl >= 3; tl--) {
     const int tw = 1 << tl;
-    const int bw0 = (((tw - 1) * L.step + L.win) + 15) & ~15;
+    // TMA wants the box to start on a 16-byte boundary in x: tiles whose x origin (tx * tw * step) is not
+    // a multiple of 16 start their box at the aligned address below it and carry up to 15 spare bytes
+    const int slack = ((tw * L.step) % 16 == 0) ? 0 : 15;
+    const int bw0 = (((tw - 1) * L.step + L.win + slack) + 15) & ~15;
     for (int bw = bw0; bw <= std::min(256, bw0 + (g_tune_pitch ? 80 : 0)); bw += 16) {
       const int bh_max = std::min(256, K2_TILE_BYTES / bw);
       if (bh_max < L.win) continue;
@@ -744,6 +747,14 @@ int jdaB200DetectBatch(void *cascador, const unsigned char *frames, const jdaB20
     return -2;
   }
   return detect_batch(c, frames, *batch, results, stats);
+}
+
+void jdaB200ResultsRelease(jdaResult *results, int n) {
+  if (!results) return;
+  for (int i = 0; i < n; i++) {
+    jdaResultRelease(results[i]);
+    results[i].bboxes = nullptr; results[i].shapes = nullptr; results[i].scores = nullptr; results[i].n = 0;
+  }
 }
 
 int jdaB200SetDevice(void *cascador, int device) {

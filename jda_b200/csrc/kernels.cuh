@@ -35,7 +35,7 @@ struct LevelInfo {
 #define JDA_K2_WARPS 12
 #endif
 #ifndef JDA_K2_GLOBAL_WIDE
-#define JDA_K2_GLOBAL_WIDE 1
+#define JDA_K2_GLOBAL_WIDE 0  /* 8-wide groups on the global-memory levels: measured slower (r1) */
 #endif
 #ifndef JDA_K2_TILE_BYTES
 #define JDA_K2_TILE_BYTES 8192
@@ -549,7 +549,9 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
       const int x0w = tx * tw, y0w = ty * lv.th;
       const int cw = min(tw, lv.nx - x0w), ch = min(lv.th, lv.ny - y0w);
       if (lv.use_smem) {
-        const int px0 = x0w * lv.step, py0 = y0w * lv.step;
+        // box origin: x rounded down to 16 bytes (TMA alignment), the windows sit `xs` bytes into the tile
+        const int px0 = (x0w * lv.step) & ~15, py0 = y0w * lv.step;
+        const int xs = x0w * lv.step - px0;
         if (P.use_tma) {
           if (lane == 0) {
             mbar_expect_tx(bar, (uint32_t)(lv.box_w * lv.box_h));
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
           }
           __syncwarp();
         }
-        scan_tile<true, NW, TRACE>(P, lv, li, smem, norm_off, tile_off, ws->lscore, ws->lwid, frame, x0w,
+        scan_tile<true, NW, TRACE>(P, lv, li, smem, norm_off, tile_off + (uint32_t)xs, ws->lscore, ws->lwid, frame, x0w,
                                    y0w, cw, ch, lane);
       } else {
         scan_tile<false, NW, TRACE>(P, lv, li, smem, norm_off, tile_off, ws->lscore, ws->lwid, frame, x0w,
@@ -844,20 +846,26 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
       __syncthreads();  // chunk ci landed for everyone (and, first time round, the leaves are written)
       const float *rb = rows + (size_t)(ci & 1) * chunk_floats;
       const int carts = min(K3S_CHUNK, K - ci * K3S_CHUNK);
-      for (int cl = 0; cl < carts; cl++) {
-        const int k = ci * K3S_CHUNK + cl;
+      const int k0 = ci * K3S_CHUNK;
 #pragma unroll
-        for (int s = 0; s < K3S_PER_WARP; s++) {
-          if (c0 + warp * K3S_PER_WARP + s >= total) continue;  // no survivor in this seat: its leaves are stale
-          const int leaf = leaves[(size_t)(warp * K3S_PER_WARP + s) * kpad + k];
-          const float2 *row = reinterpret_cast<const float2 *>(rb + (size_t)(cl * kLeaves + leaf) * D);
+      for (int s = 0; s < K3S_PER_WARP; s++) {
+        if (c0 + warp * K3S_PER_WARP + s >= total) continue;  // no survivor in this seat: its leaves are stale
+        // the chunk's 8 leaf indices of this survivor in two 32-bit loads (kpad and k0 are multiples of 4)
+        const uint32_t *lp = reinterpret_cast<const uint32_t *>(leaves + (warp * K3S_PER_WARP + s) * kpad + k0);
+        const uint32_t l03 = lp[0], l47 = lp[1];
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int p = lane + 32 * h;
-            if (2 * p + 1 < D) {
-              const float2 v = row[p];
-              acc[s][h].x = __fadd_rn(acc[s][h].x, v.x);
-              acc[s][h].y = __fadd_rn(acc[s][h].y, v.y);
+        for (int cl = 0; cl < K3S_CHUNK; cl++) {
+          if (cl < carts) {
+            const uint32_t leaf = ((cl < 4 ? l03 : l47) >> (8 * (cl & 3))) & 0xffu;
+            const float2 *row = reinterpret_cast<const float2 *>(rb + (cl * kLeaves + leaf) * D);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int p = lane + 32 * h;
+              if (2 * p + 1 < D) {
+                const float2 v = row[p];
+                acc[s][h].x = __fadd_rn(acc[s][h].x, v.x);
+                acc[s][h].y = __fadd_rn(acc[s][h].y, v.y);
+              }
             }
           }
         }

@@ -119,6 +119,28 @@ def test_scan_kernel_variants(oracle, oracle_shipped, nw, stragglers):
         del os.environ["JDA_B200_STRAGGLERS"]
 
 
+def test_tile_origins_not_multiple_of_16(oracle, oracle_shipped):
+    """Tiles whose x origin is not 16-byte aligned (8-wide tiles at step 5: origin 40*tx): the TMA box starts
+    at the aligned address below and the windows are addressed with the remainder."""
+    os.environ["JDA_B200_MIN_TILE_WINDOWS"] = "32"
+    try:
+        assert any(p["smem"] and (p["tw"] * p["step"]) % 16 for p in api.describe_plan(640, 480))
+        c = api.Cascador(SHIPPED_F32, double=False)
+        img = synth.face_canvas()
+        for flags in (0, api.NO_TMA):
+            got = c.detect_batch(img[None], th=0.0, flags=flags)[0]
+            _same(got, oracle.detect(oracle_shipped, img))
+        nwin = api.count_windows(640, 480)
+        tn, ts, lv = c.trace(img, leaf_range=(nwin - 40000, nwin - 36000))
+        on, os_, olv = oracle.trace(oracle_shipped, img, leaf_range=(nwin - 40000, nwin - 36000))
+        np.testing.assert_array_equal(tn, on)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+        np.testing.assert_array_equal(lv, olv)
+        c.close()
+    finally:
+        del os.environ["JDA_B200_MIN_TILE_WINDOWS"]
+
+
 # ---- synthetic models: deep survivors, normalised scores, scaled (h/q) nodes --------------------
 
 SYN = [
