@@ -269,8 +269,8 @@ def main():
                       "l2": "inputs larger than L2 (157 MB batch, two batches alternate)",
                       "model": "shipped T=5 K=540 L=27 (tests/golden/jda_shipped_f32.model)",
                       "parallelism": "frames sharded, %d rank(s), NCCL all-gather of detections" % world},
-           "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": B * W * H,
-                   "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps},
+           "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": B * W * H * world,
+                   "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps},
            "gpu_launches": acc["launches"], "clocks": clocks,
            "kernel_ms_per_step": {"k2_scan": acc["ms_scan"] / a.steps, "k3_cascade": acc["ms_cascade"] / a.steps,
                                   "d2h": acc["ms_d2h"] / a.steps, "host_nms": acc["ms_host"] / a.steps},
