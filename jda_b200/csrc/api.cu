@@ -133,7 +133,7 @@ struct Context {
 
 constexpr int kCntSurv = kMaxLevels, kCntHit = kMaxLevels + 1, kCntTotal = kMaxLevels + 2;
 
-size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * sizeof(WarpScratch); }
+size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * K2_WARP_BYTES; }
 size_t k3s_smem_bytes(int K, int D) {
   return (size_t)K3S_COHORT * ((K + 15) & ~15) + (size_t)2 * K3S_CHUNK * kLeaves * D * 4;
 }
@@ -285,9 +285,10 @@ int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflic
 // read pixels from global memory in "virtual" tiles of 32 x 16 windows.  Among the shapes that fit,
 // the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
 // pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
-void plan_level(LevelInfo &L) {
-  if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
-  if (const char *e = getenv("JDA_B200_TUNE_PITCH")) g_tune_pitch = atoi(e);
+int g_max_span = 4;
+
+// best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
+int plan_tile(LevelInfo &L, int tile_bytes) {
   double best_cost = 1e30;
   int best_windows = 0;
   for (int tl = 5; tl >= 3; tl--) {
@@ -297,7 +298,7 @@ void plan_level(LevelInfo &L) {
     const int slack = ((tw * L.step) % 16 == 0) ? 0 : 15;
     const int bw0 = (((tw - 1) * L.step + L.win + slack) + 15) & ~15;
     for (int bw = bw0; bw <= std::min(256, bw0 + (g_tune_pitch ? 80 : 0)); bw += 16) {
-      const int bh_max = std::min(256, K2_TILE_BYTES / bw);
+      const int bh_max = std::min(256, tile_bytes / bw);
       if (bh_max < L.win) continue;
       int th = (bh_max - L.win) / L.step + 1;
       th = std::min(th, K2_LIST_CAP / tw);
@@ -316,12 +317,34 @@ void plan_level(LevelInfo &L) {
       }
     }
   }
-  if (best_windows > 0) {
-    L.use_smem = 1;
+  return best_windows;
+}
+
+// Per-level tile shapes.  A level runs from shared-memory tiles when a tile of at least 64 windows
+// (with its 16-byte-granular pixel box) fits a warp's 8 KB buffer -- or, for coarser levels, the
+// buffers of 2 or 4 neighbouring warps (only every 2nd / 4th warp then works on that level).  Levels
+// that fit neither read pixels from global memory in "virtual" tiles of 32 x 16 windows.
+void plan_level(LevelInfo &L) {
+  if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
+  if (const char *e = getenv("JDA_B200_TUNE_PITCH")) g_tune_pitch = atoi(e);
+  if (const char *e = getenv("JDA_B200_MAX_SPAN")) g_max_span = std::max(1, atoi(e));
+  L.use_smem = 0;
+  L.span = 1;
+  if (plan_tile(L, K2_TILE_BYTES) > 0) {
+    L.use_smem = 1;  // fits a single warp's buffer: every warp works
   } else {
-    L.use_smem = 0;
-    L.tw_log2 = 5; L.th = K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0;
+    // lend buffers: more bytes per tile (more windows, shorter tails) against fewer working warps
+    double best = 0;
+    LevelInfo pick = L;
+    for (int span = 2; span <= g_max_span && span <= 4 && K2_WARPS % span == 0; span *= 2) {
+      LevelInfo t = L;
+      const int windows = plan_tile(t, span * K2_TILE_BYTES);
+      const double score = windows * std::sqrt((double)K2_WARPS / span);
+      if (windows > 0 && score > best) { best = score; pick = t; pick.use_smem = 1; pick.span = span; }
+    }
+    L = pick;
   }
+  if (!L.use_smem) { L.tw_log2 = 5; L.th = K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0; }
   const int tw = 1 << L.tw_log2;
   L.ntx = (L.nx + tw - 1) / tw;
   L.nty = (L.ny + L.th - 1) / L.th;
@@ -508,6 +531,16 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       }
       for (int i = 0; i < g.n_levels; i++) n_smem += g.lv[i].use_smem;
       st.levels_smem = n_smem;
+      {  // share of the scan work per level, in processing order (coarse -> fine)
+        double w[kMaxLevels], tot = 0;
+        for (int i = 0; i < g.n_levels; i++) {
+          const LevelInfo &L = g.lv[g.n_levels - 1 - i];
+          w[i] = (double)L.nx * L.ny * (L.use_smem ? (L.span == 1 ? 1.0 : 1.4) : 2.2);
+          tot += w[i];
+        }
+        double acc = 0;
+        for (int i = 0; i < g.n_levels; i++) { acc += w[i]; P.level_cum[i] = (float)(acc / tot); }
+      }
       P.use_tma = tma_ok ? 1 : 0;
       P.stragglers = c->stragglers;
       if (tracing) {
@@ -816,8 +849,8 @@ int jdaB200DescribePlan(int width, int height, float scale, int min_size, int ma
     L.nx = (width - L.win) / L.step + 1; L.ny = (height - L.win) / L.step + 1;
     plan_level(L);
     if (buf && o < cap)
-      o += snprintf(buf + o, cap - o, "%d %d %d %d %d %d %d %d %d %d\n", L.win, L.step, L.nx, L.ny, 1 << L.tw_log2,
-                    L.th, L.box_w, L.box_h, L.use_smem, (1 << L.tw_log2) * L.th);
+      o += snprintf(buf + o, cap - o, "%d %d %d %d %d %d %d %d %d %d %d\n", L.win, L.step, L.nx, L.ny, 1 << L.tw_log2,
+                    L.th, L.box_w, L.box_h, L.use_smem, (1 << L.tw_log2) * L.th, L.span);
   }
   return n;
 }

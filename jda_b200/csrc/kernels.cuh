@@ -27,6 +27,7 @@ struct LevelInfo {
   int ntx, nty;         // tiles per frame
   int box_w, box_h;     // shared-memory tile in pixels (box_w is the tile pitch); global path: 0
   int use_smem;
+  int span;             // warps whose tile buffers one tile spans (1, 2 or 4): only every span-th warp works
   int table_off;        // byte offset of this level's stage-0 table
   long long win_base;   // scan-order index of the level's first window inside a frame
 };
@@ -45,14 +46,18 @@ constexpr int K2_TILE_BYTES = JDA_K2_TILE_BYTES;  // per-warp pixel tile
 constexpr int K2_LIST_CAP = 512;     // windows per tile (fits u16 ids)
 constexpr int K2_MAX_SCHED = 32;
 
-struct __align__(128) WarpScratch {
-  uint8_t tile[K2_TILE_BYTES];
+// Shared memory of a scan block:
+//   [ stage-0 table | norm table (256 B) | K2_WARPS pixel tiles, contiguous | K2_WARPS WarpLists ]
+// The tiles are contiguous so that a coarse level can give one warp the buffers of 2 or 4
+// neighbours (LevelInfo::span) while those neighbours sit the level out.
+struct __align__(128) WarpLists {
   float lscore[K2_LIST_CAP];
   uint16_t lwid[K2_LIST_CAP];
   unsigned long long mbar;
   unsigned char pad[120];
 };
-static_assert(sizeof(WarpScratch) % 128 == 0, "WarpScratch must keep 128-byte alignment");
+static_assert(sizeof(WarpLists) % 128 == 0, "WarpLists must keep 128-byte alignment");
+constexpr size_t K2_WARP_BYTES = K2_TILE_BYTES + sizeof(WarpLists);
 
 struct ScanParams {
   CUtensorMap maps[kMaxLevels];  // one 3-D u8 map per level (box = that level's tile)
@@ -72,6 +77,7 @@ struct ScanParams {
   short sched[K2_MAX_SCHED];     // cart index at which each phase ends; last == K
   int use_tma;
   int stragglers;                // 1: finish nearly empty tiles in cart-parallel straggler mode
+  float level_cum[kMaxLevels];   // cumulative share of the scan work in processing order (coarse -> fine)
   // trace (TRACE instantiation only)
   int *trace_n;
   float *trace_s;
@@ -511,14 +517,15 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
 template <int NW, bool TRACE>
 __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ int s_skip;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t table_sz = (uint32_t)(P.table_bytes + 127) & ~127u;
   const uint32_t norm_off = table_sz;
-  const uint32_t ws_off = table_sz + 256u + (uint32_t)warp * (uint32_t)sizeof(WarpScratch);
-  WarpScratch *ws = reinterpret_cast<WarpScratch *>(smem + ws_off);
-  const uint32_t tile_off = ws_off;  // tile is the first member
-  const uint32_t bar = smem_u32(&ws->mbar);
-  const uint32_t tile_s = smem_u32(ws->tile);
+  const uint32_t tile_off = table_sz + 256u + (uint32_t)warp * K2_TILE_BYTES;
+  WarpLists *wl = reinterpret_cast<WarpLists *>(smem + table_sz + 256u + (uint32_t)K2_WARPS * K2_TILE_BYTES) + warp;
+  uint8_t *tile = smem + tile_off;
+  const uint32_t bar = smem_u32(&wl->mbar);
+  const uint32_t tile_s = smem_u32(tile);
   uint32_t parity = 0;
 
   if (lane == 0) mbar_init(bar, 1);
@@ -526,17 +533,33 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
   for (int i = threadIdx.x; i < kMaxNorm * 2; i += blockDim.x)
     reinterpret_cast<float *>(smem + norm_off)[i] = reinterpret_cast<const float *>(P.norms)[i];
 
-  for (int li = P.n_levels - 1; li >= 0; --li) {  // coarse levels first, finest (most tiles) last
+  // Levels are visited coarse -> fine, but every block starts at the level where its share of the total
+  // work begins (and wraps around), so most blocks load one or two tables instead of all of them and the
+  // block-wide barrier at a level switch is paid far less often.  Levels whose tiles are all taken are
+  // skipped without loading their table.
+  int start = 0;
+  {
+    const float f = ((float)blockIdx.x + 0.5f) / (float)gridDim.x;
+    while (start + 1 < P.n_levels && P.level_cum[start] < f) start++;
+  }
+  for (int it = 0; it < P.n_levels; ++it) {
+    int pos = start + it;
+    if (pos >= P.n_levels) pos -= P.n_levels;
+    const int li = P.n_levels - 1 - pos;
     const LevelInfo &lv = P.lv[li];
+    const int tiles_per_frame = lv.ntx * lv.nty;
+    const unsigned total = (unsigned)tiles_per_frame * (unsigned)P.n_frames;
+    __syncthreads();  // everyone is done with the previous level's table
+    if (threadIdx.x == 0) s_skip = *reinterpret_cast<volatile unsigned *>(&P.tile_counters[li]) >= total;
     __syncthreads();
+    if (s_skip) continue;
     {
       const uint4 *src = reinterpret_cast<const uint4 *>(P.tables + lv.table_off);
       uint4 *dst = reinterpret_cast<uint4 *>(smem);
       for (int i = threadIdx.x; i < (int)(table_sz / 16); i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    const int tiles_per_frame = lv.ntx * lv.nty;
-    const unsigned total = (unsigned)tiles_per_frame * (unsigned)P.n_frames;
+    if (warp % lv.span != 0) continue;  // this warp's tile buffer is lent to a neighbour on this level
     const int tw = 1 << lv.tw_log2;
     for (;;) {
       unsigned item = 0;
@@ -564,14 +587,14 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
           for (int i = lane; i < lv.box_w * lv.box_h; i += 32) {
             const int yy = i / lv.box_w, xx = i - yy * lv.box_w;
             const int gx = px0 + xx, gy = py0 + yy;
-            ws->tile[i] = (gx < P.W && gy < P.H) ? src[(size_t)gy * P.pitch + gx] : (uint8_t)0;
+            tile[i] = (gx < P.W && gy < P.H) ? src[(size_t)gy * P.pitch + gx] : (uint8_t)0;
           }
           __syncwarp();
         }
-        scan_tile<true, NW, TRACE>(P, lv, li, smem, norm_off, tile_off + (uint32_t)xs, ws->lscore, ws->lwid, frame, x0w,
+        scan_tile<true, NW, TRACE>(P, lv, li, smem, norm_off, tile_off + (uint32_t)xs, wl->lscore, wl->lwid, frame, x0w,
                                    y0w, cw, ch, lane);
       } else {
-        scan_tile<false, NW, TRACE>(P, lv, li, smem, norm_off, tile_off, ws->lscore, ws->lwid, frame, x0w,
+        scan_tile<false, NW, TRACE>(P, lv, li, smem, norm_off, tile_off, wl->lscore, wl->lwid, frame, x0w,
                                     y0w, cw, ch, lane);
       }
     }
