@@ -2,7 +2,7 @@
 # A/B harness for gpurun: each line "NAME ENV..." runs a short resident-frames bench and prints one summary row.
 run() {
   name=$1; shift
-  out=$(env "$@" timeout 300 python bench.py --steps ${STEPS:-6} --warmup 2 --no-cpu-baseline ${EXTRA:---no-breakdown} 2>&1 | tail -1)
+  out=$(env "$@" timeout 300 python bench.py --batch ${BATCH:-512} --steps ${STEPS:-6} --warmup 2 --no-cpu-baseline ${EXTRA:---no-breakdown} 2>&1 | tail -1)
   echo "$out" | python -c "
 import sys, json
 name = sys.argv[1]
