@@ -285,7 +285,7 @@ int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflic
 // read pixels from global memory in "virtual" tiles of 32 x 16 windows.  Among the shapes that fit,
 // the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
 // pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
-int g_max_span = 4;
+int g_max_span = 1;  // lending tile buffers (span 2/4) measured slower than the global-memory path: idle warps (r1)
 
 // best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
 int plan_tile(LevelInfo &L, int tile_bytes) {

@@ -54,7 +54,8 @@ struct __align__(128) WarpLists {
   float lscore[K2_LIST_CAP];
   uint16_t lwid[K2_LIST_CAP];
   unsigned long long mbar;
-  unsigned char pad[120];
+  unsigned parity;  // phase of `mbar` to wait for next (kept here so a group of warps can share one barrier)
+  unsigned char pad[116];
 };
 static_assert(sizeof(WarpLists) % 128 == 0, "WarpLists must keep 128-byte alignment");
 constexpr size_t K2_WARP_BYTES = K2_TILE_BYTES + sizeof(WarpLists);
@@ -518,6 +519,7 @@ template <int NW, bool TRACE>
 __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ int s_skip;
+  __shared__ unsigned s_item[K2_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t table_sz = (uint32_t)(P.table_bytes + 127) & ~127u;
   const uint32_t norm_off = table_sz;
@@ -526,9 +528,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
   uint8_t *tile = smem + tile_off;
   const uint32_t bar = smem_u32(&wl->mbar);
   const uint32_t tile_s = smem_u32(tile);
-  uint32_t parity = 0;
-
-  if (lane == 0) mbar_init(bar, 1);
+  if (lane == 0) { mbar_init(bar, 1); wl->parity = 0; }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int i = threadIdx.x; i < kMaxNorm * 2; i += blockDim.x)
     reinterpret_cast<float *>(smem + norm_off)[i] = reinterpret_cast<const float *>(P.norms)[i];
@@ -559,8 +559,66 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
       for (int i = threadIdx.x; i < (int)(table_sz / 16); i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    if (warp % lv.span != 0) continue;  // this warp's tile buffer is lent to a neighbour on this level
     const int tw = 1 << lv.tw_log2;
+    if (lv.span > 1) {
+      // Coarse level: `span` neighbouring warps pool their tile buffers into one tile, load it once (the
+      // group's first warp issues the TMA on its barrier) and split its window rows between them.
+      const int gl = warp % lv.span, grp = warp / lv.span;
+      WarpLists *lead = wl - gl;
+      const uint32_t gbar = smem_u32(&lead->mbar);
+      const uint32_t gtile_off = tile_off - (uint32_t)gl * K2_TILE_BYTES;
+      const uint32_t gtile_s = tile_s - (uint32_t)gl * K2_TILE_BYTES;
+      const int nthr = lv.span * 32;
+      bool loaded = false;
+      for (;;) {
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthr) : "memory");  // group is done with the previous tile
+        int frame = 0, x0w = 0, y0w = 0;
+        if (gl == 0) {
+          if (lane == 0) {
+            if (loaded && P.use_tma) lead->parity ^= 1u;
+            const unsigned it2 = atomicAdd(&P.tile_counters[li], 1u);
+            s_item[grp] = it2;
+            if (it2 < total && P.use_tma) {
+              const int f = it2 / tiles_per_frame, r = it2 - f * tiles_per_frame;
+              const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
+              mbar_expect_tx(gbar, (uint32_t)(lv.box_w * lv.box_h));
+              tma_load_3d(gtile_s, &P.maps[li], (tx * tw * lv.step) & ~15, ty * lv.th * lv.step, f, gbar);
+            }
+          }
+          __syncwarp();
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthr) : "memory");  // tile id published
+        const unsigned item = s_item[grp];
+        if (item >= total) break;
+        loaded = true;
+        frame = item / tiles_per_frame;
+        {
+          const int r = item - frame * tiles_per_frame;
+          const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
+          x0w = tx * tw; y0w = ty * lv.th;
+        }
+        const int cw = min(tw, lv.nx - x0w), ch = min(lv.th, lv.ny - y0w);
+        const int px0 = (x0w * lv.step) & ~15, py0 = y0w * lv.step;
+        const int xs = x0w * lv.step - px0;
+        if (P.use_tma) {
+          mbar_wait(gbar, lead->parity);
+        } else {
+          uint8_t *gt = smem + gtile_off;
+          const uint8_t *src = P.frames + (size_t)frame * P.frame_stride;
+          for (int i = gl * 32 + lane; i < lv.box_w * lv.box_h; i += nthr) {
+            const int yy = i / lv.box_w, xx = i - yy * lv.box_w;
+            const int gx = px0 + xx, gy = py0 + yy;
+            gt[i] = (gx < P.W && gy < P.H) ? src[(size_t)gy * P.pitch + gx] : (uint8_t)0;
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthr) : "memory");
+        }
+        const int r0 = ch * gl / lv.span, r1 = ch * (gl + 1) / lv.span;
+        if (r1 > r0)
+          scan_tile<true, NW, TRACE>(P, lv, li, smem, norm_off, gtile_off + (uint32_t)(xs + r0 * lv.step * lv.box_w),
+                                     wl->lscore, wl->lwid, frame, x0w, y0w + r0, cw, r1 - r0, lane);
+      }
+      continue;
+    }
     for (;;) {
       unsigned item = 0;
       if (lane == 0) item = atomicAdd(&P.tile_counters[li], 1u);
@@ -580,8 +638,10 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
             mbar_expect_tx(bar, (uint32_t)(lv.box_w * lv.box_h));
             tma_load_3d(tile_s, &P.maps[li], px0, py0, frame, bar);
           }
-          mbar_wait(bar, parity);
-          parity ^= 1u;
+          mbar_wait(bar, wl->parity);
+          __syncwarp();
+          if (lane == 0) wl->parity ^= 1u;
+          __syncwarp();
         } else {
           const uint8_t *src = P.frames + (size_t)frame * P.frame_stride;
           for (int i = lane; i < lv.box_w * lv.box_h; i += 32) {

@@ -141,6 +141,27 @@ def test_tile_origins_not_multiple_of_16(oracle, oracle_shipped):
         del os.environ["JDA_B200_MIN_TILE_WINDOWS"]
 
 
+@pytest.mark.parametrize("span", ["2", "4"])
+def test_pooled_tile_buffers(oracle, oracle_shipped, span):
+    """coarse levels served from tiles that span several warps' buffers, rows split across the group"""
+    os.environ["JDA_B200_MAX_SPAN"] = span
+    try:
+        assert any(p["span"] > 1 for p in api.describe_plan(640, 480))
+        c = api.Cascador(SHIPPED_F32, double=False)
+        for img in (synth.face_canvas(), synth.noise_frame(4)):
+            nwin = api.count_windows(640, 480)
+            for flags in (0, api.NO_TMA):
+                tn, ts, lv = c.trace(img, flags=flags, leaf_range=(nwin - 12000, nwin - 8000))
+                on, os_, olv = oracle.trace(oracle_shipped, img, leaf_range=(nwin - 12000, nwin - 8000))
+                np.testing.assert_array_equal(tn, on)
+                np.testing.assert_array_equal(_bits(ts), _bits(os_))
+                np.testing.assert_array_equal(lv, olv)
+        _same(c.detect(synth.face_canvas()), oracle.detect(oracle_shipped, synth.face_canvas()))
+        c.close()
+    finally:
+        del os.environ["JDA_B200_MAX_SPAN"]
+
+
 # ---- synthetic models: deep survivors, normalised scores, scaled (h/q) nodes --------------------
 
 SYN = [
