@@ -246,6 +246,28 @@ class Cascador:
         L.jdaB200ResultsRelease(res, n)
         return out
 
+    def detect_many(self, frames, **kw):
+        """frames of mixed sizes (e.g. FDDB-shaped): grouped by shape, one
+        batch call per group, results returned in input order."""
+        groups = {}
+        for i, f in enumerate(frames):
+            groups.setdefault(tuple(f.shape), []).append(i)
+        out = [None] * len(frames)
+        stats = None
+        for shape, idx in groups.items():
+            res = self.detect_batch(np.stack([np.ascontiguousarray(frames[i], np.uint8) for i in idx]), **kw)
+            for i, r in zip(idx, res):
+                out[i] = r
+            st = self.last_stats
+            if stats is None:
+                stats = dict(st)
+            else:
+                for k in ("windows", "stage0_survivors", "raw_hits", "detections", "ms_h2d", "ms_resize", "ms_scan",
+                          "ms_cascade", "ms_d2h", "ms_host", "scan_launches", "cascade_launches", "resize_launches"):
+                    stats[k] += st[k]
+        self.last_stats = stats
+        return out
+
     def trace(self, img, scale=1.25, min_size=24, max_size=-1, t_limit=0, flags=0, leaf_range=None):
         """per-window (carts evaluated, exit score) in scan order + optional leaf indices."""
         a = np.ascontiguousarray(img, np.uint8)

@@ -238,6 +238,15 @@ def test_device_resident_frames(casc):
         _same(a, b)
 
 
+def test_mixed_size_frames_fddb_shaped(casc, oracle, oracle_shipped):
+    """BASELINE config 4 shape: FDDB-like frame sizes, grouped by shape behind detect_many"""
+    frames = [synth.facemix_frame(300 + i, *synth.fddb_shape(i % 5)) for i in range(12)]
+    got = casc.detect_many(frames, th=-0.5)
+    assert casc.last_stats["windows"] == sum(api.count_windows(f.shape[1], f.shape[0]) for f in frames)
+    for f, g in zip(frames, got):
+        _same(g, oracle.detect(oracle_shipped, f, th=-0.5))
+
+
 @pytest.mark.parametrize("t_limit", [1, 2, 5])
 def test_mining_mode_truncated_cascade(casc, oracle, oracle_shipped, t_limit):
     """Validate()'s partial cascade (src/jda/cascador.cpp:178-197): first t stages, every survivor
