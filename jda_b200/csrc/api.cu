@@ -93,12 +93,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
+constexpr int kMaxChunks = 4;  // host batches are copied and scanned in up to 4 overlapping chunks
+
 struct Context {
   HostModel m;
   std::mutex mu;
   int device = -1;
   bool inited = false;
-  cudaStream_t own_stream = nullptr, user_stream = nullptr;
+  cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copy[kMaxChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int sm_count = 148;
   EncodeTiledFn encode = nullptr;
   // device model
@@ -131,7 +134,7 @@ struct Context {
   cudaStream_t stream() const { return user_stream ? user_stream : own_stream; }
 };
 
-constexpr int kCntSurv = kMaxLevels, kCntHit = kMaxLevels + 1, kCntTotal = kMaxLevels + 2;
+constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntHit = kCntSurv + 1, kCntWork = kCntSurv + 2, kCntTotal = kCntSurv + 3;
 
 size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * K2_WARP_BYTES; }
 size_t k3s_smem_bytes(int K, int D) {
@@ -164,6 +167,8 @@ bool ctx_init(Context *c) {
   c->sm_count = prop.multiProcessorCount;
   CU_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   for (auto &e : c->ev) CU_OK(cudaEventCreate(&e));
+  CU_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto &e : c->ev_copy) CU_OK(cudaEventCreate(&e));
   const HostModel &m = c->m;
   CU_OK(cudaMalloc(&c->d_nodes, m.nodes.size() * sizeof(NodeRec)));
   CU_OK(cudaMalloc(&c->d_leaf, m.leaf.size() * 4));
@@ -231,6 +236,8 @@ void ctx_free(Context *c) {
     c->d_tables.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
     c->d_surv.release(); c->d_shape0.release(); c->d_tables_packed.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
   }
   delete c;
@@ -285,7 +292,7 @@ int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflic
 // read pixels from global memory in "virtual" tiles of 32 x 16 windows.  Among the shapes that fit,
 // the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
 // pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
-int g_max_span = 1;  // lending tile buffers (span 2/4) measured slower than the global-memory path: idle warps (r1)
+int g_max_span = 4;  // coarse levels pool up to 4 warps' tile buffers (measured +2.4 % over the global-memory path, r1)
 
 // best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
 int plan_tile(LevelInfo &L, int tile_bytes) {
@@ -440,20 +447,32 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   const uint8_t *d_frames;
   int pitch;
   size_t fstride;
+  int nchunks = 1;
   if (b.flags & JDA_B200_DEVICE_INPUT) {
     d_frames = frames; pitch = b.pitch; fstride = b.frame_stride;
   } else {
     pitch = (b.width + 15) & ~15;
     fstride = (size_t)pitch * b.height;
     if (!c->d_frames.ensure(fstride * b.n_frames + 256)) return false;
-    if (b.frame_stride == (size_t)b.pitch * b.height) {
-      CU_OK(cudaMemcpy2DAsync(c->d_frames.p, pitch, frames, b.pitch, b.width, (size_t)b.height * b.n_frames,
-                              cudaMemcpyHostToDevice, s));
-    } else {
-      for (int f = 0; f < b.n_frames; f++)
-        CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * fstride, pitch, frames + f * b.frame_stride, b.pitch,
-                                b.width, b.height, cudaMemcpyHostToDevice, s));
+    // Large host batches travel in chunks on a second stream; the scan of chunk i overlaps the copy of i+1.
+    if (b.n_frames >= 128 && !m.any_scaled && m.stage0_lut_ok && !trace && !(b.flags & JDA_B200_NO_STAGE0_SCAN) &&
+        !getenv("JDA_B200_NO_CHUNKS"))
+      nchunks = kMaxChunks;
+    CU_OK(cudaEventRecord(c->ev_copy[kMaxChunks], s));
+    CU_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
+    for (int ch = 0; ch < nchunks; ch++) {
+      const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
+      if (b.frame_stride == (size_t)b.pitch * b.height) {
+        CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f0 * fstride, pitch, frames + f0 * b.frame_stride, b.pitch, b.width,
+                                (size_t)b.height * (f1 - f0), cudaMemcpyHostToDevice, c->copy_stream));
+      } else {
+        for (int f = f0; f < f1; f++)
+          CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * fstride, pitch, frames + f * b.frame_stride, b.pitch,
+                                  b.width, b.height, cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
     }
+    if (nchunks == 1) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[0], 0));
     d_frames = c->d_frames.p;
   }
   CU_OK(cudaEventRecord(c->ev[1], s));
@@ -512,23 +531,9 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       P.n_sched = (int)c->sched.size();
       for (int i = 0; i < P.n_sched; i++) P.sched[i] = c->sched[i];
       // TMA needs 16-byte aligned base and strides
-      bool tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)d_frames % 16 == 0) &&
-                    pitch % 16 == 0 && fstride % 16 == 0;
+      const bool tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)d_frames % 16 == 0) &&
+                          pitch % 16 == 0 && fstride % 16 == 0;
       int n_smem = 0;
-      for (int i = 0; i < g.n_levels && tma_ok; i++) {
-        if (!g.lv[i].use_smem) continue;
-        cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)b.n_frames};
-        cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
-        cuuint32_t box[3] = {(cuuint32_t)g.lv[i].box_w, (cuuint32_t)g.lv[i].box_h, 1};
-        cuuint32_t es[3] = {1, 1, 1};
-        CUresult cr = c->encode(&P.maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_frames, dims, strides, box,
-                                es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) {
-          set_err("cuTensorMapEncodeTiled failed (%d) for level %d box %dx%d", (int)cr, i, g.lv[i].box_w, g.lv[i].box_h);
-          return false;
-        }
-      }
       for (int i = 0; i < g.n_levels; i++) n_smem += g.lv[i].use_smem;
       st.levels_smem = n_smem;
       {  // share of the scan work per level, in processing order (coarse -> fine)
@@ -550,19 +555,44 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       }
       const size_t smem = k2_smem_bytes(g.table_bytes);
       const int grid = c->sm_count;
-      if (tracing) {
-        if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
-        else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
-        else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
-      } else if (c->nw == 1) {
-        k2_scan<1, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
-      } else if (c->nw == 4) {
-        k2_scan<4, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
-      } else {
-        k2_scan<2, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
+      // one launch per chunk of frames (a single chunk unless the host copy is being overlapped)
+      for (int ch = 0; ch < nchunks; ch++) {
+        const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
+        if (f1 <= f0) continue;
+        P.frames = d_frames + (size_t)f0 * fstride;
+        P.n_frames = f1 - f0;
+        P.frame_base = f0;
+        P.tile_counters = c->d_counters + ch * kMaxLevels;
+        for (int i = 0; i < g.n_levels && tma_ok; i++) {
+          if (!g.lv[i].use_smem) continue;
+          cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)(f1 - f0)};
+          cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
+          cuuint32_t box[3] = {(cuuint32_t)g.lv[i].box_w, (cuuint32_t)g.lv[i].box_h, 1};
+          cuuint32_t es[3] = {1, 1, 1};
+          CUresult cr = c->encode(&P.maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)P.frames, dims, strides, box,
+                                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (cr != CUDA_SUCCESS) {
+            set_err("cuTensorMapEncodeTiled failed (%d) for level %d box %dx%d", (int)cr, i, g.lv[i].box_w, g.lv[i].box_h);
+            return false;
+          }
+        }
+        if (nchunks > 1) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[ch], 0));
+        if (tracing) {
+          if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
+          else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
+          else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
+        } else if (c->nw == 1) {
+          k2_scan<1, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
+        } else if (c->nw == 4) {
+          k2_scan<4, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
+        } else {
+          k2_scan<2, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
+        }
+        CU_OK(cudaGetLastError());
+        st.scan_launches++;
       }
-      CU_OK(cudaGetLastError());
-      st.scan_launches++;
+
     }
     CU_OK(cudaEventRecord(c->ev[3], s));
     if (use_scan) {  // stage 0 of the survivors: leaves + regression gather, cohort-staged
@@ -595,6 +625,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       Q.dense = use_scan ? 0 : 1; Q.dense_total = total_windows;
       Q.t_start = use_scan ? 1 : 0; Q.init_shape = use_scan ? c->d_shape0.p : nullptr;
       Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
+      Q.work_counter = c->d_counters + kCntWork;
       Q.rec_words = rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
       if (tracing) {
         Q.trace_n = c->d_trace_n.p; Q.trace_s = c->d_trace_s.p;
@@ -630,7 +661,8 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     }
     CU_OK(cudaEventRecord(c->ev[5], s));
     CU_OK(cudaStreamSynchronize(s));
-    cudaEventElapsedTime(&st.ms_h2d, c->ev[0], c->ev[1]);
+    if (b.flags & JDA_B200_DEVICE_INPUT) st.ms_h2d = 0.f;
+    else cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[nchunks - 1]);
     cudaEventElapsedTime(&st.ms_resize, c->ev[1], c->ev[2]);
     cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
     cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);

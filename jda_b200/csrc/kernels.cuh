@@ -66,6 +66,7 @@ struct ScanParams {
   const uint8_t *frames;
   size_t frame_stride;
   int pitch, W, H, n_frames;
+  int frame_base;                // index of frames[0] inside the caller's batch (chunked launches)
   int n_levels, K, table_bytes;
   const uint8_t *tables;         // n_levels x table_bytes (padded to 128)
   const Stage0Norm *norms;       // kMaxNorm entries
@@ -115,6 +116,7 @@ struct CascadeParams {
   float *hits;         // records of rec_words 4-byte words
   unsigned *hit_count;
   unsigned hit_cap;
+  unsigned *work_counter;  // queue mode: next survivor to take (dynamic distribution evens out deep survivors)
   int rec_words;
   float th;
   int use_th;
@@ -465,7 +467,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
   c.tw_log2 = lv.tw_log2; c.tw_mask = (1 << lv.tw_log2) - 1; c.step = lv.step;
   c.pitch = SMEM ? lv.box_w : P.pitch;
   c.gbase = P.frames + (size_t)frame * P.frame_stride + (size_t)(y0w * lv.step) * P.pitch + (size_t)x0w * lv.step;
-  c.gw0 = (long long)frame * P.windows_per_frame + lv.win_base;
+  c.gw0 = (long long)(frame + P.frame_base) * P.windows_per_frame + lv.win_base;
   c.tile_off = tile_off; c.x0w = x0w; c.y0w = y0w; c.cw = cw; c.lane = lane;
 
   int n = ch << c.tw_log2;  // dense enumeration; columns >= cw are masked off in phase 0
@@ -508,7 +510,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
       const unsigned slot = slot0 + __popc(m & ((1u << lane) - 1u));
       const int w = lwid[e];
       if (slot < P.surv_cap)
-        P.surv[slot] = make_uint4((unsigned)frame, pack_key(li, y0w + (w >> c.tw_log2), x0w + (w & c.tw_mask)),
+        P.surv[slot] = make_uint4((unsigned)(frame + P.frame_base), pack_key(li, y0w + (w >> c.tw_log2), x0w + (w & c.tw_mask)),
                                   __float_as_uint(lscore[e]), 0u);
     }
   }
@@ -683,7 +685,16 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
   uint8_t *leafs = reinterpret_cast<uint8_t *>(shape + kMaxDim);
 
   const long long total = P.dense ? P.dense_total : (long long)min(*P.surv_count, P.surv_cap);
-  for (long long e = (long long)blockIdx.x * K3_WARPS + warp; e < total; e += (long long)gridDim.x * K3_WARPS) {
+  long long e = (long long)blockIdx.x * K3_WARPS + warp - (long long)gridDim.x * K3_WARPS;
+  for (;;) {
+    if (P.dense) {
+      e += (long long)gridDim.x * K3_WARPS;
+    } else {
+      unsigned t = 0;
+      if (lane == 0) t = atomicAdd(P.work_counter, 1u);
+      e = (long long)__shfl_sync(0xffffffffu, t, 0);
+    }
+    if (e >= total) break;
     int frame, level, xi, yi;
     float score0 = 0.f;
     if (P.dense) {
@@ -767,15 +778,17 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
         }
         // replay the score over this chunk in cart order
         const int cnt = min(32, P.K - kc);
+        const unsigned normed = __ballot_sync(0xffffffffu, cp.y != 0.f || cp.z != 1.f);  // carts with a real (mean, std)
         int stop = -1;
         for (int j = 0; j < cnt; j++) {
           const float sj = __shfl_sync(0xffffffffu, ls, j);
           const float thj = __shfl_sync(0xffffffffu, cp.x, j);
-          const float mj = __shfl_sync(0xffffffffu, cp.y, j);
-          const float dj = __shfl_sync(0xffffffffu, cp.z, j);
           score = __fadd_rn(score, sj);                      // c/jda.c:396
-          // c/jda.c:397; (score - 0) / 1 is score exactly, so the divide only runs where it matters
-          if (mj != 0.f || dj != 1.f) score = __fdiv_rn(__fsub_rn(score, mj), dj);
+          if ((normed >> j) & 1u) {                          // c/jda.c:397; (score - 0) / 1 is score exactly
+            const float mj = __shfl_sync(0xffffffffu, cp.y, j);
+            const float dj = __shfl_sync(0xffffffffu, cp.z, j);
+            score = __fdiv_rn(__fsub_rn(score, mj), dj);
+          }
           n_eval++;
           if (score < thj) { stop = j; break; }              // c/jda.c:399
         }

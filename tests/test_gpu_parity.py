@@ -247,6 +247,24 @@ def test_mixed_size_frames_fddb_shaped(casc, oracle, oracle_shipped):
         _same(g, oracle.detect(oracle_shipped, f, th=-0.5))
 
 
+def test_chunked_host_batch_equals_resident(casc, oracle, oracle_shipped):
+    """>= 128 host frames are copied and scanned in overlapping chunks; same answer as one resident batch"""
+    import torch
+    frames = synth.make_frames("facemix", 131, 200, 150, seed0=900)
+    frames[7, 20:128, 30:141] = np.load(os.path.join(os.path.dirname(__file__), "golden", "face_111x108.npy"))
+    host = casc.detect_batch(frames, th=-0.5)
+    assert casc.last_stats["scan_launches"] == 4
+    d = torch.from_numpy(frames).cuda()
+    torch.cuda.synchronize()
+    dev = casc.detect_batch(None, device_ptr=d.data_ptr(), shape=tuple(d.shape), th=-0.5)
+    assert casc.last_stats["scan_launches"] == 1
+    assert sum(len(r[1]) for r in host) >= 1
+    for a, b in zip(host, dev):
+        _same(a, b)
+    for f in (0, 7, 65, 130):
+        _same(host[f], oracle.detect(oracle_shipped, frames[f], th=-0.5))
+
+
 @pytest.mark.parametrize("t_limit", [1, 2, 5])
 def test_mining_mode_truncated_cascade(casc, oracle, oracle_shipped, t_limit):
     """Validate()'s partial cascade (src/jda/cascador.cpp:178-197): first t stages, every survivor
