@@ -320,6 +320,42 @@ def main():
                      "k3_ms": ac["ms_cascade"] / 5}
             del t
         out["by_distribution"] = by
+    if not a.no_breakdown and not dist_on:
+        # the other BASELINE.json configs, as context (not the headline): config 3 = one 1080p frame per
+        # plain jdaDetect call (5-octave pyramid), config 5 = mining scan (first stage only, every survivor)
+        from jda_b200 import synth
+        ex = {}
+        hd = [synth.facemix_frame(7000 + i, 1920, 1080) for i in range(4)]
+        for i in range(6):
+            c.detect(hd[i % 4], 1.25, 0.1, 24, 768, 0.0)
+        lat = []
+        for i in range(40):
+            t0 = time.perf_counter()
+            c.detect(hd[i % 4], 1.25, 0.1, 24, 768, 0.0)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        ex["cfg3_1080p_5oct_jdaDetect_ms"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                                              "windows_per_frame": 1245202}
+        vga = synth.noise_frame(1)
+        for i in range(6):
+            c.detect(vga, 1.25, 0.1, 24, 192, 0.0)
+        lat = []
+        for i in range(40):
+            t0 = time.perf_counter()
+            c.detect(vga, 1.25, 0.1, 24, 192, 0.0)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        ex["vga_3oct_single_frame_jdaDetect_ms"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99))}
+        p = frame_pool(32, "noise", 9000)
+        t = torch.from_numpy(tile_batch(p, B, 0)).cuda()
+        torch.cuda.synchronize()
+
+        def mine(i, t=t):
+            c.detect_batch(None, device_ptr=t.data_ptr(), shape=(B, H, W), unpack=False, scale=1.25, min_size=24,
+                           max_size=192, th=0.0, t_limit=1, flags=api.RAW_HITS | api.NO_FINAL_TH)
+            return c.last_stats
+        m, ac, _ = timed(mine, 5, 2)
+        ex["cfg5_mining_stage1_noise"] = {"windows_per_s": 5 * B * WINDOWS_PER_FRAME / (m * 1e-3),
+                                          "survivors_per_step": ac["raw_hits"] / 5}
+        out["other_configs"] = ex
     if rank == 0:
         print(json.dumps(out), flush=True)
     c.close()
