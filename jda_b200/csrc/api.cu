@@ -125,6 +125,9 @@ struct Context {
   unsigned *d_counters = nullptr;  // [kMaxLevels] tile counters, [kMaxLevels] surv_count, [+1] hit_count
   unsigned *h_counters = nullptr;  // pinned mirror
   std::vector<float> h_hits;
+  float *h_eager = nullptr;        // pinned: the first kEagerHits hit records
+  uint8_t *h_stage = nullptr;      // pinned staging for small pageable inputs
+  size_t h_stage_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t surv_cap = 0, hit_cap = 0;
   jdaB200Stats last;
@@ -134,6 +137,7 @@ struct Context {
   cudaStream_t stream() const { return user_stream ? user_stream : own_stream; }
 };
 
+constexpr size_t kEagerHits = 64;
 constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntHit = kCntSurv + 1, kCntWork = kCntSurv + 2, kCntTotal = kCntSurv + 3;
 
 size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * K2_WARP_BYTES; }
@@ -183,6 +187,9 @@ bool ctx_init(Context *c) {
   CU_OK(cudaMemcpy(c->d_mean, m.mean_shape.data(), m.mean_shape.size() * 4, cudaMemcpyHostToDevice));
   CU_OK(cudaMalloc(&c->d_counters, kCntTotal * sizeof(unsigned)));
   CU_OK(cudaMallocHost(&c->h_counters, kCntTotal * sizeof(unsigned)));
+  CU_OK(cudaMallocHost(&c->h_eager, kEagerHits * (kHitHeader + kMaxDim) * sizeof(float)));
+  c->h_stage_cap = (size_t)8 << 20;
+  CU_OK(cudaMallocHost(&c->h_stage, c->h_stage_cap));
   {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -233,6 +240,8 @@ void ctx_free(Context *c) {
     cudaFree(c->d_nodes); cudaFree(c->d_leaf); cudaFree(c->d_cart); cudaFree(c->d_w); cudaFree(c->d_mean);
     cudaFree(c->d_norms); cudaFree(c->d_counters);
     cudaFreeHost(c->h_counters);
+    cudaFreeHost(c->h_eager);
+    cudaFreeHost(c->h_stage);
     c->d_tables.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
     c->d_surv.release(); c->d_shape0.release(); c->d_tables_packed.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -420,7 +429,7 @@ struct TraceOut {
 // Runs the device path for one batch; on success `hits` holds the raw hit records sorted into scan
 // order (frame, level, y, x).  `store` keeps the record floats alive.
 bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, std::vector<HitRec> &hits,
-                const TraceOut *trace) {
+                const TraceOut *trace, bool timing) {
   hits.clear();
   jdaB200Stats &st = c->last;
   memset(&st, 0, sizeof st);
@@ -442,7 +451,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   const int rec_words = kHitHeader + D;
   const int t_run = (b.t_limit > 0 && b.t_limit < m.T) ? b.t_limit : m.T;
 
-  CU_OK(cudaEventRecord(c->ev[0], s));
+  if (timing) CU_OK(cudaEventRecord(c->ev[0], s));
   // ---- frames
   const uint8_t *d_frames;
   int pitch;
@@ -460,6 +469,23 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       nchunks = kMaxChunks;
     CU_OK(cudaEventRecord(c->ev_copy[kMaxChunks], s));
     CU_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
+    // a small pageable input is repacked into pinned staging on the host (device pitch) and sent as one
+    // asynchronous copy; the driver's own pageable path costs more than the whole detect for one frame
+    bool staged = false;
+    if (nchunks == 1 && fstride * b.n_frames <= c->h_stage_cap) {
+      cudaPointerAttributes pa;
+      const bool pageable = cudaPointerGetAttributes(&pa, frames) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+      cudaGetLastError();
+      if (pageable) {
+        for (int f = 0; f < b.n_frames; f++)
+          for (int y = 0; y < b.height; y++)
+            memcpy(c->h_stage + f * fstride + (size_t)y * pitch, frames + f * b.frame_stride + (size_t)y * b.pitch, b.width);
+        CU_OK(cudaMemcpyAsync(c->d_frames.p, c->h_stage, fstride * b.n_frames, cudaMemcpyHostToDevice, c->copy_stream));
+        CU_OK(cudaEventRecord(c->ev_copy[0], c->copy_stream));
+        staged = true;
+      }
+    }
+    if (!staged)
     for (int ch = 0; ch < nchunks; ch++) {
       const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
       if (b.frame_stride == (size_t)b.pitch * b.height) {
@@ -475,7 +501,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     if (nchunks == 1) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[0], 0));
     d_frames = c->d_frames.p;
   }
-  CU_OK(cudaEventRecord(c->ev[1], s));
+  if (timing) CU_OK(cudaEventRecord(c->ev[1], s));
 
   // ---- h / q planes (c/jda.c:450-457), only when some node samples them
   const float r = 1.f / sqrtf(2.f);
@@ -518,7 +544,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * rec_words)) return false;
     if (use_scan && !c->d_shape0.ensure(c->surv_cap * D)) return false;
     CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
-    CU_OK(cudaEventRecord(c->ev[2], s));
+    if (timing) CU_OK(cudaEventRecord(c->ev[2], s));
     if (use_scan) {
       ScanParams P;
       memset(&P, 0, sizeof P);
@@ -594,7 +620,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       }
 
     }
-    CU_OK(cudaEventRecord(c->ev[3], s));
+    if (timing) CU_OK(cudaEventRecord(c->ev[3], s));
     if (use_scan) {  // stage 0 of the survivors: leaves + regression gather, cohort-staged
       Stage0Params S;
       memset(&S, 0, sizeof S);
@@ -639,8 +665,11 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       CU_OK(cudaGetLastError());
       st.cascade_launches++;
     }
-    CU_OK(cudaEventRecord(c->ev[4], s));
+    if (timing) CU_OK(cudaEventRecord(c->ev[4], s));
     CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    // the first records ride along with the counters: a call with few hits needs a single round trip
+    const size_t eager = std::min<size_t>(kEagerHits, c->hit_cap);
+    CU_OK(cudaMemcpyAsync(c->h_eager, c->d_hits.p, eager * rec_words * 4, cudaMemcpyDeviceToHost, s));
     CU_OK(cudaStreamSynchronize(s));
     const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
     if (ns > c->surv_cap || nh > c->hit_cap) {  // queues overflowed: grow and run again
@@ -650,8 +679,14 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     }
     st.stage0_survivors = use_scan ? (long long)ns : 0;
     st.raw_hits = (long long)nh;
-    c->h_hits.resize(nh * rec_words);
-    if (nh) CU_OK(cudaMemcpyAsync(c->h_hits.data(), c->d_hits.p, nh * rec_words * 4, cudaMemcpyDeviceToHost, s));
+    bool more = false;
+    c->h_hits.resize(std::max(nh, (size_t)1) * rec_words);
+    memcpy(c->h_hits.data(), c->h_eager, std::min(nh, eager) * rec_words * 4);
+    if (nh > eager) {
+      CU_OK(cudaMemcpyAsync(c->h_hits.data() + eager * rec_words, c->d_hits.p + eager * rec_words,
+                            (nh - eager) * rec_words * 4, cudaMemcpyDeviceToHost, s));
+      more = true;
+    }
     if (tracing) {
       if (trace->n) CU_OK(cudaMemcpyAsync(trace->n, c->d_trace_n.p, total_windows * 4, cudaMemcpyDeviceToHost, s));
       if (trace->s) CU_OK(cudaMemcpyAsync(trace->s, c->d_trace_s.p, total_windows * 4, cudaMemcpyDeviceToHost, s));
@@ -659,14 +694,16 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         CU_OK(cudaMemcpyAsync(trace->leaf, c->d_trace_leaf.p, (size_t)(trace->w1 - trace->w0) * leaf_stride,
                               cudaMemcpyDeviceToHost, s));
     }
-    CU_OK(cudaEventRecord(c->ev[5], s));
-    CU_OK(cudaStreamSynchronize(s));
-    if (b.flags & JDA_B200_DEVICE_INPUT) st.ms_h2d = 0.f;
-    else cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[nchunks - 1]);
-    cudaEventElapsedTime(&st.ms_resize, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);
-    cudaEventElapsedTime(&st.ms_d2h, c->ev[4], c->ev[5]);
+    if (timing) CU_OK(cudaEventRecord(c->ev[5], s));
+    if (more || tracing || timing) CU_OK(cudaStreamSynchronize(s));
+    if (timing) {
+      if (b.flags & JDA_B200_DEVICE_INPUT) st.ms_h2d = 0.f;
+      else cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[nchunks - 1]);
+      cudaEventElapsedTime(&st.ms_resize, c->ev[1], c->ev[2]);
+      cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
+      cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);
+      cudaEventElapsedTime(&st.ms_d2h, c->ev[4], c->ev[5]);
+    }
     hits.resize(nh);
     for (size_t i = 0; i < nh; i++) {
       const float *rec = c->h_hits.data() + i * rec_words;
@@ -727,7 +764,7 @@ int detect_batch(Context *c, const unsigned char *frames, const jdaB200Batch &b,
   int prev_dev = -1;
   cudaGetDevice(&prev_dev);
   std::vector<HitRec> hits;
-  const bool ok = run_device(c, frames, b, hits, nullptr);
+  const bool ok = run_device(c, frames, b, hits, nullptr, stats != nullptr);
   if (!ok) {
     for (int f = 0; f < b.n_frames; f++) results[f] = empty_result(c->m.L, -1);
     if (prev_dev >= 0) cudaSetDevice(prev_dev);
@@ -906,7 +943,7 @@ long long jdaB200Trace(void *cascador, const unsigned char *frame, int width, in
   TraceOut t;
   t.n = carts_evaluated; t.s = exit_score; t.leaf = leaves; t.w0 = leaf_w0; t.w1 = leaf_w1;
   std::vector<HitRec> hits;
-  if (!run_device(c, frame, b, hits, &t)) return -1;
+  if (!run_device(c, frame, b, hits, &t, false)) return -1;
   return c->last.windows;
 }
 
