@@ -301,13 +301,14 @@ int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflic
 // read pixels from global memory in "virtual" tiles of 32 x 16 windows.  Among the shapes that fit,
 // the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
 // pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
-int g_max_span = 4;  // coarse levels pool up to 4 warps' tile buffers (measured +2.4 % over the global-memory path, r1)
+int g_max_span = K2_WARPS;  // coarse levels pool 2, 4 or all warps' tile buffers
 
 // best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
-int plan_tile(LevelInfo &L, int tile_bytes) {
+int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3) {
   double best_cost = 1e30;
   int best_windows = 0;
-  for (int tl = 5; tl >= 3; tl--) {
+  tile_bytes = std::min(tile_bytes, 65536);  // one TMA box (<= 256 x 256)
+  for (int tl = 5; tl >= min_tl; tl--) {
     const int tw = 1 << tl;
     // TMA wants the box to start on a 16-byte boundary in x: tiles whose x origin (tx * tw * step) is not
     // a multiple of 16 start their box at the aligned address below it and carry up to 15 spare bytes
@@ -322,7 +323,7 @@ int plan_tile(LevelInfo &L, int tile_bytes) {
       const int bh = (th - 1) * L.step + L.win;
       if ((long long)L.win * bw + L.win >= 65536) continue;  // u16 tile offsets
       const int windows = std::min(tw, L.nx) * th;
-      if (windows < g_min_tile_windows) continue;
+      if (windows < (min_tl < 3 ? std::min(g_min_tile_windows, 6) : g_min_tile_windows)) continue;
       // default: most windows per tile, wider tiles on ties; tuned: modelled wavefronts x tail factor
       const double cost = g_tune_pitch ? (4.0 + 6.0 * estimate_wavefronts(L.win, L.step, tw, th, bw)) * (1.0 + 40.0 / windows)
                                        : -(double)windows;
@@ -349,18 +350,23 @@ void plan_level(LevelInfo &L) {
   if (plan_tile(L, K2_TILE_BYTES) > 0) {
     L.use_smem = 1;  // fits a single warp's buffer: every warp works
   } else {
-    // lend buffers: more bytes per tile (more windows, shorter tails) against fewer working warps
+    // pool buffers: more bytes per tile (more windows) against fewer independent groups.  With every
+    // warp of the block on one tile (span == K2_WARPS) even the coarsest windows fit; their few windows
+    // per warp go straight to cart-parallel straggler mode, which is also what keeps single-frame
+    // latency short (a 512-window tile read from global memory is a ~0.5 ms dependent chain).
     double best = 0;
     LevelInfo pick = L;
-    for (int span = 2; span <= g_max_span && span <= 4 && K2_WARPS % span == 0; span *= 2) {
+    const int spans[3] = {2, 4, K2_WARPS};
+    for (int span : spans) {
+      if (span > g_max_span || K2_WARPS % span) continue;
       LevelInfo t = L;
-      const int windows = plan_tile(t, span * K2_TILE_BYTES);
+      const int windows = plan_tile(t, span * K2_TILE_BYTES, 1);
       const double score = windows * std::sqrt((double)K2_WARPS / span);
       if (windows > 0 && score > best) { best = score; pick = t; pick.use_smem = 1; pick.span = span; }
     }
     L = pick;
   }
-  if (!L.use_smem) { L.tw_log2 = 5; L.th = K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0; }
+  if (!L.use_smem) { L.tw_log2 = 5; L.th = 4; L.box_w = 0; L.box_h = 0; }  // windows > 256 px: global memory, small virtual tiles
   const int tw = 1 << L.tw_log2;
   L.ntx = (L.nx + tw - 1) / tw;
   L.nty = (L.ny + L.th - 1) / L.th;

@@ -141,12 +141,12 @@ def test_tile_origins_not_multiple_of_16(oracle, oracle_shipped):
         del os.environ["JDA_B200_MIN_TILE_WINDOWS"]
 
 
-@pytest.mark.parametrize("span", ["2", "4"])
+@pytest.mark.parametrize("span", ["1", "2", "4", "12"])
 def test_pooled_tile_buffers(oracle, oracle_shipped, span):
     """coarse levels served from tiles that span several warps' buffers, rows split across the group"""
     os.environ["JDA_B200_MAX_SPAN"] = span
     try:
-        assert any(p["span"] > 1 for p in api.describe_plan(640, 480))
+        assert span == "1" or any(p["span"] > 1 for p in api.describe_plan(640, 480))
         c = api.Cascador(SHIPPED_F32, double=False)
         for img in (synth.face_canvas(), synth.noise_frame(4)):
             nwin = api.count_windows(640, 480)

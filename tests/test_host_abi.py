@@ -106,10 +106,10 @@ def test_tile_plan_invariants(w, h, mx):
     assert [p["win"] for p in plan] == api.levels(w, h, 1.25, 24, mx)
     for p in plan:
         assert p["step"] == int(np.float32(p["win"]) * np.float32(0.1))
-        assert p["tw"] * p["th"] <= 512 and p["tw"] in (8, 16, 32)
+        assert p["tw"] * p["th"] <= 512 and p["tw"] in (2, 4, 8, 16, 32)
         if p["smem"]:
             assert p["box_w"] % 16 == 0 and p["box_w"] <= 256 and p["box_h"] <= 256
-            assert p["span"] in (1, 2, 4) and p["box_w"] * p["box_h"] <= 8192 * p["span"]
+            assert p["span"] in (1, 2, 4, 12) and p["box_w"] * p["box_h"] <= min(8192 * p["span"], 65536)
             slack = 0 if (p["tw"] * p["step"]) % 16 == 0 else 15
             assert p["box_w"] >= (p["tw"] - 1) * p["step"] + p["win"] + slack
             assert p["box_h"] == (p["th"] - 1) * p["step"] + p["win"]
