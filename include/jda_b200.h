@@ -139,7 +139,8 @@ JDA_API long long jdaB200CountWindows(int width, int height, float scale, int mi
 JDA_API void jdaB200Nms(int n, const int *bboxes, const float *scores, unsigned char *keep);
 
 /* The scan kernel's tile plan for a (w, h) frame, one text line per pyramid level:
- * "win step nx ny tw th box_w box_h smem windows span".  Returns the number of levels (host only). */
+ * "win step nx ny tw th box_w box_h smem windows span".  Returns the number of levels (host only).
+ * cap > 0: the throughput plan (batches of more than 4 frames); cap < 0: the latency plan, |cap| bytes. */
 JDA_API int jdaB200DescribePlan(int width, int height, float scale, int min_size, int max_size,
                                 char *buf, int cap);
 

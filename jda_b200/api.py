@@ -127,10 +127,10 @@ def count_windows(w, h, scale=1.25, min_size=24, max_size=-1):
     return int(lib().jdaB200CountWindows(w, h, scale, min_size, max_size))
 
 
-def describe_plan(w, h, scale=1.25, min_size=24, max_size=-1):
-    """scan-kernel tile plan: list of dicts per level (host only)."""
+def describe_plan(w, h, scale=1.25, min_size=24, max_size=-1, latency=False):
+    """scan-kernel tile plan: list of dicts per level (host only).  latency=True: plan of <= 4-frame calls."""
     buf = C.create_string_buffer(4096)
-    lib().jdaB200DescribePlan(w, h, scale, min_size, max_size, buf, 4096)
+    lib().jdaB200DescribePlan(w, h, scale, min_size, max_size, buf, -4096 if latency else 4096)
     keys = ["win", "step", "nx", "ny", "tw", "th", "box_w", "box_h", "smem", "windows", "span"]
     return [dict(zip(keys, map(int, ln.split()))) for ln in buf.value.decode().splitlines()]
 

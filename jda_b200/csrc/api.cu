@@ -73,6 +73,7 @@ struct DevBuf {
 struct Geometry {
   int w = 0, h = 0, min_size = 0, max_size = 0;
   float scale = 0.f;
+  bool latency = false;  // which tile plan (see plan_level)
   int n_levels = 0;
   LevelInfo lv[kMaxLevels];
   long long windows_per_frame = 0;
@@ -138,6 +139,7 @@ struct Context {
 };
 
 constexpr size_t kEagerHits = 64;
+constexpr int kLatencyFrames = 4;  // batches this small use the latency tile plan
 constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntHit = kCntSurv + 1, kCntWork = kCntSurv + 2, kCntTotal = kCntSurv + 3;
 
 size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * K2_WARP_BYTES; }
@@ -301,7 +303,7 @@ int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflic
 // read pixels from global memory in "virtual" tiles of 32 x 16 windows.  Among the shapes that fit,
 // the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
 // pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
-int g_max_span = K2_WARPS;  // coarse levels pool 2, 4 or all warps' tile buffers
+int g_max_span = -1;  // -1: by mode (throughput plan: up to 4 warps' buffers; latency plan: the whole block's)
 
 // best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
 int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3) {
@@ -341,10 +343,16 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3) {
 // (with its 16-byte-granular pixel box) fits a warp's 8 KB buffer -- or, for coarser levels, the
 // buffers of 2 or 4 neighbouring warps (only every 2nd / 4th warp then works on that level).  Levels
 // that fit neither read pixels from global memory in "virtual" tiles of 32 x 16 windows.
-void plan_level(LevelInfo &L) {
+void plan_level(LevelInfo &L, bool latency) {
   if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
   if (const char *e = getenv("JDA_B200_TUNE_PITCH")) g_tune_pitch = atoi(e);
   if (const char *e = getenv("JDA_B200_MAX_SPAN")) g_max_span = std::max(1, atoi(e));
+  // Two plans.  Throughput (many frames in flight): coarse levels pool at most 4 warps' buffers, what is
+  // left reads global memory in 512-window virtual tiles -- measured fastest on 128+ frame batches.
+  // Latency (a handful of frames): the coarsest levels pool the whole block's buffers and go straight to
+  // cart-parallel straggler mode, global-memory tiles are small: a single VGA frame's scan drops from
+  // 0.58 ms to 0.29 ms because no warp is left with a 0.5 ms dependent chain.
+  const int max_span = g_max_span > 0 ? g_max_span : (latency ? K2_WARPS : 4);
   L.use_smem = 0;
   L.span = 1;
   if (plan_tile(L, K2_TILE_BYTES) > 0) {
@@ -358,26 +366,27 @@ void plan_level(LevelInfo &L) {
     LevelInfo pick = L;
     const int spans[3] = {2, 4, K2_WARPS};
     for (int span : spans) {
-      if (span > g_max_span || K2_WARPS % span) continue;
+      if (span > max_span || K2_WARPS % span) continue;
       LevelInfo t = L;
-      const int windows = plan_tile(t, span * K2_TILE_BYTES, 1);
+      const int windows = plan_tile(t, span * K2_TILE_BYTES, latency ? 1 : 3);
       const double score = windows * std::sqrt((double)K2_WARPS / span);
       if (windows > 0 && score > best) { best = score; pick = t; pick.use_smem = 1; pick.span = span; }
     }
     L = pick;
   }
-  if (!L.use_smem) { L.tw_log2 = 5; L.th = 4; L.box_w = 0; L.box_h = 0; }  // windows > 256 px: global memory, small virtual tiles
+  if (!L.use_smem) { L.tw_log2 = 5; L.th = latency ? 4 : K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0; }  // global-memory virtual tiles
   const int tw = 1 << L.tw_log2;
   L.ntx = (L.nx + tw - 1) / tw;
   L.nty = (L.ny + L.th - 1) / L.th;
 }
 
-bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int max_size, bool force_global) {
+bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int max_size, bool latency) {
   Geometry &g = c->geo;
-  if (g.valid && g.w == w && g.h == h && g.scale == scale && g.min_size == min_size && g.max_size == max_size)
+  if (g.valid && g.w == w && g.h == h && g.scale == scale && g.min_size == min_size && g.max_size == max_size &&
+      g.latency == latency)
     return true;
   g.valid = false;
-  g.w = w; g.h = h; g.scale = scale; g.min_size = min_size; g.max_size = max_size;
+  g.w = w; g.h = h; g.scale = scale; g.min_size = min_size; g.max_size = max_size; g.latency = latency;
   int wins[kMaxLevels + 1];
   int n = (w < 24 || h < 24) ? 0 : enumerate_levels(w, h, scale, min_size, max_size, wins, kMaxLevels + 1);
   if (n > kMaxLevels) {
@@ -396,13 +405,12 @@ bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int ma
     L.nx = (w - L.win) / L.step + 1;
     L.ny = (h - L.win) / L.step + 1;
     if (L.nx > 8191 || L.ny > 8191) { set_err("frame too large for 13-bit window indices"); return false; }
-    plan_level(L);
+    plan_level(L, latency);
     L.table_off = i * g.table_bytes;
     L.win_base = base;
     base += (long long)L.nx * L.ny;
   }
   g.windows_per_frame = base;
-  (void)force_global;
   if (n > 0 && c->m.stage0_lut_ok) {
     std::vector<uint8_t> tab((size_t)n * g.table_bytes, 0);
     Stage0Norm norms[kMaxNorm];
@@ -445,8 +453,8 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     return false;
   }
   if (!ctx_init(c)) return false;
-  const bool force_global = false;
-  if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, force_global)) return false;
+  const bool latency_plan = b.n_frames <= kLatencyFrames;
+  if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, latency_plan)) return false;
   const Geometry &g = c->geo;
   st.n_levels = g.n_levels;
   st.windows = g.windows_per_frame * b.n_frames;
@@ -912,6 +920,8 @@ long long jdaB200CountWindows(int width, int height, float scale, int min_size, 
 }
 
 int jdaB200DescribePlan(int width, int height, float scale, int min_size, int max_size, char *buf, int cap) {
+  const bool latency = cap < 0;  // negative cap: describe the latency plan (batches of <= 4 frames)
+  if (cap < 0) cap = -cap;
   int wins[kMaxLevels + 1];
   int n = (width < 24 || height < 24) ? 0 : enumerate_levels(width, height, scale, min_size, max_size, wins, kMaxLevels + 1);
   n = std::min(n, kMaxLevels);
@@ -922,7 +932,7 @@ int jdaB200DescribePlan(int width, int height, float scale, int min_size, int ma
     memset(&L, 0, sizeof L);
     L.win = wins[i]; L.step = level_step(L.win);
     L.nx = (width - L.win) / L.step + 1; L.ny = (height - L.win) / L.step + 1;
-    plan_level(L);
+    plan_level(L, latency);
     if (buf && o < cap)
       o += snprintf(buf + o, cap - o, "%d %d %d %d %d %d %d %d %d %d %d\n", L.win, L.step, L.nx, L.ny, 1 << L.tw_log2,
                     L.th, L.box_w, L.box_h, L.use_smem, (1 << L.tw_log2) * L.th, L.span);

@@ -124,7 +124,7 @@ def test_tile_origins_not_multiple_of_16(oracle, oracle_shipped):
     at the aligned address below and the windows are addressed with the remainder."""
     os.environ["JDA_B200_MIN_TILE_WINDOWS"] = "32"
     try:
-        assert any(p["smem"] and (p["tw"] * p["step"]) % 16 for p in api.describe_plan(640, 480))
+        assert any(p["smem"] and (p["tw"] * p["step"]) % 16 for p in api.describe_plan(640, 480, latency=True))
         c = api.Cascador(SHIPPED_F32, double=False)
         img = synth.face_canvas()
         for flags in (0, api.NO_TMA):
@@ -146,7 +146,7 @@ def test_pooled_tile_buffers(oracle, oracle_shipped, span):
     """coarse levels served from tiles that span several warps' buffers, rows split across the group"""
     os.environ["JDA_B200_MAX_SPAN"] = span
     try:
-        assert span == "1" or any(p["span"] > 1 for p in api.describe_plan(640, 480))
+        assert span == "1" or any(p["span"] > 1 for p in api.describe_plan(640, 480, latency=True))
         c = api.Cascador(SHIPPED_F32, double=False)
         for img in (synth.face_canvas(), synth.noise_frame(4)):
             nwin = api.count_windows(640, 480)

@@ -100,9 +100,10 @@ def test_detect_without_gpu_fails_loudly():
 
 
 @pytest.mark.parametrize("w,h,mx", [(640, 480, 192), (640, 480, -1), (1920, 1080, 768), (60, 300, -1), (451, 333, -1)])
-def test_tile_plan_invariants(w, h, mx):
-    """every planned shared-memory tile fits the per-warp scratch and TMA's box rules"""
-    plan = api.describe_plan(w, h, 1.25, 24, mx)
+@pytest.mark.parametrize("latency", [False, True])
+def test_tile_plan_invariants(w, h, mx, latency):
+    """every planned shared-memory tile fits the pooled scratch and TMA's box rules"""
+    plan = api.describe_plan(w, h, 1.25, 24, mx, latency=latency)
     assert [p["win"] for p in plan] == api.levels(w, h, 1.25, 24, mx)
     for p in plan:
         assert p["step"] == int(np.float32(p["win"]) * np.float32(0.1))
