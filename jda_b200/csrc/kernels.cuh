@@ -674,6 +674,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
 // for k = 0..K-1 in ascending order -- 2L independent chains, each in the reference's order.
 
 constexpr int K3_WARPS = 4;
+constexpr int K3_G = 4;  // chunks of 32 carts walked together per survivor
 
 template <bool TRACE>
 __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constant__ CascadeParams P) {
@@ -734,77 +735,116 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
     int n_eval = resumed ? P.t_start * P.K : 0;
     bool rejected = false;
     for (int t = resumed ? P.t_start : 0; t < P.t_run && !rejected; t++) {
-      for (int kc = 0; kc < P.K && !rejected; kc += 32) {
-        const int k = kc + lane;
-        float ls = 0.f;
-        float4 cp = make_float4(0.f, 0.f, 1.f, 0.f);
-        if (k < P.K) {
-          const size_t c = (size_t)t * P.K + k;
-          const NodeRec *nd = P.nodes + c * kNodes;
-          int idx = 0;
+      // K3_G chunks of 32 carts are walked together (independent load chains: the tree walk is a string of
+      // dependent L2 accesses), then their scores are replayed chunk by chunk with early exit
+      for (int kc = 0; kc < P.K && !rejected; kc += 32 * K3_G) {
+        float ls[K3_G];
+        float4 cp[K3_G];
+        int idx[K3_G];
+        const NodeRec *nd[K3_G];
+        bool ok[K3_G];
 #pragma unroll
-          for (int lvl = 0; lvl < kDepth - 1; lvl++) {
-            const int4 a = __ldg(reinterpret_cast<const int4 *>(nd + idx));
-            const float4 o = __ldg(reinterpret_cast<const float4 *>(nd + idx) + 1);
+        for (int g = 0; g < K3_G; g++) {
+          const int k = kc + 32 * g + lane;
+          ok[g] = k < P.K;
+          nd[g] = P.nodes + ((size_t)t * P.K + (ok[g] ? k : 0)) * kNodes;
+          idx[g] = 0;
+          ls[g] = 0.f;
+          cp[g] = make_float4(0.f, 0.f, 1.f, 0.f);
+        }
+#pragma unroll
+        for (int lvl = 0; lvl < kDepth - 1; lvl++) {
+          int4 a[K3_G];
+          float4 o[K3_G];
+#pragma unroll
+          for (int g = 0; g < K3_G; g++) {
+            a[g] = __ldg(reinterpret_cast<const int4 *>(nd[g] + idx[g]));
+            o[g] = __ldg(reinterpret_cast<const float4 *>(nd[g] + idx[g]) + 1);
+          }
+          int p1[K3_G], p2[K3_G];
+#pragma unroll
+          for (int g = 0; g < K3_G; g++) {
             // a = scale, lm1, lm2, th ; o = o1x, o1y, o2x, o2y   (c/jda.c:371-389)
-            const float x1 = __fadd_rn(shape[a.y], o.x), y1 = __fadd_rn(shape[a.y + 1], o.y);
-            const float x2 = __fadd_rn(shape[a.z], o.z), y2 = __fadd_rn(shape[a.z + 1], o.w);
+            const float x1 = __fadd_rn(shape[a[g].y], o[g].x), y1 = __fadd_rn(shape[a[g].y + 1], o[g].y);
+            const float x2 = __fadd_rn(shape[a[g].z], o[g].z), y2 = __fadd_rn(shape[a[g].z + 1], o[g].w);
             int x1_ = __float2int_rz(__fmul_rn(x1, fwin)), y1_ = __float2int_rz(__fmul_rn(y1, fwin));
             int x2_ = __float2int_rz(__fmul_rn(x2, fwin)), y2_ = __float2int_rz(__fmul_rn(y2, fwin));
             x1_ = min(max(x1_, 0), win - 1); y1_ = min(max(y1_, 0), win - 1);
             x2_ = min(max(x2_, 0), win - 1); y2_ = min(max(y2_, 0), win - 1);
-            int p1, p2;
-            if (a.x == 0) {
-              p1 = __ldg(po + (size_t)(y + y1_) * P.pitch + x + x1_);
-              p2 = __ldg(po + (size_t)(y + y2_) * P.pitch + x + x2_);
+            if (a[g].x == 0) {
+              p1[g] = __ldg(po + (size_t)(y + y1_) * P.pitch + x + x1_);
+              p2[g] = __ldg(po + (size_t)(y + y2_) * P.pitch + x + x2_);
             } else {
               // h / q views keep w = win (c/jda.c:347,352); linear index like the reference, reads
               // past the plane buffer (undefined there) are defined as 0 here
-              const uint8_t *pp = (a.x == 1) ? ph : pq;
-              const int pw = (a.x == 1) ? P.hw : P.qw, phh = (a.x == 1) ? P.hh : P.qh;
-              const int bx = (a.x == 1) ? hx : qx, by = (a.x == 1) ? hy : qy;
+              const uint8_t *pp = (a[g].x == 1) ? ph : pq;
+              const int pw = (a[g].x == 1) ? P.hw : P.qw, phh = (a[g].x == 1) ? P.hh : P.qh;
+              const int bx = (a[g].x == 1) ? hx : qx, by = (a[g].x == 1) ? hy : qy;
               const long long lim = (long long)pw * phh;
               const long long i1 = (long long)(by + y1_) * pw + bx + x1_;
               const long long i2 = (long long)(by + y2_) * pw + bx + x2_;
-              p1 = (i1 < lim) ? (int)__ldg(pp + i1) : 0;
-              p2 = (i2 < lim) ? (int)__ldg(pp + i2) : 0;
+              p1[g] = (i1 < lim) ? (int)__ldg(pp + i1) : 0;
+              p2[g] = (i2 < lim) ? (int)__ldg(pp + i2) : 0;
             }
-            idx = (p1 - p2 <= a.w) ? 2 * idx + 1 : 2 * idx + 2;
           }
-          const int lf = idx - kNodes;
-          leafs[k] = (uint8_t)lf;
-          ls = __ldg(P.leaf + c * kLeaves + lf);
-          cp = __ldg(P.cart + c);
+#pragma unroll
+          for (int g = 0; g < K3_G; g++) idx[g] = (p1[g] - p2[g] <= a[g].w) ? 2 * idx[g] + 1 : 2 * idx[g] + 2;
         }
-        // replay the score over this chunk in cart order
-        const int cnt = min(32, P.K - kc);
-        const unsigned normed = __ballot_sync(0xffffffffu, cp.y != 0.f || cp.z != 1.f);  // carts with a real (mean, std)
-        int stop = -1;
-        for (int j = 0; j < cnt; j++) {
-          const float sj = __shfl_sync(0xffffffffu, ls, j);
-          const float thj = __shfl_sync(0xffffffffu, cp.x, j);
-          score = __fadd_rn(score, sj);                      // c/jda.c:396
-          if ((normed >> j) & 1u) {                          // c/jda.c:397; (score - 0) / 1 is score exactly
-            const float mj = __shfl_sync(0xffffffffu, cp.y, j);
-            const float dj = __shfl_sync(0xffffffffu, cp.z, j);
-            score = __fdiv_rn(__fsub_rn(score, mj), dj);
+#pragma unroll
+        for (int g = 0; g < K3_G; g++) {
+          if (ok[g]) {
+            const int k = kc + 32 * g + lane;
+            const size_t c = (size_t)t * P.K + k;
+            const int lf = idx[g] - kNodes;
+            leafs[k] = (uint8_t)lf;
+            ls[g] = __ldg(P.leaf + c * kLeaves + lf);
+            cp[g] = __ldg(P.cart + c);
           }
-          n_eval++;
-          if (score < thj) { stop = j; break; }              // c/jda.c:399
         }
-        if (TRACE && trace_leaf && k < P.K && (stop < 0 || lane <= stop))
-          P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + (size_t)t * P.K + k] = leafs[k];
-        if (stop >= 0) rejected = true;
+        // replay the score in cart order, one chunk of 32 at a time
+#pragma unroll
+        for (int g = 0; g < K3_G; g++) {
+          const int cnt = min(32, P.K - (kc + 32 * g));
+          if (cnt <= 0 || rejected) continue;
+          const unsigned normed = __ballot_sync(0xffffffffu, cp[g].y != 0.f || cp[g].z != 1.f);  // carts with a real (mean, std)
+          int stop = -1;
+          for (int j = 0; j < cnt; j++) {
+            const float sj = __shfl_sync(0xffffffffu, ls[g], j);
+            const float thj = __shfl_sync(0xffffffffu, cp[g].x, j);
+            score = __fadd_rn(score, sj);                      // c/jda.c:396
+            if ((normed >> j) & 1u) {                          // c/jda.c:397; (score - 0) / 1 is score exactly
+              const float mj = __shfl_sync(0xffffffffu, cp[g].y, j);
+              const float dj = __shfl_sync(0xffffffffu, cp[g].z, j);
+              score = __fdiv_rn(__fsub_rn(score, mj), dj);
+            }
+            n_eval++;
+            if (score < thj) { stop = j; break; }              // c/jda.c:399
+          }
+          if (TRACE && trace_leaf && ok[g] && (stop < 0 || lane <= stop))
+            P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + (size_t)t * P.K + kc + 32 * g + lane] = leafs[kc + 32 * g + lane];
+          if (stop >= 0) rejected = true;
+        }
       }
       if (rejected) break;
       __syncwarp();
       // global regression, c/jda.c:403-411
       const float *wt = P.w + (size_t)t * P.K * kLeaves * D;
-      for (int i = lane; i < D; i += 32) {
-        float acc = shape[i];
+      for (int i0 = 0; i0 < D; i0 += 128) {
+        // up to four coordinates per lane in one sweep over the K rows (independent chains, each k ascending)
+        float acc[4];
+        bool on[4];
+#pragma unroll
+        for (int h = 0; h < 4; h++) { on[h] = i0 + 32 * h + lane < D; acc[h] = on[h] ? shape[i0 + 32 * h + lane] : 0.f; }
 #pragma unroll 8
-        for (int k = 0; k < P.K; k++) acc = __fadd_rn(acc, __ldg(wt + (size_t)(k * kLeaves + leafs[k]) * D + i));
-        shape[i] = acc;
+        for (int k = 0; k < P.K; k++) {
+          const float *row = wt + (size_t)(k * kLeaves + leafs[k]) * D + i0 + lane;
+#pragma unroll
+          for (int h = 0; h < 4; h++)
+            if (on[h]) acc[h] = __fadd_rn(acc[h], __ldg(row + 32 * h));
+        }
+#pragma unroll
+        for (int h = 0; h < 4; h++)
+          if (on[h]) shape[i0 + 32 * h + lane] = acc[h];
       }
       __syncwarp();
     }
