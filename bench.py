@@ -290,7 +290,10 @@ def main():
         k2_s = acc["ms_scan"] / a.steps * 1e-3
         achieved = B * WINDOWS_PER_FRAME * bytes_pw / k2_s / 1e9
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                           "frac": achieved / peak, "traffic": None, "kernel": "k2_scan",
+                           "frac": achieved / peak,
+                           # dram__bytes_read+write of k2_scan from the committed ncu capture
+                           # (profiles/r1_final_metrics_k2_k3.txt: 87.8 MB for a 256-frame launch), scaled to B frames
+                           "traffic": 87.8e6 / 256 * B, "kernel": "k2_scan",
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                            "note": "logical (algorithmic touched) bytes: 118 B x carts/window + 216 B; data is "
                                    "served from shared memory/L2 so frac may exceed 1; compulsory DRAM is "
