@@ -101,7 +101,9 @@ struct Context {
   std::mutex mu;
   int device = -1;
   bool inited = false;
-  cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_stream = nullptr;
+  cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_k2[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_aux[2] = {nullptr, nullptr};
   cudaEvent_t ev_copy[kMaxChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int sm_count = 148;
   EncodeTiledFn encode = nullptr;
@@ -140,7 +142,8 @@ struct Context {
 
 constexpr size_t kEagerHits = 64;
 constexpr int kLatencyFrames = 4;  // batches this small use the latency tile plan
-constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntHit = kCntSurv + 1, kCntWork = kCntSurv + 2, kCntTotal = kCntSurv + 3;
+constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntWork = kCntSurv + kMaxChunks, kCntHit = kCntWork + kMaxChunks,
+              kCntTotal = kCntHit + 1;
 
 size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * K2_WARP_BYTES; }
 size_t k3s_smem_bytes(int K, int D) {
@@ -174,6 +177,9 @@ bool ctx_init(Context *c) {
   CU_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   for (auto &e : c->ev) CU_OK(cudaEventCreate(&e));
   CU_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU_OK(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+  for (auto &e : c->ev_k2) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : c->ev_aux) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : c->ev_copy) CU_OK(cudaEventCreate(&e));
   const HostModel &m = c->m;
   CU_OK(cudaMalloc(&c->d_nodes, m.nodes.size() * sizeof(NodeRec)));
@@ -249,6 +255,9 @@ void ctx_free(Context *c) {
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    for (auto &e : c->ev_k2) if (e) cudaEventDestroy(e);
+    for (auto &e : c->ev_aux) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
   }
   delete c;
@@ -470,7 +479,8 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   const uint8_t *d_frames;
   int pitch;
   size_t fstride;
-  int nchunks = 1;
+  int nchunks = 1;      // launches of the scan (and of the cascade kernels behind it)
+  int copy_chunks = 1;  // pieces the host batch is copied in
   if (b.flags & JDA_B200_DEVICE_INPUT) {
     d_frames = frames; pitch = b.pitch; fstride = b.frame_stride;
   } else {
@@ -480,7 +490,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     // Large host batches travel in chunks on a second stream; the scan of chunk i overlaps the copy of i+1.
     if (b.n_frames >= 128 && !m.any_scaled && m.stage0_lut_ok && !trace && !(b.flags & JDA_B200_NO_STAGE0_SCAN) &&
         !getenv("JDA_B200_NO_CHUNKS"))
-      nchunks = kMaxChunks;
+      nchunks = copy_chunks = kMaxChunks;
     CU_OK(cudaEventRecord(c->ev_copy[kMaxChunks], s));
     CU_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
     // a small pageable input is repacked into pinned staging on the host (device pitch) and sent as one
@@ -512,7 +522,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       }
       CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
     }
-    if (nchunks == 1) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[0], 0));
+    if (copy_chunks == 1) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[0], 0));
     d_frames = c->d_frames.p;
   }
   if (timing) CU_OK(cudaEventRecord(c->ev[1], s));
@@ -554,25 +564,34 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   c->surv_cap = std::max(c->surv_cap, (size_t)b.n_frames * 1024);
   c->hit_cap = std::max(c->hit_cap, (size_t)b.n_frames * 128);
 
+  // Chunks: a resident batch of >= 128 frames is also cut into kMaxChunks pieces so that the cascade
+  // kernels of chunk i (small, latency-bound, little shared memory: they fit on the SMs next to the
+  // persistent scan blocks) run on a second stream under the scan of chunk i+1.
+  if (nchunks == 1 && use_scan && !tracing && b.n_frames >= 128 && !m.any_scaled && !getenv("JDA_B200_NO_CHUNKS"))
+    nchunks = kMaxChunks;
+  const bool host_chunks = !(b.flags & JDA_B200_DEVICE_INPUT) && copy_chunks > 1;
+
   for (int attempt = 0; attempt < 4; attempt++) {
     if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * rec_words)) return false;
     if (use_scan && !c->d_shape0.ensure(c->surv_cap * D)) return false;
+    const size_t cap_chunk = c->surv_cap / nchunks;
     CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
     if (timing) CU_OK(cudaEventRecord(c->ev[2], s));
+
+    ScanParams P;
+    memset(&P, 0, sizeof P);
+    bool tma_ok = false;
     if (use_scan) {
-      ScanParams P;
-      memset(&P, 0, sizeof P);
       for (int i = 0; i < g.n_levels; i++) P.lv[i] = g.lv[i];
-      P.frames = d_frames; P.frame_stride = fstride; P.pitch = pitch; P.W = b.width; P.H = b.height;
-      P.n_frames = b.n_frames; P.n_levels = g.n_levels; P.K = m.K; P.table_bytes = g.table_bytes;
-      P.tables = c->d_tables.p; P.norms = c->d_norms; P.tile_counters = c->d_counters;
-      P.surv = c->d_surv.p; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)c->surv_cap;
+      P.frame_stride = fstride; P.pitch = pitch; P.W = b.width; P.H = b.height;
+      P.n_levels = g.n_levels; P.K = m.K; P.table_bytes = g.table_bytes;
+      P.tables = c->d_tables.p; P.norms = c->d_norms;
       P.windows_per_frame = g.windows_per_frame;
       P.n_sched = (int)c->sched.size();
       for (int i = 0; i < P.n_sched; i++) P.sched[i] = c->sched[i];
       // TMA needs 16-byte aligned base and strides
-      const bool tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)d_frames % 16 == 0) &&
-                          pitch % 16 == 0 && fstride % 16 == 0;
+      tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)d_frames % 16 == 0) && pitch % 16 == 0 &&
+               fstride % 16 == 0;
       int n_smem = 0;
       for (int i = 0; i < g.n_levels; i++) n_smem += g.lv[i].use_smem;
       st.levels_smem = n_smem;
@@ -593,16 +612,54 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         P.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;
         P.leaf_w0 = trace->w0; P.leaf_w1 = trace->w1; P.leaf_stride = leaf_stride;
       }
-      const size_t smem = k2_smem_bytes(g.table_bytes);
-      const int grid = c->sm_count;
-      // one launch per chunk of frames (a single chunk unless the host copy is being overlapped)
-      for (int ch = 0; ch < nchunks; ch++) {
-        const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
-        if (f1 <= f0) continue;
+    }
+    Stage0Params S;
+    memset(&S, 0, sizeof S);
+    S.frames = d_frames; S.frame_stride = fstride; S.pitch = pitch;
+    S.tables_packed = c->d_tables_packed.p; S.table_bytes = g.table_bytes;
+    S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
+    for (int i = 0; i < g.n_levels; i++) S.lv_step[i] = g.lv[i].step;
+    CascadeParams Q;
+    memset(&Q, 0, sizeof Q);
+    Q.frames = d_frames; Q.frame_stride = fstride; Q.pitch = pitch; Q.W = b.width; Q.H = b.height;
+    Q.hq = m.any_scaled ? c->d_hq.p : nullptr; Q.hq_stride = hq_stride; Q.hw = hw; Q.hh = hh; Q.qw = qw; Q.qh = qh;
+    Q.nodes = c->d_nodes; Q.leaf = c->d_leaf; Q.cart = c->d_cart; Q.w = c->d_w; Q.mean_shape = c->d_mean;
+    Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.t_run = t_run; Q.r = r;
+    Q.n_levels = g.n_levels;
+    for (int i = 0; i < g.n_levels; i++) {
+      Q.lv_win[i] = g.lv[i].win; Q.lv_step[i] = g.lv[i].step; Q.lv_nx[i] = g.lv[i].nx; Q.lv_ny[i] = g.lv[i].ny;
+      Q.lv_base[i] = g.lv[i].win_base;
+    }
+    Q.windows_per_frame = g.windows_per_frame;
+    Q.dense = use_scan ? 0 : 1; Q.dense_total = total_windows;
+    Q.t_start = use_scan ? 1 : 0;
+    Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
+    Q.rec_words = rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
+    if (tracing) {
+      Q.trace_n = c->d_trace_n.p; Q.trace_s = c->d_trace_s.p;
+      Q.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;
+      Q.leaf_w0 = trace->w0; Q.leaf_w1 = trace->w1; Q.leaf_stride = leaf_stride;
+    }
+
+    const bool piped = nchunks > 1;
+    cudaStream_t ks = piped ? c->aux_stream : s;  // where the cascade kernels go
+    if (piped && timing) {
+      CU_OK(cudaEventRecord(c->ev_aux[0], s));
+      CU_OK(cudaStreamWaitEvent(ks, c->ev_aux[0], 0));
+    } else if (piped) {
+      CU_OK(cudaEventRecord(c->ev_aux[0], s));
+      CU_OK(cudaStreamWaitEvent(ks, c->ev_aux[0], 0));  // counters are zeroed before any cascade kernel runs
+    }
+    for (int ch = 0; ch < nchunks; ch++) {
+      const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
+      if (f1 <= f0) continue;
+      const size_t qoff = (size_t)ch * cap_chunk;
+      if (use_scan) {
         P.frames = d_frames + (size_t)f0 * fstride;
         P.n_frames = f1 - f0;
         P.frame_base = f0;
         P.tile_counters = c->d_counters + ch * kMaxLevels;
+        P.surv = c->d_surv.p + qoff; P.surv_count = c->d_counters + kCntSurv + ch; P.surv_cap = (unsigned)cap_chunk;
         for (int i = 0; i < g.n_levels && tma_ok; i++) {
           if (!g.lv[i].use_smem) continue;
           cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)(f1 - f0)};
@@ -617,7 +674,9 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
             return false;
           }
         }
-        if (nchunks > 1) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[ch], 0));
+        if (host_chunks) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[ch], 0));  // copy_chunks == nchunks here
+        const size_t smem = k2_smem_bytes(g.table_bytes);
+        const int grid = c->sm_count;
         if (tracing) {
           if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
           else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
@@ -631,53 +690,33 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         }
         CU_OK(cudaGetLastError());
         st.scan_launches++;
+        if (piped) {
+          CU_OK(cudaEventRecord(c->ev_k2[ch], s));
+          CU_OK(cudaStreamWaitEvent(ks, c->ev_k2[ch], 0));
+        }
+        // stage 0 of this chunk's survivors: leaves + regression gather, cohort-staged
+        S.surv = c->d_surv.p + qoff; S.surv_count = c->d_counters + kCntSurv + ch; S.surv_cap = (unsigned)cap_chunk;
+        S.out_shape = c->d_shape0.p + qoff * D;
+        k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), ks>>>(S);
+        CU_OK(cudaGetLastError());
+        st.cascade_launches++;
       }
-
+      Q.surv = c->d_surv.p + qoff; Q.surv_count = c->d_counters + kCntSurv + ch; Q.surv_cap = (unsigned)cap_chunk;
+      Q.init_shape = use_scan ? c->d_shape0.p + qoff * D : nullptr;
+      Q.work_counter = c->d_counters + kCntWork + ch;
+      {
+        const int grid = c->sm_count * 8;
+        const size_t smem = k3_smem_bytes(m.K);
+        if (tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, ks>>>(Q);
+        else k3_cascade<false><<<grid, K3_WARPS * 32, smem, ks>>>(Q);
+        CU_OK(cudaGetLastError());
+        st.cascade_launches++;
+      }
     }
-    if (timing) CU_OK(cudaEventRecord(c->ev[3], s));
-    if (use_scan) {  // stage 0 of the survivors: leaves + regression gather, cohort-staged
-      Stage0Params S;
-      memset(&S, 0, sizeof S);
-      S.frames = d_frames; S.frame_stride = fstride; S.pitch = pitch;
-      S.tables_packed = c->d_tables_packed.p; S.table_bytes = g.table_bytes;
-      S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
-      for (int i = 0; i < g.n_levels; i++) S.lv_step[i] = g.lv[i].step;
-      S.surv = c->d_surv.p; S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)c->surv_cap;
-      S.out_shape = c->d_shape0.p;
-      k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), s>>>(S);
-      CU_OK(cudaGetLastError());
-      st.cascade_launches++;
-    }
-    {
-      CascadeParams Q;
-      memset(&Q, 0, sizeof Q);
-      Q.frames = d_frames; Q.frame_stride = fstride; Q.pitch = pitch; Q.W = b.width; Q.H = b.height;
-      Q.hq = m.any_scaled ? c->d_hq.p : nullptr; Q.hq_stride = hq_stride; Q.hw = hw; Q.hh = hh; Q.qw = qw; Q.qh = qh;
-      Q.nodes = c->d_nodes; Q.leaf = c->d_leaf; Q.cart = c->d_cart; Q.w = c->d_w; Q.mean_shape = c->d_mean;
-      Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.t_run = t_run; Q.r = r;
-      Q.n_levels = g.n_levels;
-      for (int i = 0; i < g.n_levels; i++) {
-        Q.lv_win[i] = g.lv[i].win; Q.lv_step[i] = g.lv[i].step; Q.lv_nx[i] = g.lv[i].nx; Q.lv_ny[i] = g.lv[i].ny;
-        Q.lv_base[i] = g.lv[i].win_base;
-      }
-      Q.windows_per_frame = g.windows_per_frame;
-      Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
-      Q.dense = use_scan ? 0 : 1; Q.dense_total = total_windows;
-      Q.t_start = use_scan ? 1 : 0; Q.init_shape = use_scan ? c->d_shape0.p : nullptr;
-      Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
-      Q.work_counter = c->d_counters + kCntWork;
-      Q.rec_words = rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
-      if (tracing) {
-        Q.trace_n = c->d_trace_n.p; Q.trace_s = c->d_trace_s.p;
-        Q.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;
-        Q.leaf_w0 = trace->w0; Q.leaf_w1 = trace->w1; Q.leaf_stride = leaf_stride;
-      }
-      const int grid = c->sm_count * 8;
-      const size_t smem = k3_smem_bytes(m.K);
-      if (tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, s>>>(Q);
-      else k3_cascade<false><<<grid, K3_WARPS * 32, smem, s>>>(Q);
-      CU_OK(cudaGetLastError());
-      st.cascade_launches++;
+    if (timing) CU_OK(cudaEventRecord(c->ev[3], s));  // end of the last scan
+    if (piped) {
+      CU_OK(cudaEventRecord(c->ev_aux[1], ks));
+      CU_OK(cudaStreamWaitEvent(s, c->ev_aux[1], 0));
     }
     if (timing) CU_OK(cudaEventRecord(c->ev[4], s));
     CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
@@ -685,9 +724,14 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     const size_t eager = std::min<size_t>(kEagerHits, c->hit_cap);
     CU_OK(cudaMemcpyAsync(c->h_eager, c->d_hits.p, eager * rec_words * 4, cudaMemcpyDeviceToHost, s));
     CU_OK(cudaStreamSynchronize(s));
-    const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
-    if (ns > c->surv_cap || nh > c->hit_cap) {  // queues overflowed: grow and run again
-      if (ns > c->surv_cap) c->surv_cap = ns + ns / 4;
+    size_t ns = 0, ns_max = 0;
+    for (int ch = 0; ch < nchunks; ch++) {
+      ns += c->h_counters[kCntSurv + ch];
+      ns_max = std::max(ns_max, (size_t)c->h_counters[kCntSurv + ch]);
+    }
+    const size_t nh = c->h_counters[kCntHit];
+    if (ns_max > cap_chunk || nh > c->hit_cap) {  // queues overflowed: grow and run again
+      if (ns_max > cap_chunk) c->surv_cap = (ns_max + ns_max / 4) * nchunks;
       if (nh > c->hit_cap) c->hit_cap = nh + nh / 4;
       continue;
     }
@@ -712,7 +756,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     if (more || tracing || timing) CU_OK(cudaStreamSynchronize(s));
     if (timing) {
       if (b.flags & JDA_B200_DEVICE_INPUT) st.ms_h2d = 0.f;
-      else cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[nchunks - 1]);
+      else cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[copy_chunks - 1]);
       cudaEventElapsedTime(&st.ms_resize, c->ev[1], c->ev[2]);
       cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
       cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);

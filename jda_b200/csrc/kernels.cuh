@@ -888,7 +888,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
 constexpr int K3S_WARPS = 8;
 constexpr int K3S_PER_WARP = 4;
 constexpr int K3S_COHORT = K3S_WARPS * K3S_PER_WARP;
-constexpr int K3S_CHUNK = 8;  // carts staged per step
+constexpr int K3S_CHUNK = 4;  // carts staged per step (6.9 KB x 2 buffers: the block fits on an SM next to a scan block)
+static_assert(K3S_CHUNK % 4 == 0, "leaf indices are fetched four at a time");
 
 struct Stage0Params {
   const uint8_t *frames;
@@ -986,13 +987,15 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
 #pragma unroll
       for (int s = 0; s < K3S_PER_WARP; s++) {
         if (c0 + warp * K3S_PER_WARP + s >= total) continue;  // no survivor in this seat: its leaves are stale
-        // the chunk's 8 leaf indices of this survivor in two 32-bit loads (kpad and k0 are multiples of 4)
+        // the chunk's leaf indices of this survivor, four per 32-bit load (kpad and k0 are multiples of 4)
         const uint32_t *lp = reinterpret_cast<const uint32_t *>(leaves + (warp * K3S_PER_WARP + s) * kpad + k0);
-        const uint32_t l03 = lp[0], l47 = lp[1];
+        uint32_t lq[K3S_CHUNK / 4];
+#pragma unroll
+        for (int q = 0; q < K3S_CHUNK / 4; q++) lq[q] = lp[q];
 #pragma unroll
         for (int cl = 0; cl < K3S_CHUNK; cl++) {
           if (cl < carts) {
-            const uint32_t leaf = ((cl < 4 ? l03 : l47) >> (8 * (cl & 3))) & 0xffu;
+            const uint32_t leaf = (lq[cl >> 2] >> (8 * (cl & 3))) & 0xffu;
             const float2 *row = reinterpret_cast<const float2 *>(rb + (cl * kLeaves + leaf) * D);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
