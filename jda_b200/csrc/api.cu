@@ -177,7 +177,11 @@ bool ctx_init(Context *c) {
   CU_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   for (auto &e : c->ev) CU_OK(cudaEventCreate(&e));
   CU_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  CU_OK(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+  {  // the cascade kernels must never take an SM away from the next chunk's scan blocks: lowest priority
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CU_OK(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, lo));
+  }
   for (auto &e : c->ev_k2) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : c->ev_aux) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : c->ev_copy) CU_OK(cudaEventCreate(&e));
@@ -694,6 +698,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
           CU_OK(cudaEventRecord(c->ev_k2[ch], s));
           CU_OK(cudaStreamWaitEvent(ks, c->ev_k2[ch], 0));
         }
+        if (timing && ch == nchunks - 1) CU_OK(cudaEventRecord(c->ev[3], s));  // end of the last scan
         // stage 0 of this chunk's survivors: leaves + regression gather, cohort-staged
         S.surv = c->d_surv.p + qoff; S.surv_count = c->d_counters + kCntSurv + ch; S.surv_cap = (unsigned)cap_chunk;
         S.out_shape = c->d_shape0.p + qoff * D;
@@ -713,7 +718,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         st.cascade_launches++;
       }
     }
-    if (timing) CU_OK(cudaEventRecord(c->ev[3], s));  // end of the last scan
+    if (timing && !use_scan) CU_OK(cudaEventRecord(c->ev[3], s));
     if (piped) {
       CU_OK(cudaEventRecord(c->ev_aux[1], ks));
       CU_OK(cudaStreamWaitEvent(s, c->ev_aux[1], 0));
