@@ -568,17 +568,16 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   c->surv_cap = std::max(c->surv_cap, (size_t)b.n_frames * 1024);
   c->hit_cap = std::max(c->hit_cap, (size_t)b.n_frames * 128);
 
-  // Chunks: a resident batch of >= 128 frames is also cut into kMaxChunks pieces so that the cascade
-  // kernels of chunk i (small, latency-bound, little shared memory: they fit on the SMs next to the
-  // persistent scan blocks) run on a second stream under the scan of chunk i+1.
-  if (nchunks == 1 && use_scan && !tracing && b.n_frames >= 128 && !m.any_scaled && !getenv("JDA_B200_NO_CHUNKS"))
-    nchunks = kMaxChunks;
+  // Host batches are scanned chunk by chunk behind their copies (nchunks == copy_chunks); all chunks feed one
+  // survivor queue and the cascade kernels run once at the end.  Running the cascade kernels of chunk i on a
+  // second stream under the scan of chunk i+1 was tried (they fit next to the scan blocks): the scan slowed
+  // down by more than the cascade time it hid (r1: 31.9 vs 30.2 ms per 512-frame step), so it is not done.
   const bool host_chunks = !(b.flags & JDA_B200_DEVICE_INPUT) && copy_chunks > 1;
 
   for (int attempt = 0; attempt < 4; attempt++) {
     if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * rec_words)) return false;
     if (use_scan && !c->d_shape0.ensure(c->surv_cap * D)) return false;
-    const size_t cap_chunk = c->surv_cap / nchunks;
+    const size_t cap_chunk = c->surv_cap;  // one queue shared by every chunk
     CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
     if (timing) CU_OK(cudaEventRecord(c->ev[2], s));
 
@@ -645,25 +644,17 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       Q.leaf_w0 = trace->w0; Q.leaf_w1 = trace->w1; Q.leaf_stride = leaf_stride;
     }
 
-    const bool piped = nchunks > 1;
-    cudaStream_t ks = piped ? c->aux_stream : s;  // where the cascade kernels go
-    if (piped && timing) {
-      CU_OK(cudaEventRecord(c->ev_aux[0], s));
-      CU_OK(cudaStreamWaitEvent(ks, c->ev_aux[0], 0));
-    } else if (piped) {
-      CU_OK(cudaEventRecord(c->ev_aux[0], s));
-      CU_OK(cudaStreamWaitEvent(ks, c->ev_aux[0], 0));  // counters are zeroed before any cascade kernel runs
-    }
+    cudaStream_t ks = s;
     for (int ch = 0; ch < nchunks; ch++) {
       const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
       if (f1 <= f0) continue;
-      const size_t qoff = (size_t)ch * cap_chunk;
+      const size_t qoff = 0;
       if (use_scan) {
         P.frames = d_frames + (size_t)f0 * fstride;
         P.n_frames = f1 - f0;
         P.frame_base = f0;
         P.tile_counters = c->d_counters + ch * kMaxLevels;
-        P.surv = c->d_surv.p + qoff; P.surv_count = c->d_counters + kCntSurv + ch; P.surv_cap = (unsigned)cap_chunk;
+        P.surv = c->d_surv.p + qoff; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)cap_chunk;
         for (int i = 0; i < g.n_levels && tma_ok; i++) {
           if (!g.lv[i].use_smem) continue;
           cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)(f1 - f0)};
@@ -694,21 +685,18 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         }
         CU_OK(cudaGetLastError());
         st.scan_launches++;
-        if (piped) {
-          CU_OK(cudaEventRecord(c->ev_k2[ch], s));
-          CU_OK(cudaStreamWaitEvent(ks, c->ev_k2[ch], 0));
-        }
         if (timing && ch == nchunks - 1) CU_OK(cudaEventRecord(c->ev[3], s));  // end of the last scan
-        // stage 0 of this chunk's survivors: leaves + regression gather, cohort-staged
-        S.surv = c->d_surv.p + qoff; S.surv_count = c->d_counters + kCntSurv + ch; S.surv_cap = (unsigned)cap_chunk;
-        S.out_shape = c->d_shape0.p + qoff * D;
+        if (ch < nchunks - 1) continue;  // the cascade kernels run once, behind the last chunk's scan
+        // stage 0 of the survivors: leaves + regression gather, cohort-staged
+        S.surv = c->d_surv.p; S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)cap_chunk;
+        S.out_shape = c->d_shape0.p;
         k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), ks>>>(S);
         CU_OK(cudaGetLastError());
         st.cascade_launches++;
       }
-      Q.surv = c->d_surv.p + qoff; Q.surv_count = c->d_counters + kCntSurv + ch; Q.surv_cap = (unsigned)cap_chunk;
-      Q.init_shape = use_scan ? c->d_shape0.p + qoff * D : nullptr;
-      Q.work_counter = c->d_counters + kCntWork + ch;
+      Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)cap_chunk;
+      Q.init_shape = use_scan ? c->d_shape0.p : nullptr;
+      Q.work_counter = c->d_counters + kCntWork;
       {
         const int grid = c->sm_count * 8;
         const size_t smem = k3_smem_bytes(m.K);
@@ -719,24 +707,15 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       }
     }
     if (timing && !use_scan) CU_OK(cudaEventRecord(c->ev[3], s));
-    if (piped) {
-      CU_OK(cudaEventRecord(c->ev_aux[1], ks));
-      CU_OK(cudaStreamWaitEvent(s, c->ev_aux[1], 0));
-    }
     if (timing) CU_OK(cudaEventRecord(c->ev[4], s));
     CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     // the first records ride along with the counters: a call with few hits needs a single round trip
     const size_t eager = std::min<size_t>(kEagerHits, c->hit_cap);
     CU_OK(cudaMemcpyAsync(c->h_eager, c->d_hits.p, eager * rec_words * 4, cudaMemcpyDeviceToHost, s));
     CU_OK(cudaStreamSynchronize(s));
-    size_t ns = 0, ns_max = 0;
-    for (int ch = 0; ch < nchunks; ch++) {
-      ns += c->h_counters[kCntSurv + ch];
-      ns_max = std::max(ns_max, (size_t)c->h_counters[kCntSurv + ch]);
-    }
-    const size_t nh = c->h_counters[kCntHit];
-    if (ns_max > cap_chunk || nh > c->hit_cap) {  // queues overflowed: grow and run again
-      if (ns_max > cap_chunk) c->surv_cap = (ns_max + ns_max / 4) * nchunks;
+    const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
+    if (ns > cap_chunk || nh > c->hit_cap) {  // queues overflowed: grow and run again
+      if (ns > cap_chunk) c->surv_cap = ns + ns / 4;
       if (nh > c->hit_cap) c->hit_cap = nh + nh / 4;
       continue;
     }

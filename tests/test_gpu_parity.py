@@ -257,15 +257,7 @@ def test_chunked_host_batch_equals_resident(casc, oracle, oracle_shipped):
     d = torch.from_numpy(frames).cuda()
     torch.cuda.synchronize()
     dev = casc.detect_batch(None, device_ptr=d.data_ptr(), shape=tuple(d.shape), th=-0.5)
-    assert casc.last_stats["scan_launches"] == 4          # resident batches are pipelined in chunks too
-    os.environ["JDA_B200_NO_CHUNKS"] = "1"
-    try:
-        one = casc.detect_batch(None, device_ptr=d.data_ptr(), shape=tuple(d.shape), th=-0.5)
-        assert casc.last_stats["scan_launches"] == 1
-    finally:
-        del os.environ["JDA_B200_NO_CHUNKS"]
-    for a, b in zip(dev, one):
-        _same(a, b)
+    assert casc.last_stats["scan_launches"] == 1
     assert sum(len(r[1]) for r in host) >= 1
     for a, b in zip(host, dev):
         _same(a, b)
