@@ -101,9 +101,7 @@ struct Context {
   std::mutex mu;
   int device = -1;
   bool inited = false;
-  cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
-  cudaEvent_t ev_k2[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_aux[2] = {nullptr, nullptr};
+  cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy[kMaxChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int sm_count = 148;
   EncodeTiledFn encode = nullptr;
@@ -177,13 +175,6 @@ bool ctx_init(Context *c) {
   CU_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   for (auto &e : c->ev) CU_OK(cudaEventCreate(&e));
   CU_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  {  // the cascade kernels must never take an SM away from the next chunk's scan blocks: lowest priority
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    CU_OK(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, lo));
-  }
-  for (auto &e : c->ev_k2) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto &e : c->ev_aux) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &e : c->ev_copy) CU_OK(cudaEventCreate(&e));
   const HostModel &m = c->m;
   CU_OK(cudaMalloc(&c->d_nodes, m.nodes.size() * sizeof(NodeRec)));
@@ -259,9 +250,6 @@ void ctx_free(Context *c) {
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    for (auto &e : c->ev_k2) if (e) cudaEventDestroy(e);
-    for (auto &e : c->ev_aux) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
   }
   delete c;
@@ -644,7 +632,6 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       Q.leaf_w0 = trace->w0; Q.leaf_w1 = trace->w1; Q.leaf_stride = leaf_stride;
     }
 
-    cudaStream_t ks = s;
     for (int ch = 0; ch < nchunks; ch++) {
       const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
       if (f1 <= f0) continue;
@@ -690,7 +677,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         // stage 0 of the survivors: leaves + regression gather, cohort-staged
         S.surv = c->d_surv.p; S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)cap_chunk;
         S.out_shape = c->d_shape0.p;
-        k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), ks>>>(S);
+        k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), s>>>(S);
         CU_OK(cudaGetLastError());
         st.cascade_launches++;
       }
@@ -700,8 +687,8 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       {
         const int grid = c->sm_count * 8;
         const size_t smem = k3_smem_bytes(m.K);
-        if (tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, ks>>>(Q);
-        else k3_cascade<false><<<grid, K3_WARPS * 32, smem, ks>>>(Q);
+        if (tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, s>>>(Q);
+        else k3_cascade<false><<<grid, K3_WARPS * 32, smem, s>>>(Q);
         CU_OK(cudaGetLastError());
         st.cascade_launches++;
       }

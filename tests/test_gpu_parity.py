@@ -276,6 +276,46 @@ def test_mining_mode_truncated_cascade(casc, oracle, oracle_shipped, t_limit):
     _same(got, (ob, osc, osh))
 
 
+def test_concurrent_callers_and_changing_arguments(casc, oracle, oracle_shipped):
+    """jdaDetect is re-entrant in the reference: threads share one handle; calls with different
+    sizes / pyramids interleave (the per-handle geometry cache is rebuilt as needed)."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = [(synth.face_canvas(), dict(th=0.0)), (synth.facemix_frame(5), dict(scale=1.2, min_size=30, max_size=300, th=-1.0)),
+            (synth.facemix_frame(7, *synth.fddb_shape(7)), dict(th=0.0)), (synth.blur_frame(2, 30, 27), dict(th=-5.0)),
+            (synth.facemix_frame(3), dict(max_size=192, th=0.0))] * 3
+    want = [oracle.detect(oracle_shipped, img, **kw) for img, kw in jobs[:5]] * 3
+    with ThreadPoolExecutor(6) as ex:
+        got = list(ex.map(lambda j: casc.detect(j[0], **j[1]), jobs))
+    for g, w in zip(got, want):
+        _same(g, w)
+    c2 = api.Cascador(SHIPPED_F32, double=False)       # a second handle on the same device
+    with ThreadPoolExecutor(4) as ex:
+        got = list(ex.map(lambda a: (casc if a[0] % 2 else c2).detect(a[1][0], **a[1][1]), enumerate(jobs)))
+    for g, w in zip(got, want):
+        _same(g, w)
+    c2.close()
+
+
+def test_concurrent_callers_and_changing_arguments(casc, oracle, oracle_shipped):
+    """jdaDetect is re-entrant in the reference: threads share one handle; calls with different
+    sizes / pyramids interleave (the per-handle geometry cache is rebuilt as needed)."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = [(synth.face_canvas(), dict(th=0.0)), (synth.facemix_frame(5), dict(scale=1.2, min_size=30, max_size=300, th=-1.0)),
+            (synth.facemix_frame(7, *synth.fddb_shape(7)), dict(th=0.0)), (synth.blur_frame(2, 30, 27), dict(th=-5.0)),
+            (synth.facemix_frame(3), dict(max_size=192, th=0.0))] * 3
+    want = [oracle.detect(oracle_shipped, img, **kw) for img, kw in jobs[:5]] * 3
+    with ThreadPoolExecutor(6) as ex:
+        got = list(ex.map(lambda j: casc.detect(j[0], **j[1]), jobs))
+    for g, w in zip(got, want):
+        _same(g, w)
+    c2 = api.Cascador(SHIPPED_F32, double=False)       # a second handle on the same device
+    with ThreadPoolExecutor(4) as ex:
+        got = list(ex.map(lambda a: (casc if a[0] % 2 else c2).detect(a[1][0], **a[1][1]), enumerate(jobs)))
+    for g, w in zip(got, want):
+        _same(g, w)
+    c2.close()
+
+
 # ---- edges ------------------------------------------------------------------------------------
 
 def test_edge_cases(casc, oracle, oracle_shipped):
