@@ -119,7 +119,7 @@ struct Context {
   DevBuf<uint8_t> d_frames, d_hq, d_trace_leaf;
   DevBuf<uint4> d_surv;
   DevBuf<float> d_shape0;
-  DevBuf<uint8_t> d_tables_packed;
+  DevBuf<uint8_t> d_surv_leaves;
   DevBuf<float> d_hits;
   DevBuf<int> d_trace_n;
   DevBuf<float> d_trace_s;
@@ -246,7 +246,7 @@ void ctx_free(Context *c) {
     cudaFreeHost(c->h_eager);
     cudaFreeHost(c->h_stage);
     c->d_tables.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
-    c->d_surv.release(); c->d_shape0.release(); c->d_tables_packed.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
+    c->d_surv.release(); c->d_shape0.release(); c->d_surv_leaves.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -421,12 +421,6 @@ bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int ma
                          tab.data() + (size_t)i * g.table_bytes, norms);
     if (!c->d_tables.ensure(tab.size())) return false;
     CU_OK(cudaMemcpyAsync(c->d_tables.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, c->stream()));
-    // the same tables in packed-coordinate form for every level: k3_stage0 reads pixels from global memory
-    std::vector<uint8_t> tabp((size_t)n * g.table_bytes, 0);
-    Stage0Norm norms2[kMaxNorm];
-    for (int i = 0; i < n; i++) build_stage0_table(c->m, g.lv[i].win, 0, tabp.data() + (size_t)i * g.table_bytes, norms2);
-    if (!c->d_tables_packed.ensure(tabp.size())) return false;
-    CU_OK(cudaMemcpyAsync(c->d_tables_packed.p, tabp.data(), tabp.size(), cudaMemcpyHostToDevice, c->stream()));
     CU_OK(cudaMemcpyAsync(c->d_norms, norms, sizeof norms, cudaMemcpyHostToDevice, c->stream()));
     CU_OK(cudaStreamSynchronize(c->stream()));
   }
@@ -564,7 +558,8 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
 
   for (int attempt = 0; attempt < 4; attempt++) {
     if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * rec_words)) return false;
-    if (use_scan && !c->d_shape0.ensure(c->surv_cap * D)) return false;
+    const int leaf_pad = (m.K + 15) & ~15;
+    if (use_scan && (!c->d_shape0.ensure(c->surv_cap * D) || !c->d_surv_leaves.ensure(c->surv_cap * leaf_pad))) return false;
     const size_t cap_chunk = c->surv_cap;  // one queue shared by every chunk
     CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
     if (timing) CU_OK(cudaEventRecord(c->ev[2], s));
@@ -607,7 +602,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     Stage0Params S;
     memset(&S, 0, sizeof S);
     S.frames = d_frames; S.frame_stride = fstride; S.pitch = pitch;
-    S.tables_packed = c->d_tables_packed.p; S.table_bytes = g.table_bytes;
+    S.surv_leaves = c->d_surv_leaves.p;
     S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
     for (int i = 0; i < g.n_levels; i++) S.lv_step[i] = g.lv[i].step;
     CascadeParams Q;
@@ -642,6 +637,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         P.frame_base = f0;
         P.tile_counters = c->d_counters + ch * kMaxLevels;
         P.surv = c->d_surv.p + qoff; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)cap_chunk;
+        P.surv_leaves = c->d_surv_leaves.p; P.leaf_pad = leaf_pad;
         for (int i = 0; i < g.n_levels && tma_ok; i++) {
           if (!g.lv[i].use_smem) continue;
           cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)(f1 - f0)};

@@ -74,6 +74,8 @@ struct ScanParams {
   uint4 *surv;                   // stage-0 survivors: {frame, level<<26 | yi<<13 | xi, score bits, 0}
   unsigned *surv_count;
   unsigned surv_cap;
+  uint8_t *surv_leaves;          // [surv_cap][leaf_pad]: the K stage-0 leaf indices of every survivor
+  int leaf_pad;
   long long windows_per_frame;
   int n_sched;
   short sched[K2_MAX_SCHED];     // cart index at which each phase ends; last == K
@@ -498,7 +500,10 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
       break;
     }
   }
-  // windows that passed every cart of stage 0
+  // windows that passed every cart of stage 0: queue them for the cascade kernels together with their K leaf
+  // indices.  The phases did not keep the leaves, so each survivor (a handful per tile) is re-walked here, one
+  // cart per lane, while its pixels and the table are still in shared memory -- ~17 dense steps per survivor,
+  // instead of 9 x K scattered global loads later in k3_stage0.
   for (int base = 0; base < n; base += 32) {
     const int e = base + lane;
     const bool v = e < n;
@@ -506,12 +511,25 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
     unsigned slot0 = 0;
     if (lane == 0) slot0 = atomicAdd(P.surv_count, (unsigned)__popc(m));
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-    if (v) {
-      const unsigned slot = slot0 + __popc(m & ((1u << lane) - 1u));
-      const int w = lwid[e];
-      if (slot < P.surv_cap)
-        P.surv[slot] = make_uint4((unsigned)(frame + P.frame_base), pack_key(li, y0w + (w >> c.tw_log2), x0w + (w & c.tw_mask)),
-                                  __float_as_uint(lscore[e]), 0u);
+    const unsigned slot = slot0 + __popc(m & ((1u << lane) - 1u));
+    const int w = v ? (int)lwid[e] : 0;
+    if (v && slot < P.surv_cap)
+      P.surv[slot] = make_uint4((unsigned)(frame + P.frame_base), pack_key(li, y0w + (w >> c.tw_log2), x0w + (w & c.tw_mask)),
+                                __float_as_uint(lscore[e]), 0u);
+    for (unsigned rest = m; rest; rest &= rest - 1) {
+      const int src = __ffs(rest) - 1;
+      const unsigned sl = __shfl_sync(0xffffffffu, slot, src);
+      const PixBase<SMEM> pb = window_base<SMEM>(c, __shfl_sync(0xffffffffu, w, src), true);
+      if (sl >= P.surv_cap) continue;
+      uint8_t *out = P.surv_leaves + (size_t)sl * P.leaf_pad;
+      for (int k0 = 0; k0 < P.K; k0 += 32) {
+        const int k = min(k0 + lane, P.K - 1);
+        const uint32_t co = (uint32_t)k * kCartBytes;
+        int idx = node_test<SMEM>(smem, *reinterpret_cast<const uint2 *>(smem + co), pb, c.pitch);
+        idx = 2 * idx + node_test<SMEM>(smem, *reinterpret_cast<const uint2 *>(smem + co + idx * 8), pb, c.pitch);
+        idx = 2 * idx + node_test<SMEM>(smem, *reinterpret_cast<const uint2 *>(smem + co + idx * 8), pb, c.pitch);
+        if (k0 + lane < P.K) out[k0 + lane] = (uint8_t)(idx - kNodes);
+      }
     }
   }
   __syncwarp();
@@ -880,7 +898,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
 // Stage 0 for the survivors of k2_scan: they are known to pass every cart of the stage and k2 has
 // their exit score, so only two things are left -- the K leaf indices and the regression gather
 //   shape = mean_shape + sum_k w[0][8k + leaf_k]        (k ascending, c/jda.c:403-411).
-// Leaves come from the packed stage-0 LUT of the window's level (integer offsets, L1-resident).
+// The leaves were recorded by k2_scan (a re-walk of each survivor while its tile was in shared memory).
 // The gather is the expensive part: 8K rows x 2L floats stream from L2 per survivor if done naively
 // (that made k3_cascade L2-bound in profiles/r1_v1).  Here a block takes a cohort of 32 survivors and
 // stages w[0] through shared memory 8 carts (64 rows) at a time with cp.async double buffering, so
@@ -895,8 +913,7 @@ struct Stage0Params {
   const uint8_t *frames;
   size_t frame_stride;
   int pitch;
-  const uint8_t *tables_packed;  // [n_levels][table_bytes], packed-coordinate format
-  int table_bytes;
+  const uint8_t *surv_leaves;    // [surv_cap][(K + 15) & ~15] leaf indices written by k2_scan
   const float *w0;               // w[0]: [8K][2L]
   const float *mean_shape;
   int K, L;
@@ -923,37 +940,14 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
   const int n_chunks = (K + K3S_CHUNK - 1) / K3S_CHUNK;
 
   for (int c0 = blockIdx.x * K3S_COHORT; c0 < total; c0 += gridDim.x * K3S_COHORT) {
-    // ---- leaves of my K3S_PER_WARP survivors: the walks are interleaved (independent load chains)
-    {
-      PixBase<false> pb[K3S_PER_WARP];
-      const uint8_t *tab[K3S_PER_WARP];
-      bool ok[K3S_PER_WARP];
+    // ---- leaves of my K3S_PER_WARP survivors: computed by k2_scan while the window was in shared memory
 #pragma unroll
-      for (int s = 0; s < K3S_PER_WARP; s++) {
-        const int e = c0 + warp * K3S_PER_WARP + s;
-        ok[s] = e < total;
-        const uint4 q = P.surv[ok[s] ? e : c0];
-        const int level = (int)(q.y >> 26), yi = (int)((q.y >> 13) & 0x1fff), xi = (int)(q.y & 0x1fff);
-        const int step = P.lv_step[level];
-        pb[s].ptr = P.frames + (size_t)q.x * P.frame_stride + (size_t)(yi * step) * P.pitch + (size_t)xi * step;
-        tab[s] = P.tables_packed + (size_t)level * P.table_bytes;
-      }
-      for (int k = lane; k < K; k += 32) {
-        int idx[K3S_PER_WARP];
-        const uint2 *nd[K3S_PER_WARP];
-#pragma unroll
-        for (int s = 0; s < K3S_PER_WARP; s++) {
-          nd[s] = reinterpret_cast<const uint2 *>(tab[s] + (size_t)k * kCartBytes);
-          idx[s] = node_test<false>(nullptr, __ldg(nd[s]), pb[s], P.pitch);
-        }
-#pragma unroll
-        for (int s = 0; s < K3S_PER_WARP; s++) idx[s] = 2 * idx[s] + node_test<false>(nullptr, __ldg(nd[s] + idx[s]), pb[s], P.pitch);
-#pragma unroll
-        for (int s = 0; s < K3S_PER_WARP; s++) idx[s] = 2 * idx[s] + node_test<false>(nullptr, __ldg(nd[s] + idx[s]), pb[s], P.pitch);
-#pragma unroll
-        for (int s = 0; s < K3S_PER_WARP; s++)
-          if (ok[s]) leaves[(size_t)(warp * K3S_PER_WARP + s) * kpad + k] = (uint8_t)(idx[s] - kNodes);
-      }
+    for (int s = 0; s < K3S_PER_WARP; s++) {
+      const int e = c0 + warp * K3S_PER_WARP + s;
+      if (e >= total) continue;
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(P.surv_leaves + (size_t)e * kpad);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(leaves + (size_t)(warp * K3S_PER_WARP + s) * kpad);
+      for (int i = lane; i < kpad / 4; i += 32) dst[i] = __ldg(src + i);
     }
     // ---- regression gather over staged chunks of w[0]
     float2 acc[K3S_PER_WARP][2];
