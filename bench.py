@@ -300,7 +300,7 @@ def main():
                                    "~1.8 B/window (see DESIGN.md)",
                            "carts_per_window": carts_pw, "algorithmic_bytes_per_window": bytes_pw,
                            "k2_windows_per_s": B * WINDOWS_PER_FRAME / k2_s}
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:  # the reported CPU baseline is an N=1 item
             cores = os.cpu_count() or 1
             n = max(8, min(cores, 48))
             dt, kind = cpu_reference_run(pool[:n], cores)

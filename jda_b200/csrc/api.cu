@@ -601,10 +601,8 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     }
     Stage0Params S;
     memset(&S, 0, sizeof S);
-    S.frames = d_frames; S.frame_stride = fstride; S.pitch = pitch;
     S.surv_leaves = c->d_surv_leaves.p;
     S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
-    for (int i = 0; i < g.n_levels; i++) S.lv_step[i] = g.lv[i].step;
     CascadeParams Q;
     memset(&Q, 0, sizeof Q);
     Q.frames = d_frames; Q.frame_stride = fstride; Q.pitch = pitch; Q.W = b.width; Q.H = b.height;
@@ -671,7 +669,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         if (timing && ch == nchunks - 1) CU_OK(cudaEventRecord(c->ev[3], s));  // end of the last scan
         if (ch < nchunks - 1) continue;  // the cascade kernels run once, behind the last chunk's scan
         // stage 0 of the survivors: leaves + regression gather, cohort-staged
-        S.surv = c->d_surv.p; S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)cap_chunk;
+        S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)cap_chunk;
         S.out_shape = c->d_shape0.p;
         k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), s>>>(S);
         CU_OK(cudaGetLastError());

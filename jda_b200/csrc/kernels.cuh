@@ -910,15 +910,10 @@ constexpr int K3S_CHUNK = 4;  // carts staged per step (6.9 KB x 2 buffers: the 
 static_assert(K3S_CHUNK % 4 == 0, "leaf indices are fetched four at a time");
 
 struct Stage0Params {
-  const uint8_t *frames;
-  size_t frame_stride;
-  int pitch;
   const uint8_t *surv_leaves;    // [surv_cap][(K + 15) & ~15] leaf indices written by k2_scan
   const float *w0;               // w[0]: [8K][2L]
   const float *mean_shape;
   int K, L;
-  int lv_step[kMaxLevels];
-  const uint4 *surv;
   const unsigned *surv_count;
   unsigned surv_cap;
   float *out_shape;              // [surv_cap][2L]
