@@ -1,0 +1,90 @@
+"""Command-line glue around libjda_b200.so (the reference's src/test.cpp / c/main.cpp
+are GUI/OpenCV demos and are not rebuilt).
+
+  python -m jda_b200 info    MODEL [--float] [--size WxH] [--max-size N]
+  python -m jda_b200 convert MODEL_DOUBLE OUT_FLOAT32          (jdaCascadorSerializeTo, c/jda.c:644-716)
+  python -m jda_b200 detect  MODEL IMAGE... [--float] [--fddb-out FILE] [--scale S --min-size N --max-size N --th T]
+
+`detect` reads gray images (.npy u8 arrays, binary .pgm, or anything cv2 can open when cv2 is present) and, with
+--fddb-out, writes the result-file format of the reference's FDDB runner (src/test.cpp:153,163):
+    <path>\\n<n>\\n<x> <y> <w> <h> <score>\\n ...
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from . import api
+
+
+def read_gray(path):
+    if path.endswith(".npy"):
+        a = np.load(path)
+    elif path.endswith(".pgm"):
+        with open(path, "rb") as f:
+            tok = []
+            while len(tok) < 4:
+                line = f.readline()
+                if not line.startswith(b"#"):
+                    tok += line.split()
+            assert tok[0] == b"P5" and int(tok[3]) == 255, "only 8-bit binary PGM"
+            w, h = int(tok[1]), int(tok[2])
+            a = np.frombuffer(f.read(w * h), np.uint8).reshape(h, w)
+    else:
+        import cv2
+        a = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+        if a is None:
+            raise SystemExit("cannot read " + path)
+    if a.ndim == 3:
+        a = a.mean(axis=2)
+    return np.ascontiguousarray(a, np.uint8)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="python -m jda_b200")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    p = sub.add_parser("info")
+    p.add_argument("model"); p.add_argument("--float", action="store_true")
+    p.add_argument("--size", default="640x480"); p.add_argument("--max-size", type=int, default=-1)
+    p = sub.add_parser("convert")
+    p.add_argument("model"); p.add_argument("out")
+    p = sub.add_parser("detect")
+    p.add_argument("model"); p.add_argument("images", nargs="+"); p.add_argument("--float", action="store_true")
+    p.add_argument("--fddb-out"); p.add_argument("--scale", type=float, default=1.25)
+    p.add_argument("--min-size", type=int, default=24); p.add_argument("--max-size", type=int, default=-1)
+    p.add_argument("--th", type=float, default=0.0)
+    a = ap.parse_args(argv)
+
+    if a.cmd == "convert":
+        c = api.Cascador(a.model, double=True)
+        c.save_f32(a.out)
+        print("wrote %s (%d bytes, float32 flavour, T=%d K=%d L=%d)" % (a.out, os.path.getsize(a.out), c.T, c.K, c.L))
+        return 0
+    c = api.Cascador(a.model, double=not a.float)
+    if a.cmd == "info":
+        w, h = map(int, a.size.split("x"))
+        print("T=%d K=%d landmarks=%d depth=%d" % (c.T, c.K, c.L, c.depth))
+        print("%dx%d, max_size %d: %d candidate windows" % (w, h, a.max_size, api.count_windows(w, h, 1.25, 24, a.max_size)))
+        for lat in (False, True):
+            print("scan plan (%s):" % ("<= 4 frames per call" if lat else "batches"))
+            for q in api.describe_plan(w, h, 1.25, 24, a.max_size, latency=lat):
+                print("   win %3d step %2d  %4d x %-4d windows  tile %2d x %-2d  box %3d x %-3d  %s" %
+                      (q["win"], q["step"], q["nx"], q["ny"], q["tw"], q["th"], q["box_w"], q["box_h"],
+                       ("shared memory, %d warp(s) per tile" % q["span"]) if q["smem"] else "global memory"))
+        return 0
+    frames = [read_gray(p) for p in a.images]
+    res = c.detect_many(frames, scale=a.scale, min_size=a.min_size, max_size=a.max_size, th=a.th)
+    out = open(a.fddb_out, "w") if a.fddb_out else sys.stdout
+    for path, (boxes, scores, shapes) in zip(a.images, res):
+        name = os.path.splitext(path)[0]
+        out.write("%s\n%d\n" % (name, len(scores)))
+        for b, s in zip(boxes, scores):
+            out.write("%d %d %d %d %f\n" % (b[0], b[1], b[2], b[2], s))
+    if a.fddb_out:
+        out.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -356,3 +356,18 @@ def test_full_size_batch_properties(casc, oracle, oracle_shipped):
         _same(raw[f], (ob, osc, osh))
         s0 += ost["stage_survivors"][0]
     assert casc.last_stats["stage0_survivors"] == s0
+
+
+def test_cli_detect_fddb_format(tmp_path, oracle, oracle_shipped):
+    from jda_b200.__main__ import main
+    img = synth.face_canvas()
+    np.save(tmp_path / "a.npy", img)
+    with open(tmp_path / "b.pgm", "wb") as f:
+        f.write(b"P5\n640 480\n255\n" + img.tobytes())
+    out = tmp_path / "fold-01-out.txt"
+    assert main(["detect", SHIPPED_F32, str(tmp_path / "a.npy"), str(tmp_path / "b.pgm"), "--float", "--fddb-out", str(out)]) == 0
+    lines = out.read_text().split("\n")
+    b, s, _ = oracle.detect(oracle_shipped, img)
+    assert lines[0] == str(tmp_path / "a") and lines[1] == "2"
+    assert lines[2] == "%d %d %d %d %f" % (b[0][0], b[0][1], b[0][2], b[0][2], s[0])
+    assert lines[4] == str(tmp_path / "b") and lines[5] == "2"

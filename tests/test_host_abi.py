@@ -116,3 +116,14 @@ def test_tile_plan_invariants(w, h, mx, latency):
             assert p["box_h"] == (p["th"] - 1) * p["step"] + p["win"]
             assert (p["win"] - 1) * p["box_w"] + p["win"] - 1 < 65536
     assert any(p["smem"] for p in plan)
+
+
+def test_cli_convert_and_info(tmp_path, capsys):
+    from jda_b200.__main__ import main
+    wide = synth.widen_f32_model(SHIPPED_F32, str(tmp_path / "wide.model"))
+    out = tmp_path / "f32.model"
+    assert main(["convert", wide, str(out)]) == 0
+    assert out.read_bytes() == open(SHIPPED_F32, "rb").read()
+    assert main(["info", str(out), "--float", "--size", "640x480", "--max-size", "192"]) == 0
+    txt = capsys.readouterr().out
+    assert "169236 candidate windows" in txt and "T=5 K=540 landmarks=27" in txt
