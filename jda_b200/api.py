@@ -45,6 +45,9 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+_RESULT_DTYPE = np.dtype([("n", np.int32), ("landmark_n", np.int32), ("bboxes", np.uint64), ("shapes", np.uint64),
+                          ("scores", np.uint64)])
+
 _lib = None
 
 
@@ -229,20 +232,20 @@ class Cascador:
         if rc != 0:
             raise RuntimeError("jdaB200DetectBatch failed: " + last_error())
         lm = self.L
+        # vectorised view of the jdaResult array (c/jda.h:18-24: two ints + three pointers)
+        view = np.frombuffer(res, dtype=_RESULT_DTYPE, count=n)
+        counts = view["n"]
         if not unpack:
-            tot = sum(res[i].n for i in range(n))
+            tot = int(counts.sum())
             L.jdaB200ResultsRelease(res, n)
             return tot
         empty = (np.zeros((0, 3), np.int32), np.zeros((0,), np.float32), np.zeros((0, 2 * lm), np.float32))
-        out = []
-        for i in range(n):
-            k = res[i].n
-            if k > 0:
-                out.append((np.ctypeslib.as_array(res[i].bboxes, shape=(k, 3)).copy(),
-                            np.ctypeslib.as_array(res[i].scores, shape=(k,)).copy(),
-                            np.ctypeslib.as_array(res[i].shapes, shape=(k, 2 * lm)).copy()))
-            else:
-                out.append(empty)
+        out = [empty] * n
+        for i in np.nonzero(counts > 0)[0]:
+            k = int(counts[i])
+            out[i] = (np.ctypeslib.as_array(res[i].bboxes, shape=(k, 3)).copy(),
+                      np.ctypeslib.as_array(res[i].scores, shape=(k,)).copy(),
+                      np.ctypeslib.as_array(res[i].shapes, shape=(k, 2 * lm)).copy())
         L.jdaB200ResultsRelease(res, n)
         return out
 
