@@ -136,8 +136,9 @@ def run_reference_arm(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = max(8, min(cores, 64))
-    pool = frame_pool(n, a.dist, 0)
+    n = max(8, min(2 * cores, 256))  # two frames per host thread so every core stays busy for the whole step
+    pool = frame_pool(min(n, 96), a.dist, 0)
+    pool = pool[np.arange(n) % len(pool)]
     for _ in range(a.warmup):
         cpu_reference_run(pool[:max(2, n // 4)], cores)
     tot = 0.0
@@ -292,8 +293,9 @@ def main():
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak,
                            # dram__bytes_read+write of k2_scan from the committed ncu capture
-                           # (profiles/r1_final_metrics_k2_k3.txt: 87.8 MB for a 256-frame launch), scaled to B frames
-                           "traffic": 87.8e6 / 256 * B, "kernel": "k2_scan",
+                           # (profiles/r1_final_metrics_k2_k3.txt: 106.0 MB read + 26.1 MB written for a 256-frame
+                           # launch: the frames, the tables, the survivors' leaf records), scaled to B frames
+                           "traffic": (106.0e6 + 26.1e6) / 256 * B, "kernel": "k2_scan",
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                            "note": "logical (algorithmic touched) bytes: 118 B x carts/window + 216 B; data is "
                                    "served from shared memory/L2 so frac may exceed 1; compulsory DRAM is "
@@ -302,8 +304,8 @@ def main():
                            "k2_windows_per_s": B * WINDOWS_PER_FRAME / k2_s}
         if not a.no_cpu_baseline and world == 1:  # the reported CPU baseline is an N=1 item
             cores = os.cpu_count() or 1
-            n = max(8, min(cores, 48))
-            dt, kind = cpu_reference_run(pool[:n], cores)
+            n = max(8, min(2 * cores, 256))
+            dt, kind = cpu_reference_run(pool[np.arange(n) % len(pool)], cores)
             out["cpu_baseline"] = {"value": n * WINDOWS_PER_FRAME / dt, "unit": "windows/s", "cores": cores,
                                    "kind": kind, "sample": "%d %s VGA frames, %d threads over jdaDetect (%.1f s)"
                                    % (n, a.dist, cores, dt)}
