@@ -545,10 +545,14 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   }
 
   const bool use_scan = m.stage0_lut_ok && !(b.flags & JDA_B200_NO_STAGE0_SCAN);
-  if (c->surv_cap == 0) c->surv_cap = 1 << 16;
-  if (c->hit_cap == 0) c->hit_cap = 1 << 14;
-  c->surv_cap = std::max(c->surv_cap, (size_t)b.n_frames * 1024);
-  c->hit_cap = std::max(c->hit_cap, (size_t)b.n_frames * 128);
+  if (const char *e = getenv("JDA_B200_TINY_QUEUES")) {  // test hook: start with queues that overflow, exercise grow-and-retry
+    if (atoi(e) && c->surv_cap == 0) { c->surv_cap = 8; c->hit_cap = 2; }
+  } else {
+    if (c->surv_cap == 0) c->surv_cap = 1 << 16;
+    if (c->hit_cap == 0) c->hit_cap = 1 << 14;
+    c->surv_cap = std::max(c->surv_cap, (size_t)b.n_frames * 1024);
+    c->hit_cap = std::max(c->hit_cap, (size_t)b.n_frames * 128);
+  }
 
   // Host batches are scanned chunk by chunk behind their copies (nchunks == copy_chunks); all chunks feed one
   // survivor queue and the cascade kernels run once at the end.  Running the cascade kernels of chunk i on a

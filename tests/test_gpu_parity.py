@@ -371,3 +371,21 @@ def test_cli_detect_fddb_format(tmp_path, oracle, oracle_shipped):
     assert lines[0] == str(tmp_path / "a") and lines[1] == "2"
     assert lines[2] == "%d %d %d %d %f" % (b[0][0], b[0][1], b[0][2], b[0][2], s[0])
     assert lines[4] == str(tmp_path / "b") and lines[5] == "2"
+
+
+def test_queue_overflow_grows_and_retries(oracle, oracle_shipped):
+    """survivor / hit queues that are too small are detected from the device counters, grown and the batch re-run"""
+    os.environ["JDA_B200_TINY_QUEUES"] = "1"
+    try:
+        c = api.Cascador(SHIPPED_F32, double=False)
+        frames = np.stack([synth.face_canvas(), synth.facemix_frame(5), synth.noise_frame(2)])
+        got = c.detect_batch(frames, th=-1.0)
+        assert c.last_stats["scan_launches"] >= 2 and c.last_stats["stage0_survivors"] > 8
+        for f in range(3):
+            _same(got[f], oracle.detect(oracle_shipped, frames[f], th=-1.0))
+        raw = c.detect_batch(frames[:1], flags=api.RAW_HITS | api.NO_FINAL_TH)[0]
+        ob, osc, osh, _ = oracle.detect_raw(oracle_shipped, frames[0], use_th=False)
+        _same(raw, (ob, osc, osh))
+        c.close()
+    finally:
+        del os.environ["JDA_B200_TINY_QUEUES"]
