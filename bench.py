@@ -73,13 +73,18 @@ class ClockSampler:
         self.p.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
+        in_region = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+        if not in_region:  # a very short timed region: take the samples of the warm-up just before it (same load)
+            in_region = [r for r in self.rows if t0 - 1.5 <= r[0] <= t1 + 0.05]
+        keep = set(id(r) for r in in_region)
+        for row in self.rows:
+            ts, line = row
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
                 mx = float(f[1])
-                if t0 - 0.05 <= ts <= t1 + 0.05:
+                if id(row) in keep:
                     sm.append(float(f[0]))
                     for nm, v in zip(names, f[3:7]):
                         if v.lower().startswith("active"):
@@ -220,13 +225,14 @@ def main():
         return c.last_stats
 
     def timed(step_fn, steps, warmup, sample_clocks=False):
+        # the sampler starts before the warm-up: nvidia-smi needs ~0.5 s before its first line
+        sampler = ClockSampler(local) if sample_clocks else None
         for i in range(warmup):
             step_fn(i)
         torch.cuda.synchronize()
         if dist_on:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if sample_clocks else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record(stream)
