@@ -134,7 +134,6 @@ struct Context {
   jdaB200Stats last;
   int nw = 4;
   int stragglers = 1;
-  int dense_keep = 0, dense_max = 160;  // adaptive uncompacted first phase of k2_scan (see scan_tile)
   std::vector<short> sched;
   cudaStream_t stream() const { return user_stream ? user_stream : own_stream; }
 };
@@ -219,8 +218,6 @@ bool ctx_init(Context *c) {
     if (v == 1 || v == 2 || v == 4) c->nw = v;
   }
   if (const char *e = getenv("JDA_B200_STRAGGLERS")) c->stragglers = atoi(e) ? 1 : 0;
-  if (const char *e = getenv("JDA_B200_DENSE_KEEP")) c->dense_keep = std::max(0, std::min(256, atoi(e)));
-  if (const char *e = getenv("JDA_B200_DENSE_MAX")) c->dense_max = std::max(4, atoi(e));
   c->sched.clear();
   if (const char *e = getenv("JDA_B200_SCHED")) {
     const char *p = e;
@@ -300,7 +297,6 @@ double estimate_wavefronts(int win, int step, int tw, int th, int pitch) {
 }
 
 int g_min_tile_windows = 64;
-int g_prefer_w32 = 0;   // 1: take a 32-wide tile if it holds >= 3/4 of the best tile's windows (dense packets = one row)
 int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflict model (measured: no gain, r1)
 
 // Per-level tile shapes.  A level runs from private shared-memory tiles when a tile of at least
@@ -313,7 +309,7 @@ int g_max_span = -1;  // -1: by mode (throughput plan: up to 4 warps' buffers; l
 // best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
 int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3) {
   double best_cost = 1e30;
-  int best_windows = 0, w32 = 0, w32_th = 0, w32_bw = 0, w32_bh = 0;
+  int best_windows = 0;
   tile_bytes = std::min(tile_bytes, 65536);  // one TMA box (<= 256 x 256)
   for (int tl = 5; tl >= min_tl; tl--) {
     const int tw = 1 << tl;
@@ -339,12 +335,7 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3) {
         best_windows = windows;
         L.tw_log2 = tl; L.th = th; L.box_w = bw; L.box_h = bh;
       }
-      if (tl == 5 && bw == bw0) { w32 = windows; w32_th = th; w32_bw = bw; w32_bh = bh; }
     }
-  }
-  if (g_prefer_w32 && w32 > 0 && L.tw_log2 != 5 && 4 * w32 >= 3 * best_windows) {
-    L.tw_log2 = 5; L.th = w32_th; L.box_w = w32_bw; L.box_h = w32_bh;
-    best_windows = w32;
   }
   return best_windows;
 }
@@ -356,7 +347,6 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3) {
 void plan_level(LevelInfo &L, bool latency) {
   if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
   if (const char *e = getenv("JDA_B200_TUNE_PITCH")) g_tune_pitch = atoi(e);
-  if (const char *e = getenv("JDA_B200_PREFER_W32")) g_prefer_w32 = atoi(e);
   if (const char *e = getenv("JDA_B200_MAX_SPAN")) g_max_span = std::max(1, atoi(e));
   // Two plans.  Throughput (many frames in flight): coarse levels pool at most 4 warps' buffers, what is
   // left reads global memory in 512-window virtual tiles -- measured fastest on 128+ frame batches.
@@ -607,7 +597,6 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       }
       P.use_tma = tma_ok ? 1 : 0;
       P.stragglers = c->stragglers;
-      P.dense_keep = c->dense_keep; P.dense_max = c->dense_max;
       if (tracing) {
         P.trace_n = c->d_trace_n.p; P.trace_s = c->d_trace_s.p;
         P.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;

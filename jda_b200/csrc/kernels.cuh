@@ -81,8 +81,6 @@ struct ScanParams {
   short sched[K2_MAX_SCHED];     // cart index at which each phase ends; last == K
   int use_tma;
   int stragglers;                // 1: finish nearly empty tiles in cart-parallel straggler mode
-  int dense_keep;                // x/256: the first phase runs uncompacted until fewer than this share of lanes is alive (0: fixed schedule)
-  int dense_max;                 // ... but at most this many carts
   float level_cum[kMaxLevels];   // cumulative share of the scan work in processing order (coarse -> fine)
   // trace (TRACE instantiation only)
   int *trace_n;
@@ -257,7 +255,6 @@ struct TileCtx {
   uint32_t tile_off;     // shared-memory byte offset of the tile
   int tw_log2, tw_mask, step, pitch;
   int x0w, y0w, cw;
-  int dense_lanes;  // valid lanes of the tile's first group (adaptive dense phase)
   int lane;
 };
 
@@ -280,7 +277,7 @@ __device__ __forceinline__ long long trace_index(const TileCtx &c, int wid) {
 // squeezed to the front of the in-place list at `out` (writes never pass the read cursor).
 template <bool SMEM, int NWG, bool TRACE>
 __device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, int n, int cart, int cend,
-                                           int &out, int *adaptive_end = nullptr) {
+                                           int &out) {
   const uint8_t *smem = c.smem;
   const int lane = c.lane;
   float score[NWG];
@@ -354,14 +351,6 @@ __device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, i
     for (int j = 0; j < NWG; j++) {
       score[j] = s[j];
       alive[j] = alive[j] && !(s[j] < cth);
-    }
-    if (adaptive_end && (k & 3) == 3 && k + 1 < cend) {
-      // dense phase, first group of the tile: stop where the packets have thinned out enough that squeezing
-      // the dead lanes out (and paying bank conflicts from then on) beats carrying them
-      int live = 0;
-#pragma unroll
-      for (int j = 0; j < NWG; j++) live += __popc(__ballot_sync(0xffffffffu, alive[j]));
-      if (live * 256 < c.P->dense_keep * c.dense_lanes) { *adaptive_end = k + 1; cend = k + 1; }
     }
   }
 #pragma unroll
@@ -486,25 +475,11 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
   int n = ch << c.tw_log2;  // dense enumeration; columns >= cw are masked off in phase 0
   int cart = 0;
   for (int ph = 0; ph < P.n_sched; ++ph) {
-    int cend = P.sched[ph];
-    if (cend <= cart) continue;  // boundary already passed by the adaptive dense phase
+    const int cend = P.sched[ph];
     int out = 0, base = 0;
     // full groups of NWM packets, then the remainder with as few packets as it needs.  The global-memory
     // levels run twice as wide: their pixel reads are L2-latency bound, not shared-memory bound.
     constexpr int NWM = (SMEM || TRACE || NW > 4 || !JDA_K2_GLOBAL_WIDE) ? NW : 2 * NW;
-    if (cart == 0 && P.dense_keep > 0 && n >= 32 * NWM) {
-      // Dense phase.  Packets of x-adjacent windows read shared memory without bank conflicts; once compacted
-      // they do not.  So the first phase keeps its dead lanes: the tile's first group runs until only
-      // dense_keep/256 of its lanes are alive (checked every 4 carts) and fixes the phase end for the tile.
-      int lanes = 0;
-      for (int j = 0; j < NWM; j++) lanes += __popc(__ballot_sync(0xffffffffu, ((j * 32 + lane) & c.tw_mask) < c.cw));
-      c.dense_lanes = lanes;
-      int aend = min(P.dense_max, P.K);
-      cend = aend;
-      scan_group<SMEM, NWM, TRACE>(c, 0, 0, n, 0, cend, out, &aend);
-      cend = aend;
-      base = 32 * NWM;
-    }
     for (; n - base >= 32 * NWM; base += 32 * NWM) scan_group<SMEM, NWM, TRACE>(c, ph, base, n, cart, cend, out);
     if constexpr (NWM >= 8) {
       if (n - base > 128) { scan_group<SMEM, 8, TRACE>(c, ph, base, n, cart, cend, out); base = n; }

@@ -389,26 +389,3 @@ def test_queue_overflow_grows_and_retries(oracle, oracle_shipped):
         c.close()
     finally:
         del os.environ["JDA_B200_TINY_QUEUES"]
-
-
-@pytest.mark.parametrize("keep,w32", [("110", "0"), ("150", "1"), ("60", "1")])
-def test_adaptive_dense_phase(oracle, oracle_shipped, keep, w32):
-    """uncompacted first phase of adaptive length (scheduling only: results unchanged)"""
-    os.environ["JDA_B200_DENSE_KEEP"] = keep
-    os.environ["JDA_B200_PREFER_W32"] = w32
-    try:
-        c = api.Cascador(SHIPPED_F32, double=False)
-        for img in (synth.facemix_frame(9), synth.noise_frame(3)):
-            _same(c.detect(img, th=-1.0), oracle.detect(oracle_shipped, img, th=-1.0))
-            big = np.stack([img] * 6)                      # throughput plan
-            for r in c.detect_batch(big, th=-1.0):
-                _same(r, oracle.detect(oracle_shipped, img, th=-1.0))
-            tn, ts, lv = c.trace(img, leaf_range=(0, 5000))
-            on, os_, olv = oracle.trace(oracle_shipped, img, leaf_range=(0, 5000))
-            np.testing.assert_array_equal(tn, on)
-            np.testing.assert_array_equal(_bits(ts), _bits(os_))
-            np.testing.assert_array_equal(lv, olv)
-        c.close()
-    finally:
-        del os.environ["JDA_B200_DENSE_KEEP"]
-        del os.environ["JDA_B200_PREFER_W32"]
