@@ -258,7 +258,7 @@ void ctx_free(Context *c) {
 // Expected shared-memory wavefronts of one pixel read (1 = conflict free) for packets of 32 survivors
 // drawn in row-major order from a tw x th tile at a few survival densities.  Bank = (byte address / 4)
 // mod 32; lanes on the same word broadcast, lanes on different words of one bank serialise.  The tile
-// pitch decides how the rows of a tile fold onto the 32 banks (tools/sim_banks.py has the long version).
+// pitch decides how the rows of a tile fold onto the 32 banks (tests/design_sims/sim_banks.py has the long version).
 double estimate_wavefronts(int win, int step, int tw, int th, int pitch) {
   uint32_t rng = 12345u;
   auto next = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };

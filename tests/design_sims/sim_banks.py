@@ -3,10 +3,10 @@
 wavefronts per pixel read (= max number of distinct 4-byte words per bank over the 32 lanes)."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pyoracle
 from jda_b200 import synth
-from tools.sim_lanes import SCHED
+from tests.design_sims.sim_lanes import SCHED
 
 def wavefronts(addr):
     words = addr >> 2

@@ -2,10 +2,10 @@
 per pyramid level, from oracle reject positions.  Unit: one 32-window packet-cart = 41 instructions."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pyoracle
 from jda_b200 import synth, api
-from tools.sim_lanes import SCHED
+from tests.design_sims.sim_lanes import SCHED
 
 def tile_cost(d, nw=4, strag=15):
     """d: deaths (0 = masked lane) in dense order. returns (cost, ideal, parts dict)"""

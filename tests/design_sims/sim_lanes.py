@@ -2,7 +2,7 @@
 positions.  Offline design tool (CPU only): counts warp-level cart iterations ("packet-carts")."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pyoracle
 from jda_b200 import synth
 

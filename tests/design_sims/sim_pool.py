@@ -2,10 +2,10 @@
 Time unit = one cart iteration of one warp (latency-bound regime).  Offline design tool."""
 import heapq, sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pyoracle
 from jda_b200 import synth
-from tools.sim_lanes import tiles_of_frame, SCHED
+from tests.design_sims.sim_lanes import tiles_of_frame, SCHED
 
 def simulate(tiles, W=24, R=12, NW=2, sched=SCHED, carry_frac=0.625, cap=192, load_time=3.0, verbose=False):
     G = 32 * NW; carry_min = int(G * carry_frac)
@@ -103,6 +103,6 @@ if __name__ == "__main__":
             print("  W=%d R=%d NW=%d: instr %.2fx ideal, warp util %.2f, packet-carts/time %.1f (full %d partial %d dense %d)" %
                   (W, R, NW, r["instr_vs_ideal"], r["util"], r["thr"], r["full"], r["partial"], r["dense"]))
         # v1-like reference: independent warps, one tile each, NW=2, time = iterations
-        from tools.sim_lanes import cost_current
+        from tests.design_sims.sim_lanes import cost_current
         c, i = cost_current([(True, 24, d) for d in T], 2)
         print("  v1 (12 independent warps): instr %.2fx ideal, packet-carts/time %.1f" % (c / i, i / (c / 2 / 12)))
