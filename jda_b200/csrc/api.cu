@@ -620,7 +620,10 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     }
     Q.windows_per_frame = g.windows_per_frame;
     Q.dense = use_scan ? 0 : 1; Q.dense_total = total_windows;
-    Q.t_start = use_scan ? 1 : 0;
+    // a handful of frames: the cohort-staged k3_stage0 is a ~0.1 ms serial pipeline for a few survivors, so the
+    // cascade kernel redoes stage 0 itself (same bits); batches take the staged path
+    const bool staged0 = use_scan && !latency_plan;
+    Q.t_start = staged0 ? 1 : 0;
     Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
     Q.rec_words = rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
     if (tracing) {
@@ -672,15 +675,17 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
         st.scan_launches++;
         if (timing && ch == nchunks - 1) CU_OK(cudaEventRecord(c->ev[3], s));  // end of the last scan
         if (ch < nchunks - 1) continue;  // the cascade kernels run once, behind the last chunk's scan
+        if (staged0) {
         // stage 0 of the survivors: leaves + regression gather, cohort-staged
         S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)cap_chunk;
         S.out_shape = c->d_shape0.p;
         k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), s>>>(S);
         CU_OK(cudaGetLastError());
         st.cascade_launches++;
+        }
       }
       Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)cap_chunk;
-      Q.init_shape = use_scan ? c->d_shape0.p : nullptr;
+      Q.init_shape = staged0 ? c->d_shape0.p : nullptr;
       Q.work_counter = c->d_counters + kCntWork;
       {
         const int grid = c->sm_count * 8;

@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
         bool on[4];
 #pragma unroll
         for (int h = 0; h < 4; h++) { on[h] = i0 + 32 * h + lane < D; acc[h] = on[h] ? shape[i0 + 32 * h + lane] : 0.f; }
-#pragma unroll 8
+#pragma unroll 16
         for (int k = 0; k < P.K; k++) {
           const float *row = wt + (size_t)(k * kLeaves + leafs[k]) * D + i0 + lane;
 #pragma unroll
