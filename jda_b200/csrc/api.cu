@@ -435,8 +435,307 @@ struct TraceOut {
   long long w0 = 0, w1 = 0;
 };
 
+// ---------------------------------------------------------------------------------- one batch on the device
+//
+// run_device = stage_frames -> make_planes -> [launch_scan per chunk -> launch_cascade] -> collect,
+// retried with larger queues when the device counters say a queue overflowed.
+
+// State of one run_device call.
+struct Run {
+  Context *c;
+  const jdaB200Batch *b;
+  const TraceOut *trace;
+  bool timing, tracing;
+  bool latency_plan;   // <= kLatencyFrames frames: latency tile plan, no cohort-staged stage 0
+  bool use_scan;       // stage 0 from the LUT scan (k2_scan); false: every window through k3_cascade
+  bool staged0;        // k3_stage0 computes the survivors' stage-0 shapes (batches)
+  cudaStream_t s;
+  const uint8_t *d_frames;
+  int pitch;
+  size_t fstride;
+  int nchunks;         // scan launches (the host copy is split the same way)
+  bool host_chunks;
+  int D, rec_words, t_run, leaf_stride, leaf_pad;
+  long long total_windows;
+  float r;             // 1.f / sqrtf(2.f) as the reference computes it (c/jda.c:341)
+  int hw, hh, qw, qh;
+  size_t hq_stride;
+};
+
+// Frames to HBM.  Device input is used in place; host input goes into a 16-byte-pitched store: large batches
+// in kMaxChunks pieces on the copy stream (the scan of chunk i then overlaps the copy of chunk i+1), a small
+// pageable input repacked through pinned staging (the driver's pageable path costs more than a one-frame detect).
+bool stage_frames(Run &R, const unsigned char *frames) {
+  Context *c = R.c;
+  const jdaB200Batch &b = *R.b;
+  const HostModel &m = c->m;
+  R.nchunks = 1;
+  R.host_chunks = false;
+  if (b.flags & JDA_B200_DEVICE_INPUT) {
+    R.d_frames = frames; R.pitch = b.pitch; R.fstride = b.frame_stride;
+    return true;
+  }
+  R.pitch = (b.width + 15) & ~15;
+  R.fstride = (size_t)R.pitch * b.height;
+  if (!c->d_frames.ensure(R.fstride * b.n_frames + 256)) return false;
+  if (b.n_frames >= 128 && !m.any_scaled && R.use_scan && !R.tracing && !getenv("JDA_B200_NO_CHUNKS")) {
+    R.nchunks = kMaxChunks;
+    R.host_chunks = true;
+  }
+  CU_OK(cudaEventRecord(c->ev_copy[kMaxChunks], R.s));
+  CU_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
+  bool staged = false;
+  if (R.nchunks == 1 && R.fstride * b.n_frames <= c->h_stage_cap) {
+    cudaPointerAttributes pa;
+    const bool pageable = cudaPointerGetAttributes(&pa, frames) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (pageable) {
+      for (int f = 0; f < b.n_frames; f++)
+        for (int y = 0; y < b.height; y++)
+          memcpy(c->h_stage + f * R.fstride + (size_t)y * R.pitch, frames + f * b.frame_stride + (size_t)y * b.pitch, b.width);
+      CU_OK(cudaMemcpyAsync(c->d_frames.p, c->h_stage, R.fstride * b.n_frames, cudaMemcpyHostToDevice, c->copy_stream));
+      CU_OK(cudaEventRecord(c->ev_copy[0], c->copy_stream));
+      staged = true;
+    }
+  }
+  for (int ch = 0; ch < R.nchunks && !staged; ch++) {
+    const int f0 = (int)((long long)b.n_frames * ch / R.nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / R.nchunks);
+    if (b.frame_stride == (size_t)b.pitch * b.height) {
+      CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f0 * R.fstride, R.pitch, frames + f0 * b.frame_stride, b.pitch, b.width,
+                              (size_t)b.height * (f1 - f0), cudaMemcpyHostToDevice, c->copy_stream));
+    } else {
+      for (int f = f0; f < f1; f++)
+        CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * R.fstride, R.pitch, frames + f * b.frame_stride, b.pitch, b.width,
+                                b.height, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
+  }
+  if (!R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[0], 0));
+  R.d_frames = c->d_frames.p;
+  return true;
+}
+
+// h / q planes (c/jda.c:450-457), only when some node samples them
+bool make_planes(Run &R) {
+  Context *c = R.c;
+  const jdaB200Batch &b = *R.b;
+  R.r = 1.f / sqrtf(2.f);
+  R.hw = (int)(b.width * R.r); R.hh = (int)(b.height * R.r); R.qw = b.width / 2; R.qh = b.height / 2;
+  R.hq_stride = (size_t)R.hw * R.hh + (size_t)R.qw * R.qh;
+  if (!c->m.any_scaled) return true;
+  if (!c->d_hq.ensure(R.hq_stride * b.n_frames)) return false;
+  const int big = std::max(R.hw * R.hh, R.qw * R.qh);
+  for (int f0 = 0; f0 < b.n_frames; f0 += 32768) {  // gridDim.z limit
+    dim3 grid((big + 255) / 256, 2, std::min(32768, b.n_frames - f0));
+    k1_resize<<<grid, 256, 0, R.s>>>(R.d_frames + (size_t)f0 * R.fstride, R.fstride, R.pitch, b.width, b.height,
+                                    c->d_hq.p + (size_t)f0 * R.hq_stride, R.hq_stride, R.hw, R.hh, R.qw, R.qh);
+    CU_OK(cudaGetLastError());
+  }
+  c->last.resize_launches = 1;
+  return true;
+}
+
+bool prepare_trace(Run &R) {
+  if (!R.tracing) return true;
+  Context *c = R.c;
+  if (!c->d_trace_n.ensure(R.total_windows) || !c->d_trace_s.ensure(R.total_windows)) return false;
+  CU_OK(cudaMemsetAsync(c->d_trace_n.p, 0, R.total_windows * 4, R.s));
+  CU_OK(cudaMemsetAsync(c->d_trace_s.p, 0, R.total_windows * 4, R.s));
+  if (R.trace->leaf && R.trace->w1 > R.trace->w0) {
+    const size_t nb = (size_t)(R.trace->w1 - R.trace->w0) * R.leaf_stride;
+    if (!c->d_trace_leaf.ensure(nb)) return false;
+    CU_OK(cudaMemsetAsync(c->d_trace_leaf.p, 255, nb, R.s));
+  }
+  return true;
+}
+
+// k2_scan over every chunk of frames; all chunks feed one survivor queue.
+bool launch_scan(Run &R) {
+  Context *c = R.c;
+  const jdaB200Batch &b = *R.b;
+  const Geometry &g = c->geo;
+  const HostModel &m = c->m;
+  jdaB200Stats &st = c->last;
+  ScanParams P;
+  memset(&P, 0, sizeof P);
+  for (int i = 0; i < g.n_levels; i++) P.lv[i] = g.lv[i];
+  P.frame_stride = R.fstride; P.pitch = R.pitch; P.W = b.width; P.H = b.height;
+  P.n_levels = g.n_levels; P.K = m.K; P.table_bytes = g.table_bytes;
+  P.tables = c->d_tables.p; P.norms = c->d_norms;
+  P.windows_per_frame = g.windows_per_frame;
+  P.n_sched = (int)c->sched.size();
+  for (int i = 0; i < P.n_sched; i++) P.sched[i] = c->sched[i];
+  P.surv = c->d_surv.p; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)c->surv_cap;
+  P.surv_leaves = c->d_surv_leaves.p; P.leaf_pad = R.leaf_pad;
+  // TMA needs 16-byte aligned base and strides
+  const bool tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)R.d_frames % 16 == 0) &&
+                      R.pitch % 16 == 0 && R.fstride % 16 == 0;
+  int n_smem = 0;
+  for (int i = 0; i < g.n_levels; i++) n_smem += g.lv[i].use_smem;
+  st.levels_smem = n_smem;
+  {  // share of the scan work per level, in processing order (coarse -> fine)
+    double w[kMaxLevels], tot = 0;
+    for (int i = 0; i < g.n_levels; i++) {
+      const LevelInfo &L = g.lv[g.n_levels - 1 - i];
+      w[i] = (double)L.nx * L.ny * (L.use_smem ? (L.span == 1 ? 1.0 : 1.4) : 2.2);
+      tot += w[i];
+    }
+    double acc = 0;
+    for (int i = 0; i < g.n_levels; i++) { acc += w[i]; P.level_cum[i] = (float)(acc / tot); }
+  }
+  P.use_tma = tma_ok ? 1 : 0;
+  P.stragglers = c->stragglers;
+  if (R.tracing) {
+    P.trace_n = c->d_trace_n.p; P.trace_s = c->d_trace_s.p;
+    P.trace_leaf = (R.trace->leaf && R.trace->w1 > R.trace->w0) ? c->d_trace_leaf.p : nullptr;
+    P.leaf_w0 = R.trace->w0; P.leaf_w1 = R.trace->w1; P.leaf_stride = R.leaf_stride;
+  }
+  const size_t smem = k2_smem_bytes(g.table_bytes);
+  const int grid = c->sm_count;
+  for (int ch = 0; ch < R.nchunks; ch++) {
+    const int f0 = (int)((long long)b.n_frames * ch / R.nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / R.nchunks);
+    if (f1 <= f0) continue;
+    P.frames = R.d_frames + (size_t)f0 * R.fstride;
+    P.n_frames = f1 - f0;
+    P.frame_base = f0;
+    P.tile_counters = c->d_counters + ch * kMaxLevels;
+    for (int i = 0; i < g.n_levels && tma_ok; i++) {
+      if (!g.lv[i].use_smem) continue;
+      cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)(f1 - f0)};
+      cuuint64_t strides[2] = {(cuuint64_t)R.pitch, (cuuint64_t)R.fstride};
+      cuuint32_t box[3] = {(cuuint32_t)g.lv[i].box_w, (cuuint32_t)g.lv[i].box_h, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult cr = c->encode(&P.maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)P.frames, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) {
+        set_err("cuTensorMapEncodeTiled failed (%d) for level %d box %dx%d", (int)cr, i, g.lv[i].box_w, g.lv[i].box_h);
+        return false;
+      }
+    }
+    if (R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[ch], 0));
+    if (R.tracing) {
+      if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+      else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+      else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+    } else if (c->nw == 1) {
+      k2_scan<1, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+    } else if (c->nw == 4) {
+      k2_scan<4, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+    } else {
+      k2_scan<2, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+    }
+    CU_OK(cudaGetLastError());
+    st.scan_launches++;
+  }
+  return true;
+}
+
+// k3_stage0 (batches) + k3_cascade, once, over the whole survivor queue (or over every window in dense mode).
+// Running them per chunk on a second stream under the next chunk's scan was tried -- they fit on the SMs next
+// to the scan blocks -- and slowed the scan by more than the cascade time it hid (r1: 31.9 vs 30.2 ms / step).
+bool launch_cascade(Run &R) {
+  Context *c = R.c;
+  const jdaB200Batch &b = *R.b;
+  const Geometry &g = c->geo;
+  const HostModel &m = c->m;
+  jdaB200Stats &st = c->last;
+  if (R.staged0) {
+    Stage0Params S;
+    memset(&S, 0, sizeof S);
+    S.surv_leaves = c->d_surv_leaves.p;
+    S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
+    S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)c->surv_cap;
+    S.out_shape = c->d_shape0.p;
+    k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
+    CU_OK(cudaGetLastError());
+    st.cascade_launches++;
+  }
+  CascadeParams Q;
+  memset(&Q, 0, sizeof Q);
+  Q.frames = R.d_frames; Q.frame_stride = R.fstride; Q.pitch = R.pitch; Q.W = b.width; Q.H = b.height;
+  Q.hq = m.any_scaled ? c->d_hq.p : nullptr; Q.hq_stride = R.hq_stride; Q.hw = R.hw; Q.hh = R.hh; Q.qw = R.qw; Q.qh = R.qh;
+  Q.nodes = c->d_nodes; Q.leaf = c->d_leaf; Q.cart = c->d_cart; Q.w = c->d_w; Q.mean_shape = c->d_mean;
+  Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.t_run = R.t_run; Q.r = R.r;
+  Q.n_levels = g.n_levels;
+  for (int i = 0; i < g.n_levels; i++) {
+    Q.lv_win[i] = g.lv[i].win; Q.lv_step[i] = g.lv[i].step; Q.lv_nx[i] = g.lv[i].nx; Q.lv_ny[i] = g.lv[i].ny;
+    Q.lv_base[i] = g.lv[i].win_base;
+  }
+  Q.windows_per_frame = g.windows_per_frame;
+  Q.dense = R.use_scan ? 0 : 1; Q.dense_total = R.total_windows;
+  Q.t_start = R.staged0 ? 1 : 0;
+  Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
+  Q.init_shape = R.staged0 ? c->d_shape0.p : nullptr;
+  Q.work_counter = c->d_counters + kCntWork;
+  Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
+  Q.rec_words = R.rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
+  if (R.tracing) {
+    Q.trace_n = c->d_trace_n.p; Q.trace_s = c->d_trace_s.p;
+    Q.trace_leaf = (R.trace->leaf && R.trace->w1 > R.trace->w0) ? c->d_trace_leaf.p : nullptr;
+    Q.leaf_w0 = R.trace->w0; Q.leaf_w1 = R.trace->w1; Q.leaf_stride = R.leaf_stride;
+  }
+  const int grid = c->sm_count * 8;
+  const size_t smem = k3_smem_bytes(m.K);
+  if (R.tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);
+  else k3_cascade<false><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);
+  CU_OK(cudaGetLastError());
+  st.cascade_launches++;
+  return true;
+}
+
+// Counters + hit records back to the host.  overflow = a queue was too small (capacities already grown).
+bool collect(Run &R, std::vector<HitRec> &hits, bool &overflow) {
+  Context *c = R.c;
+  jdaB200Stats &st = c->last;
+  cudaStream_t s = R.s;
+  overflow = false;
+  CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  // the first records ride along with the counters: a call with few hits needs a single round trip
+  const size_t eager = std::min<size_t>(kEagerHits, c->hit_cap);
+  CU_OK(cudaMemcpyAsync(c->h_eager, c->d_hits.p, eager * R.rec_words * 4, cudaMemcpyDeviceToHost, s));
+  CU_OK(cudaStreamSynchronize(s));
+  const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
+  if (ns > c->surv_cap || nh > c->hit_cap) {
+    if (ns > c->surv_cap) c->surv_cap = ns + ns / 4;
+    if (nh > c->hit_cap) c->hit_cap = nh + nh / 4;
+    overflow = true;
+    return true;
+  }
+  st.stage0_survivors = R.use_scan ? (long long)ns : 0;
+  st.raw_hits = (long long)nh;
+  bool more = false;
+  c->h_hits.resize(std::max(nh, (size_t)1) * R.rec_words);
+  memcpy(c->h_hits.data(), c->h_eager, std::min(nh, eager) * R.rec_words * 4);
+  if (nh > eager) {
+    CU_OK(cudaMemcpyAsync(c->h_hits.data() + eager * R.rec_words, c->d_hits.p + eager * R.rec_words,
+                          (nh - eager) * R.rec_words * 4, cudaMemcpyDeviceToHost, s));
+    more = true;
+  }
+  if (R.tracing) {
+    const TraceOut *t = R.trace;
+    if (t->n) CU_OK(cudaMemcpyAsync(t->n, c->d_trace_n.p, R.total_windows * 4, cudaMemcpyDeviceToHost, s));
+    if (t->s) CU_OK(cudaMemcpyAsync(t->s, c->d_trace_s.p, R.total_windows * 4, cudaMemcpyDeviceToHost, s));
+    if (t->leaf && t->w1 > t->w0)
+      CU_OK(cudaMemcpyAsync(t->leaf, c->d_trace_leaf.p, (size_t)(t->w1 - t->w0) * R.leaf_stride, cudaMemcpyDeviceToHost, s));
+  }
+  if (R.timing) CU_OK(cudaEventRecord(c->ev[5], s));
+  if (more || R.tracing || R.timing) CU_OK(cudaStreamSynchronize(s));
+  hits.resize(nh);
+  for (size_t i = 0; i < nh; i++) {
+    const float *rec = c->h_hits.data() + i * R.rec_words;
+    const int *ri = reinterpret_cast<const int *>(rec);
+    hits[i] = HitRec{ri[0], (uint32_t)ri[1], ri[2], ri[3], ri[4], rec[5], rec + kHitHeader};
+  }
+  // the reference's scan order: level, then y, then x (c/jda.c:332-339) -- the key packs exactly that
+  std::sort(hits.begin(), hits.end(), [](const HitRec &a, const HitRec &b2) {
+    return a.frame != b2.frame ? a.frame < b2.frame : a.key < b2.key;
+  });
+  return true;
+}
+
 // Runs the device path for one batch; on success `hits` holds the raw hit records sorted into scan
-// order (frame, level, y, x).  `store` keeps the record floats alive.
+// order (frame, level, y, x).  The record floats stay alive in the context until the next call.
 bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, std::vector<HitRec> &hits,
                 const TraceOut *trace, bool timing) {
   hits.clear();
@@ -448,103 +747,34 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     return false;
   }
   if (!ctx_init(c)) return false;
-  const bool latency_plan = b.n_frames <= kLatencyFrames;
-  if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, latency_plan)) return false;
+  Run R;
+  memset(&R, 0, sizeof R);
+  R.c = c; R.b = &b; R.trace = trace; R.timing = timing; R.tracing = trace != nullptr;
+  R.latency_plan = b.n_frames <= kLatencyFrames;
+  if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, R.latency_plan)) return false;
   const Geometry &g = c->geo;
   st.n_levels = g.n_levels;
   st.windows = g.windows_per_frame * b.n_frames;
   if (g.n_levels == 0) return true;
   const HostModel &m = c->m;
-  cudaStream_t s = c->stream();
-  const int D = m.D();
-  const int rec_words = kHitHeader + D;
-  const int t_run = (b.t_limit > 0 && b.t_limit < m.T) ? b.t_limit : m.T;
+  R.s = c->stream();
+  R.D = m.D();
+  R.rec_words = kHitHeader + R.D;
+  R.t_run = (b.t_limit > 0 && b.t_limit < m.T) ? b.t_limit : m.T;
+  R.leaf_stride = m.T * m.K;
+  R.leaf_pad = (m.K + 15) & ~15;
+  R.total_windows = st.windows;
+  R.use_scan = m.stage0_lut_ok && !(b.flags & JDA_B200_NO_STAGE0_SCAN);
+  // a handful of frames: the cohort-staged k3_stage0 is a ~0.1 ms serial pipeline for a few survivors, so the
+  // cascade kernel redoes stage 0 itself (same bits); batches take the staged path
+  R.staged0 = R.use_scan && !R.latency_plan;
+  cudaStream_t s = R.s;
 
   if (timing) CU_OK(cudaEventRecord(c->ev[0], s));
-  // ---- frames
-  const uint8_t *d_frames;
-  int pitch;
-  size_t fstride;
-  int nchunks = 1;      // launches of the scan (and of the cascade kernels behind it)
-  int copy_chunks = 1;  // pieces the host batch is copied in
-  if (b.flags & JDA_B200_DEVICE_INPUT) {
-    d_frames = frames; pitch = b.pitch; fstride = b.frame_stride;
-  } else {
-    pitch = (b.width + 15) & ~15;
-    fstride = (size_t)pitch * b.height;
-    if (!c->d_frames.ensure(fstride * b.n_frames + 256)) return false;
-    // Large host batches travel in chunks on a second stream; the scan of chunk i overlaps the copy of i+1.
-    if (b.n_frames >= 128 && !m.any_scaled && m.stage0_lut_ok && !trace && !(b.flags & JDA_B200_NO_STAGE0_SCAN) &&
-        !getenv("JDA_B200_NO_CHUNKS"))
-      nchunks = copy_chunks = kMaxChunks;
-    CU_OK(cudaEventRecord(c->ev_copy[kMaxChunks], s));
-    CU_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
-    // a small pageable input is repacked into pinned staging on the host (device pitch) and sent as one
-    // asynchronous copy; the driver's own pageable path costs more than the whole detect for one frame
-    bool staged = false;
-    if (nchunks == 1 && fstride * b.n_frames <= c->h_stage_cap) {
-      cudaPointerAttributes pa;
-      const bool pageable = cudaPointerGetAttributes(&pa, frames) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
-      cudaGetLastError();
-      if (pageable) {
-        for (int f = 0; f < b.n_frames; f++)
-          for (int y = 0; y < b.height; y++)
-            memcpy(c->h_stage + f * fstride + (size_t)y * pitch, frames + f * b.frame_stride + (size_t)y * b.pitch, b.width);
-        CU_OK(cudaMemcpyAsync(c->d_frames.p, c->h_stage, fstride * b.n_frames, cudaMemcpyHostToDevice, c->copy_stream));
-        CU_OK(cudaEventRecord(c->ev_copy[0], c->copy_stream));
-        staged = true;
-      }
-    }
-    if (!staged)
-    for (int ch = 0; ch < nchunks; ch++) {
-      const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
-      if (b.frame_stride == (size_t)b.pitch * b.height) {
-        CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f0 * fstride, pitch, frames + f0 * b.frame_stride, b.pitch, b.width,
-                                (size_t)b.height * (f1 - f0), cudaMemcpyHostToDevice, c->copy_stream));
-      } else {
-        for (int f = f0; f < f1; f++)
-          CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * fstride, pitch, frames + f * b.frame_stride, b.pitch,
-                                  b.width, b.height, cudaMemcpyHostToDevice, c->copy_stream));
-      }
-      CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
-    }
-    if (copy_chunks == 1) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[0], 0));
-    d_frames = c->d_frames.p;
-  }
+  if (!stage_frames(R, frames)) return false;
   if (timing) CU_OK(cudaEventRecord(c->ev[1], s));
+  if (!make_planes(R) || !prepare_trace(R)) return false;
 
-  // ---- h / q planes (c/jda.c:450-457), only when some node samples them
-  const float r = 1.f / sqrtf(2.f);
-  const int hw = (int)(b.width * r), hh = (int)(b.height * r), qw = b.width / 2, qh = b.height / 2;
-  const size_t hq_stride = (size_t)hw * hh + (size_t)qw * qh;
-  if (m.any_scaled) {
-    if (!c->d_hq.ensure(hq_stride * b.n_frames)) return false;
-    const int big = std::max(hw * hh, qw * qh);
-    for (int f0 = 0; f0 < b.n_frames; f0 += 32768) {  // gridDim.z limit
-      dim3 grid((big + 255) / 256, 2, std::min(32768, b.n_frames - f0));
-      k1_resize<<<grid, 256, 0, s>>>(d_frames + (size_t)f0 * fstride, fstride, pitch, b.width, b.height,
-                                     c->d_hq.p + (size_t)f0 * hq_stride, hq_stride, hw, hh, qw, qh);
-      CU_OK(cudaGetLastError());
-    }
-    st.resize_launches = 1;
-  }
-
-  // ---- trace buffers
-  const bool tracing = trace != nullptr;
-  const long long total_windows = st.windows;
-  int leaf_stride = m.T * m.K;
-  if (tracing) {
-    if (!c->d_trace_n.ensure(total_windows) || !c->d_trace_s.ensure(total_windows)) return false;
-    CU_OK(cudaMemsetAsync(c->d_trace_n.p, 0, total_windows * 4, s));
-    CU_OK(cudaMemsetAsync(c->d_trace_s.p, 0, total_windows * 4, s));
-    if (trace->leaf && trace->w1 > trace->w0) {
-      const size_t nb = (size_t)(trace->w1 - trace->w0) * leaf_stride;
-      if (!c->d_trace_leaf.ensure(nb)) return false;
-      CU_OK(cudaMemsetAsync(c->d_trace_leaf.p, 255, nb, s));
-    }
-  }
-
-  const bool use_scan = m.stage0_lut_ok && !(b.flags & JDA_B200_NO_STAGE0_SCAN);
   if (const char *e = getenv("JDA_B200_TINY_QUEUES")) {  // test hook: start with queues that overflow, exercise grow-and-retry
     if (atoi(e) && c->surv_cap == 0) { c->surv_cap = 8; c->hit_cap = 2; }
   } else {
@@ -554,197 +784,26 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     c->hit_cap = std::max(c->hit_cap, (size_t)b.n_frames * 128);
   }
 
-  // Host batches are scanned chunk by chunk behind their copies (nchunks == copy_chunks); all chunks feed one
-  // survivor queue and the cascade kernels run once at the end.  Running the cascade kernels of chunk i on a
-  // second stream under the scan of chunk i+1 was tried (they fit next to the scan blocks): the scan slowed
-  // down by more than the cascade time it hid (r1: 31.9 vs 30.2 ms per 512-frame step), so it is not done.
-  const bool host_chunks = !(b.flags & JDA_B200_DEVICE_INPUT) && copy_chunks > 1;
-
   for (int attempt = 0; attempt < 4; attempt++) {
-    if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * rec_words)) return false;
-    const int leaf_pad = (m.K + 15) & ~15;
-    if (use_scan && (!c->d_shape0.ensure(c->surv_cap * D) || !c->d_surv_leaves.ensure(c->surv_cap * leaf_pad))) return false;
-    const size_t cap_chunk = c->surv_cap;  // one queue shared by every chunk
+    if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * R.rec_words)) return false;
+    if (R.use_scan && (!c->d_shape0.ensure(c->surv_cap * R.D) || !c->d_surv_leaves.ensure(c->surv_cap * R.leaf_pad))) return false;
     CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
     if (timing) CU_OK(cudaEventRecord(c->ev[2], s));
-
-    ScanParams P;
-    memset(&P, 0, sizeof P);
-    bool tma_ok = false;
-    if (use_scan) {
-      for (int i = 0; i < g.n_levels; i++) P.lv[i] = g.lv[i];
-      P.frame_stride = fstride; P.pitch = pitch; P.W = b.width; P.H = b.height;
-      P.n_levels = g.n_levels; P.K = m.K; P.table_bytes = g.table_bytes;
-      P.tables = c->d_tables.p; P.norms = c->d_norms;
-      P.windows_per_frame = g.windows_per_frame;
-      P.n_sched = (int)c->sched.size();
-      for (int i = 0; i < P.n_sched; i++) P.sched[i] = c->sched[i];
-      // TMA needs 16-byte aligned base and strides
-      tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)d_frames % 16 == 0) && pitch % 16 == 0 &&
-               fstride % 16 == 0;
-      int n_smem = 0;
-      for (int i = 0; i < g.n_levels; i++) n_smem += g.lv[i].use_smem;
-      st.levels_smem = n_smem;
-      {  // share of the scan work per level, in processing order (coarse -> fine)
-        double w[kMaxLevels], tot = 0;
-        for (int i = 0; i < g.n_levels; i++) {
-          const LevelInfo &L = g.lv[g.n_levels - 1 - i];
-          w[i] = (double)L.nx * L.ny * (L.use_smem ? (L.span == 1 ? 1.0 : 1.4) : 2.2);
-          tot += w[i];
-        }
-        double acc = 0;
-        for (int i = 0; i < g.n_levels; i++) { acc += w[i]; P.level_cum[i] = (float)(acc / tot); }
-      }
-      P.use_tma = tma_ok ? 1 : 0;
-      P.stragglers = c->stragglers;
-      if (tracing) {
-        P.trace_n = c->d_trace_n.p; P.trace_s = c->d_trace_s.p;
-        P.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;
-        P.leaf_w0 = trace->w0; P.leaf_w1 = trace->w1; P.leaf_stride = leaf_stride;
-      }
-    }
-    Stage0Params S;
-    memset(&S, 0, sizeof S);
-    S.surv_leaves = c->d_surv_leaves.p;
-    S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
-    CascadeParams Q;
-    memset(&Q, 0, sizeof Q);
-    Q.frames = d_frames; Q.frame_stride = fstride; Q.pitch = pitch; Q.W = b.width; Q.H = b.height;
-    Q.hq = m.any_scaled ? c->d_hq.p : nullptr; Q.hq_stride = hq_stride; Q.hw = hw; Q.hh = hh; Q.qw = qw; Q.qh = qh;
-    Q.nodes = c->d_nodes; Q.leaf = c->d_leaf; Q.cart = c->d_cart; Q.w = c->d_w; Q.mean_shape = c->d_mean;
-    Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.t_run = t_run; Q.r = r;
-    Q.n_levels = g.n_levels;
-    for (int i = 0; i < g.n_levels; i++) {
-      Q.lv_win[i] = g.lv[i].win; Q.lv_step[i] = g.lv[i].step; Q.lv_nx[i] = g.lv[i].nx; Q.lv_ny[i] = g.lv[i].ny;
-      Q.lv_base[i] = g.lv[i].win_base;
-    }
-    Q.windows_per_frame = g.windows_per_frame;
-    Q.dense = use_scan ? 0 : 1; Q.dense_total = total_windows;
-    // a handful of frames: the cohort-staged k3_stage0 is a ~0.1 ms serial pipeline for a few survivors, so the
-    // cascade kernel redoes stage 0 itself (same bits); batches take the staged path
-    const bool staged0 = use_scan && !latency_plan;
-    Q.t_start = staged0 ? 1 : 0;
-    Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
-    Q.rec_words = rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
-    if (tracing) {
-      Q.trace_n = c->d_trace_n.p; Q.trace_s = c->d_trace_s.p;
-      Q.trace_leaf = (trace->leaf && trace->w1 > trace->w0) ? c->d_trace_leaf.p : nullptr;
-      Q.leaf_w0 = trace->w0; Q.leaf_w1 = trace->w1; Q.leaf_stride = leaf_stride;
-    }
-
-    for (int ch = 0; ch < nchunks; ch++) {
-      const int f0 = (int)((long long)b.n_frames * ch / nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / nchunks);
-      if (f1 <= f0) continue;
-      const size_t qoff = 0;
-      if (use_scan) {
-        P.frames = d_frames + (size_t)f0 * fstride;
-        P.n_frames = f1 - f0;
-        P.frame_base = f0;
-        P.tile_counters = c->d_counters + ch * kMaxLevels;
-        P.surv = c->d_surv.p + qoff; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)cap_chunk;
-        P.surv_leaves = c->d_surv_leaves.p; P.leaf_pad = leaf_pad;
-        for (int i = 0; i < g.n_levels && tma_ok; i++) {
-          if (!g.lv[i].use_smem) continue;
-          cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)(f1 - f0)};
-          cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
-          cuuint32_t box[3] = {(cuuint32_t)g.lv[i].box_w, (cuuint32_t)g.lv[i].box_h, 1};
-          cuuint32_t es[3] = {1, 1, 1};
-          CUresult cr = c->encode(&P.maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)P.frames, dims, strides, box,
-                                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-          if (cr != CUDA_SUCCESS) {
-            set_err("cuTensorMapEncodeTiled failed (%d) for level %d box %dx%d", (int)cr, i, g.lv[i].box_w, g.lv[i].box_h);
-            return false;
-          }
-        }
-        if (host_chunks) CU_OK(cudaStreamWaitEvent(s, c->ev_copy[ch], 0));  // copy_chunks == nchunks here
-        const size_t smem = k2_smem_bytes(g.table_bytes);
-        const int grid = c->sm_count;
-        if (tracing) {
-          if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
-          else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
-          else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, s>>>(P);
-        } else if (c->nw == 1) {
-          k2_scan<1, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
-        } else if (c->nw == 4) {
-          k2_scan<4, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
-        } else {
-          k2_scan<2, false><<<grid, K2_WARPS * 32, smem, s>>>(P);
-        }
-        CU_OK(cudaGetLastError());
-        st.scan_launches++;
-        if (timing && ch == nchunks - 1) CU_OK(cudaEventRecord(c->ev[3], s));  // end of the last scan
-        if (ch < nchunks - 1) continue;  // the cascade kernels run once, behind the last chunk's scan
-        if (staged0) {
-        // stage 0 of the survivors: leaves + regression gather, cohort-staged
-        S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)cap_chunk;
-        S.out_shape = c->d_shape0.p;
-        k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, D), s>>>(S);
-        CU_OK(cudaGetLastError());
-        st.cascade_launches++;
-        }
-      }
-      Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)cap_chunk;
-      Q.init_shape = staged0 ? c->d_shape0.p : nullptr;
-      Q.work_counter = c->d_counters + kCntWork;
-      {
-        const int grid = c->sm_count * 8;
-        const size_t smem = k3_smem_bytes(m.K);
-        if (tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, s>>>(Q);
-        else k3_cascade<false><<<grid, K3_WARPS * 32, smem, s>>>(Q);
-        CU_OK(cudaGetLastError());
-        st.cascade_launches++;
-      }
-    }
-    if (timing && !use_scan) CU_OK(cudaEventRecord(c->ev[3], s));
+    if (R.use_scan && !launch_scan(R)) return false;
+    if (timing) CU_OK(cudaEventRecord(c->ev[3], s));
+    if (!launch_cascade(R)) return false;
     if (timing) CU_OK(cudaEventRecord(c->ev[4], s));
-    CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    // the first records ride along with the counters: a call with few hits needs a single round trip
-    const size_t eager = std::min<size_t>(kEagerHits, c->hit_cap);
-    CU_OK(cudaMemcpyAsync(c->h_eager, c->d_hits.p, eager * rec_words * 4, cudaMemcpyDeviceToHost, s));
-    CU_OK(cudaStreamSynchronize(s));
-    const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
-    if (ns > cap_chunk || nh > c->hit_cap) {  // queues overflowed: grow and run again
-      if (ns > cap_chunk) c->surv_cap = ns + ns / 4;
-      if (nh > c->hit_cap) c->hit_cap = nh + nh / 4;
-      continue;
-    }
-    st.stage0_survivors = use_scan ? (long long)ns : 0;
-    st.raw_hits = (long long)nh;
-    bool more = false;
-    c->h_hits.resize(std::max(nh, (size_t)1) * rec_words);
-    memcpy(c->h_hits.data(), c->h_eager, std::min(nh, eager) * rec_words * 4);
-    if (nh > eager) {
-      CU_OK(cudaMemcpyAsync(c->h_hits.data() + eager * rec_words, c->d_hits.p + eager * rec_words,
-                            (nh - eager) * rec_words * 4, cudaMemcpyDeviceToHost, s));
-      more = true;
-    }
-    if (tracing) {
-      if (trace->n) CU_OK(cudaMemcpyAsync(trace->n, c->d_trace_n.p, total_windows * 4, cudaMemcpyDeviceToHost, s));
-      if (trace->s) CU_OK(cudaMemcpyAsync(trace->s, c->d_trace_s.p, total_windows * 4, cudaMemcpyDeviceToHost, s));
-      if (trace->leaf && trace->w1 > trace->w0)
-        CU_OK(cudaMemcpyAsync(trace->leaf, c->d_trace_leaf.p, (size_t)(trace->w1 - trace->w0) * leaf_stride,
-                              cudaMemcpyDeviceToHost, s));
-    }
-    if (timing) CU_OK(cudaEventRecord(c->ev[5], s));
-    if (more || tracing || timing) CU_OK(cudaStreamSynchronize(s));
+    bool overflow = false;
+    if (!collect(R, hits, overflow)) return false;
+    if (overflow) continue;  // queues were too small: they have been grown, run again
     if (timing) {
       if (b.flags & JDA_B200_DEVICE_INPUT) st.ms_h2d = 0.f;
-      else cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[copy_chunks - 1]);
+      else cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[R.host_chunks ? R.nchunks - 1 : 0]);
       cudaEventElapsedTime(&st.ms_resize, c->ev[1], c->ev[2]);
       cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
       cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);
       cudaEventElapsedTime(&st.ms_d2h, c->ev[4], c->ev[5]);
     }
-    hits.resize(nh);
-    for (size_t i = 0; i < nh; i++) {
-      const float *rec = c->h_hits.data() + i * rec_words;
-      const int *ri = reinterpret_cast<const int *>(rec);
-      hits[i] = HitRec{ri[0], (uint32_t)ri[1], ri[2], ri[3], ri[4], rec[5], rec + kHitHeader};
-    }
-    std::sort(hits.begin(), hits.end(), [](const HitRec &a, const HitRec &b2) {
-      return a.frame != b2.frame ? a.frame < b2.frame : a.key < b2.key;
-    });
     return true;
   }
   set_err("survivor / hit queues kept overflowing");
