@@ -304,10 +304,11 @@ int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflic
 // read pixels from global memory in "virtual" tiles of 32 x 16 windows.  Among the shapes that fit,
 // the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
 // pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
+int g_latency_tile_windows = 256;
 int g_max_span = -1;  // -1: by mode (throughput plan: up to 4 warps' buffers; latency plan: the whole block's)
 
 // best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
-int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3) {
+int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2_LIST_CAP) {
   double best_cost = 1e30;
   int best_windows = 0;
   tile_bytes = std::min(tile_bytes, 65536);  // one TMA box (<= 256 x 256)
@@ -321,7 +322,7 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3) {
       const int bh_max = std::min(256, tile_bytes / bw);
       if (bh_max < L.win) continue;
       int th = (bh_max - L.win) / L.step + 1;
-      th = std::min(th, K2_LIST_CAP / tw);
+      th = std::min(th, std::max(1, max_windows / tw));
       th = std::min(th, std::max(1, L.ny));
       const int bh = (th - 1) * L.step + L.win;
       if ((long long)L.win * bw + L.win >= 65536) continue;  // u16 tile offsets
@@ -348,6 +349,7 @@ void plan_level(LevelInfo &L, bool latency) {
   if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
   if (const char *e = getenv("JDA_B200_TUNE_PITCH")) g_tune_pitch = atoi(e);
   if (const char *e = getenv("JDA_B200_MAX_SPAN")) g_max_span = std::max(1, atoi(e));
+  if (const char *e = getenv("JDA_B200_LATENCY_TILE")) g_latency_tile_windows = std::max(64, std::min(K2_LIST_CAP, atoi(e)));
   // Two plans.  Throughput (many frames in flight): coarse levels pool at most 4 warps' buffers, what is
   // left reads global memory in 512-window virtual tiles -- measured fastest on 128+ frame batches.
   // Latency (a handful of frames): the coarsest levels pool the whole block's buffers and go straight to
@@ -356,7 +358,8 @@ void plan_level(LevelInfo &L, bool latency) {
   const int max_span = g_max_span > 0 ? g_max_span : (latency ? K2_WARPS : 4);
   L.use_smem = 0;
   L.span = 1;
-  if (plan_tile(L, K2_TILE_BYTES) > 0) {
+  // latency plan: 256-window tiles on the fine levels -- twice the tiles, shorter dependent chains per warp
+  if (plan_tile(L, K2_TILE_BYTES, 3, latency ? g_latency_tile_windows : K2_LIST_CAP) > 0) {
     L.use_smem = 1;  // fits a single warp's buffer: every warp works
   } else {
     // pool buffers: more bytes per tile (more windows) against fewer independent groups.  With every
