@@ -847,22 +847,30 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
       __syncwarp();
       // global regression, c/jda.c:403-411
       const float *wt = P.w + (size_t)t * P.K * kLeaves * D;
-      for (int i0 = 0; i0 < D; i0 += 128) {
-        // up to four coordinates per lane in one sweep over the K rows (independent chains, each k ascending)
-        float acc[4];
-        bool on[4];
+      for (int i0 = 0; i0 < D; i0 += 64) {
+        // two coordinates per lane per sweep over the K rows (independent chains, each k ascending).  The 16
+        // row loads of a batch are issued together before their adds: the gather is a string of L2 reads.
+        const bool on0 = i0 + lane < D, on1 = i0 + 32 + lane < D;
+        float acc0 = on0 ? shape[i0 + lane] : 0.f, acc1 = on1 ? shape[i0 + 32 + lane] : 0.f;
+        for (int k0 = 0; k0 < P.K; k0 += 16) {
+          float v0[16], v1[16];
 #pragma unroll
-        for (int h = 0; h < 4; h++) { on[h] = i0 + 32 * h + lane < D; acc[h] = on[h] ? shape[i0 + 32 * h + lane] : 0.f; }
-#pragma unroll 16
-        for (int k = 0; k < P.K; k++) {
-          const float *row = wt + (size_t)(k * kLeaves + leafs[k]) * D + i0 + lane;
+          for (int u = 0; u < 16; u++) {
+            const int k = min(k0 + u, P.K - 1);
+            const float *row = wt + (size_t)(k * kLeaves + leafs[k]) * D + i0 + lane;
+            v0[u] = on0 ? __ldg(row) : 0.f;
+            v1[u] = on1 ? __ldg(row + 32) : 0.f;
+          }
 #pragma unroll
-          for (int h = 0; h < 4; h++)
-            if (on[h]) acc[h] = __fadd_rn(acc[h], __ldg(row + 32 * h));
+          for (int u = 0; u < 16; u++) {
+            if (k0 + u < P.K) {
+              acc0 = __fadd_rn(acc0, v0[u]);
+              acc1 = __fadd_rn(acc1, v1[u]);
+            }
+          }
         }
-#pragma unroll
-        for (int h = 0; h < 4; h++)
-          if (on[h]) shape[i0 + 32 * h + lane] = acc[h];
+        if (on0) shape[i0 + lane] = acc0;
+        if (on1) shape[i0 + 32 + lane] = acc1;
       }
       __syncwarp();
     }
