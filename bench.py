@@ -366,6 +366,35 @@ def main():
         m, ac, _ = timed(mine, 5, 2)
         ex["cfg5_mining_stage1_noise"] = {"windows_per_s": 5 * B * WINDOWS_PER_FRAME / (m * 1e-3),
                                           "survivors_per_step": ac["raw_hits"] / 5}
+        del t
+        # config 4: 2845 FDDB-shaped frames (longest side 450) of mixed sizes through jdaB200DetectMixed -- host
+        # frames (pinned) in, H2D inside the timed region, one launch per kernel over a common canvas; next to it
+        # the older scheme (one batch call per distinct shape)
+        shapes = [synth.fddb_shape(s) for s in range(48)]
+        poolm = [synth.facemix_frame(11000 + i, *shapes[i]) for i in range(48)]
+        nfr = 2845
+        pin = torch.empty(sum(poolm[i % 48].size for i in range(nfr)), dtype=torch.uint8).pin_memory().numpy()
+        fr, o = [], 0
+        for i in range(nfr):
+            f = poolm[i % 48]
+            v = pin[o:o + f.size].reshape(f.shape)
+            v[:] = f
+            fr.append(v)
+            o += f.size
+        wins4 = sum(api.count_windows(f.shape[1], f.shape[0], 1.25, 24, -1) for f in fr)
+
+        def run4(group):
+            t0 = time.perf_counter()
+            c.detect_many(fr, group=group, th=0.0, unpack=False) if not group else c.detect_many(fr, group=True, th=0.0)
+            return time.perf_counter() - t0
+        run4(False)
+        dt = min(run4(False) for _ in range(3))
+        st4 = dict(c.last_stats)
+        dtg = run4(True)
+        ex["cfg4_fddb_2845_mixed_sizes"] = {"windows": wins4, "windows_per_s": wins4 / dt, "ms": dt * 1e3,
+                                            "k2_ms": st4["ms_scan"], "k3_ms": st4["ms_cascade"],
+                                            "h2d_bytes": int(o), "per_shape_batches_windows_per_s": wins4 / dtg,
+                                            "distinct_shapes": len({f.shape for f in fr})}
         out["other_configs"] = ex
     if rank == 0:
         print(json.dumps(out), flush=True)

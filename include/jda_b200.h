@@ -111,6 +111,23 @@ typedef struct {
 JDA_API int jdaB200DetectBatch(void *cascador, const unsigned char *frames, const jdaB200Batch *batch,
                                jdaResult *results, jdaB200Stats *stats /* may be NULL */);
 
+/* Frames of different sizes in one call (reference: test.cpp:73-235 feeds FDDB images of all shapes one by one to
+ * the detector; here they share one launch).  Host memory only.  pitch = 0 means pitch == width. */
+typedef struct {
+  const unsigned char *data;
+  int width, height;
+  int pitch;
+} jdaB200Frame;
+
+/* results[f] is what jdaDetect(frames[f].data, width, height, scale, ., min_size, max_size, th) returns for that
+ * frame alone (max_size <= 0: each frame's own min(width, height), c/jda.c:459-460).  The frames are laid out in
+ * slots of a common canvas in HBM and scanned by one launch per kernel; every frame keeps exactly the windows
+ * c/jda.c:320-339 enumerates for its own size.  t_limit / flags as in jdaB200Batch (JDA_B200_DEVICE_INPUT is
+ * ignored).  Returns 0, or a negative value on failure (results then have n = -1). */
+JDA_API int jdaB200DetectMixed(void *cascador, const jdaB200Frame *frames, int n_frames, float scale, int min_size,
+                               int max_size, float th, int t_limit, int flags, jdaResult *results,
+                               jdaB200Stats *stats /* may be NULL */);
+
 /* jdaResultRelease for a whole array of results (one call instead of n). */
 JDA_API void jdaB200ResultsRelease(jdaResult *results, int n);
 

@@ -45,6 +45,10 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Frame(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_int)]
+
+
 _RESULT_DTYPE = np.dtype([("n", np.int32), ("landmark_n", np.int32), ("bboxes", np.uint64), ("shapes", np.uint64),
                           ("scores", np.uint64)])
 
@@ -76,6 +80,9 @@ def lib():
     L.jdaResultRelease.argtypes = [_Result]
     L.jdaB200DetectBatch.restype = ci
     L.jdaB200DetectBatch.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(_Result), C.POINTER(Stats)]
+    L.jdaB200DetectMixed.restype = ci
+    L.jdaB200DetectMixed.argtypes = [vp, C.POINTER(Frame), ci, cf, ci, ci, cf, ci, ci, C.POINTER(_Result),
+                                     C.POINTER(Stats)]
     L.jdaB200ResultsRelease.restype = None
     L.jdaB200ResultsRelease.argtypes = [C.POINTER(_Result), ci]
     L.jdaB200SetDevice.restype = ci
@@ -109,7 +116,8 @@ EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSeri
            "jdaCascadorRelease", "jdaDetect", "jdaResultRelease", "jdaB200DetectBatch",
            "jdaB200SetDevice", "jdaB200SetStream", "jdaB200ModelDims", "jdaB200LastError",
            "jdaB200DeviceCount", "jdaB200Levels", "jdaB200CountWindows", "jdaB200Nms",
-           "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan", "jdaB200ResultsRelease"]
+           "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan", "jdaB200ResultsRelease",
+           "jdaB200DetectMixed"]
 
 
 def last_error():
@@ -231,6 +239,10 @@ class Cascador:
         self.last_stats = st.as_dict()
         if rc != 0:
             raise RuntimeError("jdaB200DetectBatch failed: " + last_error())
+        return self._unpack_results(res, n, unpack)
+
+    def _unpack_results(self, res, n, unpack=True):
+        L = lib()
         lm = self.L
         # vectorised view of the jdaResult array (c/jda.h:18-24: two ints + three pointers)
         view = np.frombuffer(res, dtype=_RESULT_DTYPE, count=n)
@@ -249,9 +261,31 @@ class Cascador:
         L.jdaB200ResultsRelease(res, n)
         return out
 
-    def detect_many(self, frames, **kw):
-        """frames of mixed sizes (e.g. FDDB-shaped): grouped by shape, one
-        batch call per group, results returned in input order."""
+    def detect_mixed(self, frames, scale=1.25, min_size=24, max_size=-1, th=0.0, t_limit=0, flags=0, unpack=True):
+        """jdaB200DetectMixed: host frames of different sizes (list of 2-D u8 arrays, row stride = any), one
+        launch per kernel over a common canvas.  Result i is what jdaDetect returns for frames[i] alone."""
+        n = len(frames)
+        keep = [f if (f.dtype == np.uint8 and f.ndim == 2 and f.strides[1] == 1 and f.strides[0] >= f.shape[1])
+                else np.ascontiguousarray(f, np.uint8) for f in frames]
+        arr = (Frame * max(n, 1))()
+        for i, f in enumerate(keep):
+            assert f.ndim == 2
+            h, w = f.shape
+            arr[i] = Frame(f.__array_interface__["data"][0], w, h, f.strides[0] if h > 1 else w)
+        res = (_Result * max(n, 1))()
+        st = Stats()
+        rc = lib().jdaB200DetectMixed(self._h, arr, n, scale, min_size, max_size, th, t_limit, flags, res, C.byref(st))
+        self.last_stats = st.as_dict()
+        if rc != 0:
+            raise RuntimeError("jdaB200DetectMixed failed: " + last_error())
+        return self._unpack_results(res, n, unpack)
+
+    def detect_many(self, frames, group=False, **kw):
+        """frames of mixed sizes (e.g. FDDB-shaped), results in input order.
+        Default: one jdaB200DetectMixed call (all frames share each kernel launch).  group=True: the older
+        scheme -- frames grouped by shape, one jdaB200DetectBatch call per group."""
+        if not group:
+            return self.detect_mixed(frames, **kw)
         groups = {}
         for i, f in enumerate(frames):
             groups.setdefault(tuple(f.shape), []).append(i)

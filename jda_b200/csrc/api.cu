@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -117,6 +118,7 @@ struct Context {
   Stage0Norm *d_norms = nullptr;
   // scratch
   DevBuf<uint8_t> d_frames, d_hq, d_trace_leaf;
+  DevBuf<int2> d_dims;             // mixed-size batches: (width, height) per frame
   DevBuf<uint4> d_surv;
   DevBuf<float> d_shape0;
   DevBuf<uint8_t> d_surv_leaves;
@@ -245,7 +247,7 @@ void ctx_free(Context *c) {
     cudaFreeHost(c->h_counters);
     cudaFreeHost(c->h_eager);
     cudaFreeHost(c->h_stage);
-    c->d_tables.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
+    c->d_tables.release(); c->d_dims.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
     c->d_surv.release(); c->d_shape0.release(); c->d_surv_leaves.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
@@ -447,6 +449,7 @@ struct TraceOut {
 struct Run {
   Context *c;
   const jdaB200Batch *b;
+  const jdaB200Frame *mixed;  // non-NULL: frames of different sizes, each in its own slot of a b->width x b->height canvas
   const TraceOut *trace;
   bool timing, tracing;
   bool latency_plan;   // <= kLatencyFrames frames: latency tile plan, no cohort-staged stage 0
@@ -487,6 +490,27 @@ bool stage_frames(Run &R, const unsigned char *frames) {
   }
   CU_OK(cudaEventRecord(c->ev_copy[kMaxChunks], R.s));
   CU_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
+  if (R.mixed) {
+    // every frame goes to the top-left corner of its canvas slot; what lies outside a frame inside its slot is
+    // never sampled (windows are enumerated from the frame's own width and height), so it is left as it is
+    if (!c->d_dims.ensure(b.n_frames)) return false;
+    std::vector<int2> dims(b.n_frames);
+    for (int f = 0; f < b.n_frames; f++) dims[f] = make_int2(std::max(R.mixed[f].width, 0), std::max(R.mixed[f].height, 0));
+    CU_OK(cudaMemcpyAsync(c->d_dims.p, dims.data(), dims.size() * sizeof(int2), cudaMemcpyHostToDevice, c->copy_stream));
+    for (int ch = 0; ch < R.nchunks; ch++) {
+      const int f0 = (int)((long long)b.n_frames * ch / R.nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / R.nchunks);
+      for (int f = f0; f < f1; f++) {
+        const jdaB200Frame &fr = R.mixed[f];
+        if (fr.width <= 0 || fr.height <= 0) continue;
+        CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * R.fstride, R.pitch, fr.data, fr.pitch > 0 ? fr.pitch : fr.width,
+                                fr.width, fr.height, cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
+    }
+    if (!R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[0], 0));
+    R.d_frames = c->d_frames.p;
+    return true;
+  }
   bool staged = false;
   if (R.nchunks == 1 && R.fstride * b.n_frames <= c->h_stage_cap) {
     cudaPointerAttributes pa;
@@ -570,6 +594,7 @@ bool launch_scan(Run &R) {
   for (int i = 0; i < P.n_sched; i++) P.sched[i] = c->sched[i];
   P.surv = c->d_surv.p; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)c->surv_cap;
   P.surv_leaves = c->d_surv_leaves.p; P.leaf_pad = R.leaf_pad;
+  P.frame_dims = R.mixed ? c->d_dims.p : nullptr;
   // TMA needs 16-byte aligned base and strides
   const bool tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)R.d_frames % 16 == 0) &&
                       R.pitch % 16 == 0 && R.fstride % 16 == 0;
@@ -740,24 +765,30 @@ bool collect(Run &R, std::vector<HitRec> &hits, bool &overflow) {
 // Runs the device path for one batch; on success `hits` holds the raw hit records sorted into scan
 // order (frame, level, y, x).  The record floats stay alive in the context until the next call.
 bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, std::vector<HitRec> &hits,
-                const TraceOut *trace, bool timing) {
+                const TraceOut *trace, bool timing, const jdaB200Frame *mixed = nullptr) {
   hits.clear();
   jdaB200Stats &st = c->last;
   memset(&st, 0, sizeof st);
   if (b.n_frames <= 0) return true;
-  if (b.width <= 0 || b.height <= 0 || b.pitch < b.width || b.frame_stride < (size_t)b.pitch * (b.height - 1) + b.width) {
+  if (b.width <= 0 || b.height <= 0 ||
+      (!mixed && (b.pitch < b.width || b.frame_stride < (size_t)b.pitch * (b.height - 1) + b.width))) {
     set_err("bad batch descriptor");
     return false;
   }
   if (!ctx_init(c)) return false;
   Run R;
   memset(&R, 0, sizeof R);
-  R.c = c; R.b = &b; R.trace = trace; R.timing = timing; R.tracing = trace != nullptr;
+  R.c = c; R.b = &b; R.mixed = mixed; R.trace = trace; R.timing = timing; R.tracing = trace != nullptr;
   R.latency_plan = b.n_frames <= kLatencyFrames;
   if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, R.latency_plan)) return false;
   const Geometry &g = c->geo;
   st.n_levels = g.n_levels;
   st.windows = g.windows_per_frame * b.n_frames;
+  if (mixed) {  // each frame has the windows c/jda.c:320-339 enumerates for its own size
+    st.windows = 0;
+    for (int f = 0; f < b.n_frames; f++)
+      st.windows += count_windows(mixed[f].width, mixed[f].height, b.scale, b.min_size, b.max_size);
+  }
   if (g.n_levels == 0) return true;
   const HostModel &m = c->m;
   R.s = c->stream();
@@ -768,6 +799,10 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   R.leaf_pad = (m.K + 15) & ~15;
   R.total_windows = st.windows;
   R.use_scan = m.stage0_lut_ok && !(b.flags & JDA_B200_NO_STAGE0_SCAN);
+  if (mixed && (!R.use_scan || m.any_scaled)) {
+    set_err("internal: a mixed-size batch needs the stage-0 scan path");
+    return false;
+  }
   // a handful of frames: the cohort-staged k3_stage0 is a ~0.1 ms serial pipeline for a few survivors, so the
   // cascade kernel redoes stage 0 itself (same bits); batches take the staged path
   R.staged0 = R.use_scan && !R.latency_plan;
@@ -852,6 +887,22 @@ jdaResult finish_frame(const HostModel &m, const HitRec *h, int n, bool raw) {
   return r;
 }
 
+// hits (sorted by frame, scan order inside a frame) -> one jdaResult per frame; returns the detection count
+long long finish_frames(Context *c, const std::vector<HitRec> &hits, int n_frames, bool raw, jdaResult *results,
+                        const int *frame_map /* local -> caller's index, or NULL */) {
+  size_t i = 0;
+  long long dets = 0;
+  for (int f = 0; f < n_frames; f++) {
+    size_t j = i;
+    while (j < hits.size() && hits[j].frame == f) j++;
+    jdaResult &r = results[frame_map ? frame_map[f] : f];
+    r = finish_frame(c->m, hits.data() + i, (int)(j - i), raw);
+    dets += r.n > 0 ? r.n : 0;
+    i = j;
+  }
+  return dets;
+}
+
 int detect_batch(Context *c, const unsigned char *frames, const jdaB200Batch &b, jdaResult *results,
                  jdaB200Stats *stats) {
   std::lock_guard<std::mutex> lock(c->mu);
@@ -865,19 +916,99 @@ int detect_batch(Context *c, const unsigned char *frames, const jdaB200Batch &b,
     return -1;
   }
   const auto t0 = std::chrono::steady_clock::now();
-  const bool raw = (b.flags & JDA_B200_RAW_HITS) != 0;
-  size_t i = 0;
-  long long dets = 0;
-  for (int f = 0; f < b.n_frames; f++) {
-    size_t j = i;
-    while (j < hits.size() && hits[j].frame == f) j++;
-    results[f] = finish_frame(c->m, hits.data() + i, (int)(j - i), raw);
-    dets += results[f].n > 0 ? results[f].n : 0;
-    i = j;
-  }
-  c->last.detections = dets;
+  c->last.detections = finish_frames(c, hits, b.n_frames, (b.flags & JDA_B200_RAW_HITS) != 0, results, nullptr);
   c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (stats) *stats = c->last;
+  if (prev_dev >= 0) cudaSetDevice(prev_dev);
+  return 0;
+}
+
+void add_stats(jdaB200Stats &a, const jdaB200Stats &b) {
+  a.windows += b.windows; a.stage0_survivors += b.stage0_survivors; a.raw_hits += b.raw_hits; a.detections += b.detections;
+  a.ms_h2d += b.ms_h2d; a.ms_resize += b.ms_resize; a.ms_scan += b.ms_scan; a.ms_cascade += b.ms_cascade;
+  a.ms_d2h += b.ms_d2h; a.ms_host += b.ms_host;
+  a.scan_launches += b.scan_launches; a.cascade_launches += b.cascade_launches; a.resize_launches += b.resize_launches;
+  a.n_levels = std::max(a.n_levels, b.n_levels); a.levels_smem = std::max(a.levels_smem, b.levels_smem);
+}
+
+// Frames of different sizes in one call (FDDB-shaped frames).  Result f is what jdaDetect
+// would return for frame f alone.  One launch over a common canvas when stage 0 runs from the scan kernel; models
+// that need the generic per-window kernel for stage 0, or sample the h / q planes, go shape group by shape group.
+int detect_mixed(Context *c, const jdaB200Frame *frames, int n, float scale, int min_size, int max_size, float th,
+                 int t_limit, int flags, jdaResult *results, jdaB200Stats *stats) {
+  std::lock_guard<std::mutex> lock(c->mu);
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  const bool raw = (flags & JDA_B200_RAW_HITS) != 0;
+  flags &= ~JDA_B200_DEVICE_INPUT;
+  auto fail = [&]() {
+    for (int f = 0; f < n; f++) results[f] = empty_result(c->m.L, -1);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return -1;
+  };
+  for (int f = 0; f < n; f++) {
+    results[f] = empty_result(c->m.L, 0);
+    if (!frames[f].data && frames[f].width > 0 && frames[f].height > 0) { set_err("frame %d has no data", f); return fail(); }
+    if (frames[f].pitch > 0 && frames[f].pitch < frames[f].width) { set_err("frame %d: pitch < width", f); return fail(); }
+  }
+  jdaB200Batch b;
+  memset(&b, 0, sizeof b);
+  b.scale = scale; b.min_size = min_size; b.max_size = max_size; b.th = th; b.t_limit = t_limit; b.flags = flags;
+  std::vector<HitRec> hits;
+  const bool canvas = c->m.stage0_lut_ok && !c->m.any_scaled && !(flags & JDA_B200_NO_STAGE0_SCAN);
+  if (canvas) {
+    int wc = 0, hc = 0, top = 0;
+    for (int f = 0; f < n; f++) {
+      wc = std::max(wc, frames[f].width); hc = std::max(hc, frames[f].height);
+      top = std::max(top, std::min(frames[f].width, frames[f].height));
+    }
+    if (wc <= 0 || hc <= 0) {  // nothing but empty frames
+      for (int f = 0; f < n; f++) results[f] = finish_frame(c->m, nullptr, 0, raw);
+      memset(&c->last, 0, sizeof c->last);
+      if (stats) *stats = c->last;
+      if (prev_dev >= 0) cudaSetDevice(prev_dev);
+      return 0;
+    }
+    // the canvas visits the window sizes some frame has; every frame then keeps those that fit inside itself
+    b.n_frames = n; b.width = wc; b.height = hc;
+    const int user_max = max_size;
+    b.max_size = user_max > 0 ? std::min(user_max, top) : top;
+    if (!run_device(c, nullptr, b, hits, nullptr, stats != nullptr, frames)) return fail();
+    const auto t0 = std::chrono::steady_clock::now();
+    c->last.detections = finish_frames(c, hits, n, raw, results, nullptr);
+    c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = c->last;
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return 0;
+  }
+  std::map<std::pair<int, int>, std::vector<int>> groups;
+  for (int f = 0; f < n; f++) {
+    if (frames[f].width <= 0 || frames[f].height <= 0) results[f] = finish_frame(c->m, nullptr, 0, raw);
+    else groups[{frames[f].width, frames[f].height}].push_back(f);
+  }
+  jdaB200Stats total;
+  memset(&total, 0, sizeof total);
+  std::vector<unsigned char> pack;
+  for (const auto &g : groups) {
+    const int w = g.first.first, h = g.first.second, cnt = (int)g.second.size();
+    pack.resize((size_t)w * h * cnt);
+    for (int i = 0; i < cnt; i++) {
+      const jdaB200Frame &fr = frames[g.second[i]];
+      for (int y = 0; y < h; y++)
+        memcpy(pack.data() + ((size_t)i * h + y) * w, fr.data + (size_t)y * (fr.pitch > 0 ? fr.pitch : w), w);
+    }
+    b.n_frames = cnt; b.width = w; b.height = h; b.pitch = w; b.frame_stride = (size_t)w * h;
+    if (!run_device(c, pack.data(), b, hits, nullptr, stats != nullptr)) {
+      for (int f = 0; f < n; f++) jdaResultRelease(results[f]);
+      return fail();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    c->last.detections = finish_frames(c, hits, cnt, raw, results, g.second.data());
+    c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    add_stats(total, c->last);
+  }
+  c->last = total;
+  if (stats) *stats = total;
   if (prev_dev >= 0) cudaSetDevice(prev_dev);
   return 0;
 }
@@ -943,6 +1074,17 @@ int jdaB200DetectBatch(void *cascador, const unsigned char *frames, const jdaB20
     return -2;
   }
   return detect_batch(c, frames, *batch, results, stats);
+}
+
+int jdaB200DetectMixed(void *cascador, const jdaB200Frame *frames, int n_frames, float scale, int min_size,
+                       int max_size, float th, int t_limit, int flags, jdaResult *results, jdaB200Stats *stats) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || n_frames < 0 || (n_frames > 0 && (!frames || !results))) {
+    set_err("null argument");
+    return -2;
+  }
+  if (n_frames == 0) return 0;
+  return detect_mixed(c, frames, n_frames, scale, min_size, max_size, th, t_limit, flags, results, stats);
 }
 
 void jdaB200ResultsRelease(jdaResult *results, int n) {

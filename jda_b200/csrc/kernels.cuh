@@ -67,6 +67,8 @@ struct ScanParams {
   size_t frame_stride;
   int pitch, W, H, n_frames;
   int frame_base;                // index of frames[0] inside the caller's batch (chunked launches)
+  const int2 *frame_dims;        // mixed-size batches: (width, height) of every frame of the caller's batch inside its
+                                 // W x H canvas slot; NULL = every frame is W x H
   int n_levels, K, table_bytes;
   const uint8_t *tables;         // n_levels x table_bytes (padded to 128)
   const Stage0Norm *norms;       // kMaxNorm entries
@@ -457,6 +459,23 @@ __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int car
   __syncwarp();
 }
 
+// Windows of tile (x0w, y0w) that exist in `frame`: the level's own nx x ny grid, or -- in a mixed-size batch,
+// where tiles are enumerated over the canvas -- the grid of the frame's own width and height (c/jda.c:320-339 run
+// on that frame alone).  false = no window of this tile exists in the frame.
+__device__ __forceinline__ bool tile_extent(const ScanParams &P, const LevelInfo &lv, int frame, int x0w, int y0w,
+                                            int &cw, int &ch) {
+  int nx = lv.nx, ny = lv.ny;
+  if (P.frame_dims) {
+    const int2 d = __ldg(P.frame_dims + frame + P.frame_base);
+    if (d.x < lv.win || d.y < lv.win) return false;
+    nx = (d.x - lv.win) / lv.step + 1;
+    ny = (d.y - lv.win) / lv.step + 1;
+  }
+  cw = min(1 << lv.tw_log2, nx - x0w);
+  ch = min(lv.th, ny - y0w);
+  return cw > 0 && ch > 0;
+}
+
 template <bool SMEM, int NW, bool TRACE>
 __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &lv, int li, uint8_t *smem,
                                           uint32_t norm_off, uint32_t tile_off, float *lscore,
@@ -592,7 +611,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
       bool loaded = false;
       for (;;) {
         asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthr) : "memory");  // group is done with the previous tile
-        int frame = 0, x0w = 0, y0w = 0;
+        int frame = 0, x0w = 0, y0w = 0, cw = 0, ch = 0;
         if (gl == 0) {
           if (lane == 0) {
             if (loaded && P.use_tma) lead->parity ^= 1u;
@@ -601,8 +620,10 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
             if (it2 < total && P.use_tma) {
               const int f = it2 / tiles_per_frame, r = it2 - f * tiles_per_frame;
               const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
-              mbar_expect_tx(gbar, (uint32_t)(lv.box_w * lv.box_h));
-              tma_load_3d(gtile_s, &P.maps[li], (tx * tw * lv.step) & ~15, ty * lv.th * lv.step, f, gbar);
+              if (tile_extent(P, lv, f, tx * tw, ty * lv.th, cw, ch)) {
+                mbar_expect_tx(gbar, (uint32_t)(lv.box_w * lv.box_h));
+                tma_load_3d(gtile_s, &P.maps[li], (tx * tw * lv.step) & ~15, ty * lv.th * lv.step, f, gbar);
+              }
             }
           }
           __syncwarp();
@@ -610,14 +631,14 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
         asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthr) : "memory");  // tile id published
         const unsigned item = s_item[grp];
         if (item >= total) break;
-        loaded = true;
         frame = item / tiles_per_frame;
         {
           const int r = item - frame * tiles_per_frame;
           const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
           x0w = tx * tw; y0w = ty * lv.th;
         }
-        const int cw = min(tw, lv.nx - x0w), ch = min(lv.th, lv.ny - y0w);
+        loaded = tile_extent(P, lv, frame, x0w, y0w, cw, ch);  // same answer in every thread of the group
+        if (!loaded) continue;                                  // mixed-size batch: the tile lies outside this frame
         const int px0 = (x0w * lv.step) & ~15, py0 = y0w * lv.step;
         const int xs = x0w * lv.step - px0;
         if (P.use_tma) {
@@ -648,7 +669,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
       const int r = item - frame * tiles_per_frame;
       const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
       const int x0w = tx * tw, y0w = ty * lv.th;
-      const int cw = min(tw, lv.nx - x0w), ch = min(lv.th, lv.ny - y0w);
+      int cw, ch;
+      if (!tile_extent(P, lv, frame, x0w, y0w, cw, ch)) continue;  // mixed-size batch: outside this frame
       if (lv.use_smem) {
         // box origin: x rounded down to 16 bytes (TMA alignment), the windows sit `xs` bytes into the tile
         const int px0 = (x0w * lv.step) & ~15, py0 = y0w * lv.step;

@@ -239,12 +239,65 @@ def test_device_resident_frames(casc):
 
 
 def test_mixed_size_frames_fddb_shaped(casc, oracle, oracle_shipped):
-    """BASELINE config 4 shape: FDDB-like frame sizes, grouped by shape behind detect_many"""
+    """BASELINE config 4 shape: FDDB-like frame sizes through jdaB200DetectMixed -- every frame in its slot of a
+    common canvas, one launch per kernel, each frame keeps the windows of its own size (c/jda.c:320-339)"""
     frames = [synth.facemix_frame(300 + i, *synth.fddb_shape(i % 5)) for i in range(12)]
+    want = [oracle.detect(oracle_shipped, f, th=-0.5) for f in frames]
     got = casc.detect_many(frames, th=-0.5)
     assert casc.last_stats["windows"] == sum(api.count_windows(f.shape[1], f.shape[0]) for f in frames)
-    for f, g in zip(frames, got):
-        _same(g, oracle.detect(oracle_shipped, f, th=-0.5))
+    assert casc.last_stats["scan_launches"] == 1
+    assert sum(len(w[1]) for w in want) >= 3
+    for g, w in zip(got, want):
+        _same(g, w)
+    grouped = casc.detect_many(frames, group=True, th=-0.5)   # the per-shape batches give the same answer
+    assert casc.last_stats["scan_launches"] == len({f.shape for f in frames})
+    for g, w in zip(grouped, want):
+        _same(g, w)
+
+
+def test_mixed_sizes_edge_cases(casc, oracle, oracle_shipped):
+    """canvas corner cases: portrait + landscape in one call (canvas larger than either), frames too small for any
+    window, a strided view as input, an explicit max_size, tiny and empty batches, the latency plan (<= 4 frames)"""
+    big = synth.facemix_frame(41, 300, 200)
+    wide = np.zeros((120, 400), np.uint8); wide[:] = synth.facemix_frame(42, 400, 120)
+    tall = synth.facemix_frame(43, 130, 380)
+    tiny = synth.noise_frame(3, 23, 40)           # < 24 px wide: no windows (c/jda.c:320-322)
+    exact = synth.blur_frame(5, 24, 24)           # exactly one window
+    view = synth.facemix_frame(44, 512, 256)[16:200, 40:300]   # non-contiguous rows (pitch 512, width 260)
+    frames = [big, wide, tall, tiny, exact, view]
+    for kw in (dict(th=-0.5), dict(th=-0.5, max_size=100), dict(scale=1.2, min_size=40, th=-1.0)):
+        got = casc.detect_mixed(frames, **kw)
+        st = casc.last_stats
+        assert st["windows"] == sum(api.count_windows(f.shape[1], f.shape[0], kw.get("scale", 1.25),
+                                                       kw.get("min_size", 24), kw.get("max_size", -1)) for f in frames)
+        for f, g in zip(frames, got):
+            _same(g, oracle.detect(oracle_shipped, np.ascontiguousarray(f), **kw))
+    assert casc.detect_mixed([]) == []
+    got = casc.detect_mixed([tiny])
+    assert len(got) == 1 and len(got[0][1]) == 0
+    two = casc.detect_mixed([tall, big], th=-0.5)              # <= 4 frames: latency tile plan
+    _same(two[0], oracle.detect(oracle_shipped, tall, th=-0.5))
+    _same(two[1], oracle.detect(oracle_shipped, big, th=-0.5))
+    # mining flags ride along: first stage only, every survivor, window-normalised shapes
+    raw = casc.detect_mixed([wide, tall], t_limit=1, flags=api.RAW_HITS | api.NO_FINAL_TH)
+    for f, g in zip([wide, tall], raw):
+        ob, osc, osh, _ = oracle.detect_raw(oracle_shipped, f, t_limit=1, use_th=False)
+        _same(g, (ob, osc, osh))
+
+
+def test_mixed_sizes_large_batch_chunked(casc, oracle, oracle_shipped):
+    """>= 128 mixed frames: the per-frame copies are split in chunks that overlap the scans; sampled frames vs oracle,
+    and a model that cannot use the canvas path (scaled nodes) falls back to per-shape batches with the same API"""
+    shapes = [synth.fddb_shape(s) for s in range(7)]
+    frames = [synth.facemix_frame(800 + i, *[d // 2 for d in shapes[i % 7]]) for i in range(140)]
+    got = casc.detect_mixed(frames, th=-0.5)
+    assert casc.last_stats["scan_launches"] == 4
+    assert casc.last_stats["windows"] == sum(api.count_windows(f.shape[1], f.shape[0]) for f in frames)
+    for i in (0, 1, 2, 3, 4, 5, 6, 69, 139):
+        _same(got[i], oracle.detect(oracle_shipped, frames[i], th=-0.5))
+    again = casc.detect_mixed(frames[::-1], th=-0.5)
+    for a, b in zip(got, again[::-1]):
+        _same(a, b)
 
 
 def test_chunked_host_batch_equals_resident(casc, oracle, oracle_shipped):
@@ -274,26 +327,6 @@ def test_mining_mode_truncated_cascade(casc, oracle, oracle_shipped, t_limit):
     ob, osc, osh, st = oracle.detect_raw(oracle_shipped, img, t_limit=t_limit, use_th=False)
     assert len(osc) == st["stage_survivors"][t_limit - 1] > 0
     _same(got, (ob, osc, osh))
-
-
-def test_concurrent_callers_and_changing_arguments(casc, oracle, oracle_shipped):
-    """jdaDetect is re-entrant in the reference: threads share one handle; calls with different
-    sizes / pyramids interleave (the per-handle geometry cache is rebuilt as needed)."""
-    from concurrent.futures import ThreadPoolExecutor
-    jobs = [(synth.face_canvas(), dict(th=0.0)), (synth.facemix_frame(5), dict(scale=1.2, min_size=30, max_size=300, th=-1.0)),
-            (synth.facemix_frame(7, *synth.fddb_shape(7)), dict(th=0.0)), (synth.blur_frame(2, 30, 27), dict(th=-5.0)),
-            (synth.facemix_frame(3), dict(max_size=192, th=0.0))] * 3
-    want = [oracle.detect(oracle_shipped, img, **kw) for img, kw in jobs[:5]] * 3
-    with ThreadPoolExecutor(6) as ex:
-        got = list(ex.map(lambda j: casc.detect(j[0], **j[1]), jobs))
-    for g, w in zip(got, want):
-        _same(g, w)
-    c2 = api.Cascador(SHIPPED_F32, double=False)       # a second handle on the same device
-    with ThreadPoolExecutor(4) as ex:
-        got = list(ex.map(lambda a: (casc if a[0] % 2 else c2).detect(a[1][0], **a[1][1]), enumerate(jobs)))
-    for g, w in zip(got, want):
-        _same(g, w)
-    c2.close()
 
 
 def test_concurrent_callers_and_changing_arguments(casc, oracle, oracle_shipped):

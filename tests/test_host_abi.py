@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
     import ctypes
     hdr = open(os.path.join(ROOT, "include", "jda_b200.h")).read()
     declared = re.findall(r"JDA_API\s+[\w\s\*]+?\b(jda\w+)\s*\(", hdr)
-    assert len(declared) >= 19 and set(declared) == set(api.EXPORTS)
+    assert len(declared) >= 20 and set(declared) == set(api.EXPORTS)
     L = ctypes.CDLL(api.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
@@ -96,6 +96,11 @@ def test_detect_without_gpu_fails_loudly():
     c = api.Cascador(SHIPPED_F32, double=False)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         c.detect(synth.noise_frame(0, 64, 48))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        c.detect_batch(synth.make_frames("noise", 2, 64, 48))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        c.detect_mixed([synth.noise_frame(0, 64, 48), synth.noise_frame(1, 50, 70)])
+    assert c.detect_mixed([]) == []          # nothing to do: no device needed, no failure
     c.close()
 
 

@@ -2,31 +2,34 @@
 # One gpurun call's worth of verification for the current tree: GPU parity tests, smoke, the bench line,
 # the reference arm, the ncu launch list, one `--set full` capture of the three kernels (digested on the
 # box), and a short A/B of k2_scan's phase schedule.  Everything lands in gpurun_out/<tag>_*.
-#   usage (on the GPU box, from the repo root): bash tools/gpu_round.sh <tag> [skip-tests]
+#   usage (on the GPU box, from the repo root): [NCU=0] [AB=1] bash tools/gpu_round.sh <tag> [skip-tests]
 tag=${1:-round}
-out=gpurun_out
-mkdir -p $out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_gpu.txt 2>&1
+O=gpurun_out   # (tools/ab.sh uses $out itself)
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${tag}_gpu.txt 2>&1
 if [ "$2" != "skip-tests" ]; then
-  timeout 1200 python -m pytest tests -x -q -m gpu > $out/${tag}_pytest.log 2>&1
-  echo "pytest exit $?" >> $out/${tag}_pytest.log
-  tail -5 $out/${tag}_pytest.log
+  timeout 1200 python -m pytest tests -x -q -m gpu > $O/${tag}_pytest.log 2>&1
+  echo "pytest exit $?" >> $O/${tag}_pytest.log
+  tail -5 $O/${tag}_pytest.log
 fi
-timeout 300 python __graft_entry__.py smoke > $out/${tag}_smoke.log 2>&1; echo "smoke exit $?" >> $out/${tag}_smoke.log
-tail -2 $out/${tag}_smoke.log
-timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
-tail -c 1500 $out/${tag}_bench.json
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err
-cat $out/${tag}_bench_ref.json
+timeout 300 python __graft_entry__.py smoke > $O/${tag}_smoke.log 2>&1; echo "smoke exit $?" >> $O/${tag}_smoke.log
+tail -2 $O/${tag}_smoke.log
+timeout 600 python bench.py > $O/${tag}_bench.json 2> $O/${tag}_bench.err
+tail -c 1500 $O/${tag}_bench.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/${tag}_bench_ref.json 2>> $O/${tag}_bench.err
+cat $O/${tag}_bench_ref.json
+if [ "${NCU:-1}" = "1" ]; then
 # launch list of the same command (per-launch times are cold-cache and serialised: only the shares count)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $out/${tag}_ncu_bench.log 2>&1
-grep -c k2_scan $out/${tag}_launches.csv
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${tag}_launches.csv \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $O/${tag}_ncu_bench.log 2>&1
+grep -c k2_scan $O/${tag}_launches.csv
 # full capture: one launch of each kernel at 256 resident frames
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2_scan|k3_' -s 6 -c 3 -f -o /tmp/${tag}_full \
-  python bench.py --batch 256 --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $out/${tag}_ncu_full.log 2>&1
-python tools/ncu_digest.py /tmp/${tag}_full.ncu-rep $out/${tag}_full >> $out/${tag}_ncu_full.log 2>&1
-ls -la /tmp/${tag}_full.ncu-rep >> $out/${tag}_ncu_full.log 2>&1
+  python bench.py --batch 256 --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $O/${tag}_ncu_full.log 2>&1
+python tools/ncu_digest.py /tmp/${tag}_full.ncu-rep $O/${tag}_full >> $O/${tag}_ncu_full.log 2>&1
+ls -la /tmp/${tag}_full.ncu-rep >> $O/${tag}_ncu_full.log 2>&1
+fi
+if [ "${AB:-0}" = "1" ]; then
 # phase-schedule A/B (resident frames, 6 steps each)
 source tools/ab.sh
 {
@@ -35,5 +38,6 @@ run sched_fine_early JDA_B200_SCHED=2,4,6,8,12,16,20,24,32,40,48,64,80,96,128,16
 run sched_fine_mid JDA_B200_SCHED=4,8,12,16,20,24,28,32,40,48,56,64,80,96,112,128,160,192,224,256,320,384,448
 run sched_coarse JDA_B200_SCHED=8,16,32,64,128,256
 run nw2 JDA_B200_NW=2
-} > $out/${tag}_ab.txt 2>&1
-cat $out/${tag}_ab.txt
+} > $O/${tag}_ab.txt 2>&1
+cat $O/${tag}_ab.txt
+fi
