@@ -206,6 +206,7 @@ bool ctx_init(Context *c) {
   CU_OK(cudaFuncSetAttribute(k2_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  CU_OK(cudaFuncSetAttribute(k2_scan<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
@@ -217,7 +218,7 @@ bool ctx_init(Context *c) {
   // tuning knobs (not behaviour): windows per lane and the phase schedule of k2_scan
   if (const char *e = getenv("JDA_B200_NW")) {
     int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) c->nw = v;
+    if (v == 1 || v == 2 || v == 4 || v == 8) c->nw = v;
   }
   if (const char *e = getenv("JDA_B200_STRAGGLERS")) c->stragglers = atoi(e) ? 1 : 0;
   c->sched.clear();
@@ -644,10 +645,12 @@ bool launch_scan(Run &R) {
     if (R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[ch], 0));
     if (R.tracing) {
       if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
-      else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+      else if (c->nw >= 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
       else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
     } else if (c->nw == 1) {
       k2_scan<1, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+    } else if (c->nw == 8) {
+      k2_scan<8, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
     } else if (c->nw == 4) {
       k2_scan<4, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
     } else {

@@ -30,14 +30,11 @@ python tools/ncu_digest.py /tmp/${tag}_full.ncu-rep $O/${tag}_full >> $O/${tag}_
 ls -la /tmp/${tag}_full.ncu-rep >> $O/${tag}_ncu_full.log 2>&1
 fi
 if [ "${AB:-0}" = "1" ]; then
-# phase-schedule A/B (resident frames, 6 steps each)
+# A/B of scan-kernel knobs (resident frames, 6 steps each)
 source tools/ab.sh
 {
 run default
-run sched_fine_early JDA_B200_SCHED=2,4,6,8,12,16,20,24,32,40,48,64,80,96,128,160,192,256,320,384,448
-run sched_fine_mid JDA_B200_SCHED=4,8,12,16,20,24,28,32,40,48,56,64,80,96,112,128,160,192,224,256,320,384,448
-run sched_coarse JDA_B200_SCHED=8,16,32,64,128,256
-run nw2 JDA_B200_NW=2
+run nw8 JDA_B200_NW=8
 } > $O/${tag}_ab.txt 2>&1
 cat $O/${tag}_ab.txt
 fi
