@@ -393,6 +393,7 @@ def main():
         dtg = run4(True)
         ex["cfg4_fddb_2845_mixed_sizes"] = {"windows": wins4, "windows_per_s": wins4 / dt, "ms": dt * 1e3,
                                             "k2_ms": st4["ms_scan"], "k3_ms": st4["ms_cascade"],
+                                            "h2d_ms": st4["ms_h2d"], "host_nms_ms": st4["ms_host"],
                                             "h2d_bytes": int(o), "per_shape_batches_windows_per_s": wins4 / dtg,
                                             "distinct_shapes": len({f.shape for f in fr})}
         out["other_configs"] = ex

@@ -49,6 +49,9 @@ class Frame(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_int)]
 
 
+_FRAME_DTYPE = np.dtype([("data", np.uint64), ("width", np.int32), ("height", np.int32), ("pitch", np.int32),
+                         ("_pad", np.int32)])
+
 _RESULT_DTYPE = np.dtype([("n", np.int32), ("landmark_n", np.int32), ("bboxes", np.uint64), ("shapes", np.uint64),
                           ("scores", np.uint64)])
 
@@ -267,11 +270,14 @@ class Cascador:
         n = len(frames)
         keep = [f if (f.dtype == np.uint8 and f.ndim == 2 and f.strides[1] == 1 and f.strides[0] >= f.shape[1])
                 else np.ascontiguousarray(f, np.uint8) for f in frames]
-        arr = (Frame * max(n, 1))()
-        for i, f in enumerate(keep):
-            assert f.ndim == 2
-            h, w = f.shape
-            arr[i] = Frame(f.__array_interface__["data"][0], w, h, f.strides[0] if h > 1 else w)
+        # the jdaB200Frame array (pointer, width, height, pitch; 24 bytes each), filled column by column
+        tab = np.zeros(max(n, 1), _FRAME_DTYPE)
+        if n:
+            tab["data"] = [f.__array_interface__["data"][0] for f in keep]
+            tab["height"] = [f.shape[0] for f in keep]
+            tab["width"] = [f.shape[1] for f in keep]
+            tab["pitch"] = [f.strides[0] if f.shape[0] > 1 else f.shape[1] for f in keep]
+        arr = tab.ctypes.data_as(C.POINTER(Frame))
         res = (_Result * max(n, 1))()
         st = Stats()
         rc = lib().jdaB200DetectMixed(self._h, arr, n, scale, min_size, max_size, th, t_limit, flags, res, C.byref(st))

@@ -206,7 +206,7 @@ bool ctx_init(Context *c) {
   CU_OK(cudaFuncSetAttribute(k2_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-  CU_OK(cudaFuncSetAttribute(k2_scan<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  CU_OK(cudaFuncSetAttribute(k2_scan<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
@@ -218,7 +218,7 @@ bool ctx_init(Context *c) {
   // tuning knobs (not behaviour): windows per lane and the phase schedule of k2_scan
   if (const char *e = getenv("JDA_B200_NW")) {
     int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4 || v == 8) c->nw = v;
+    if (v == 1 || v == 2 || v == 4) c->nw = v;
   }
   if (const char *e = getenv("JDA_B200_STRAGGLERS")) c->stragglers = atoi(e) ? 1 : 0;
   c->sched.clear();
@@ -461,6 +461,7 @@ struct Run {
   int pitch;
   size_t fstride;
   int nchunks;         // scan launches (the host copy is split the same way)
+  int chunks_copied;   // mixed-size batches: chunks whose host -> device copies have been issued
   bool host_chunks;
   int D, rec_words, t_run, leaf_stride, leaf_pad;
   long long total_windows;
@@ -472,6 +473,23 @@ struct Run {
 // Frames to HBM.  Device input is used in place; host input goes into a 16-byte-pitched store: large batches
 // in kMaxChunks pieces on the copy stream (the scan of chunk i then overlaps the copy of chunk i+1), a small
 // pageable input repacked through pinned staging (the driver's pageable path costs more than a one-frame detect).
+// mixed-size batch: host -> canvas slots for the frames of chunk `ch` (each chunk once per call)
+bool copy_mixed_chunk(Run &R, int ch) {
+  Context *c = R.c;
+  const jdaB200Batch &b = *R.b;
+  if (ch >= R.nchunks || ch < R.chunks_copied) return true;
+  const int f0 = (int)((long long)b.n_frames * ch / R.nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / R.nchunks);
+  for (int f = f0; f < f1; f++) {
+    const jdaB200Frame &fr = R.mixed[f];
+    if (fr.width <= 0 || fr.height <= 0) continue;
+    CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * R.fstride, R.pitch, fr.data, fr.pitch > 0 ? fr.pitch : fr.width,
+                            fr.width, fr.height, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
+  R.chunks_copied = ch + 1;
+  return true;
+}
+
 bool stage_frames(Run &R, const unsigned char *frames) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;
@@ -493,21 +511,15 @@ bool stage_frames(Run &R, const unsigned char *frames) {
   CU_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
   if (R.mixed) {
     // every frame goes to the top-left corner of its canvas slot; what lies outside a frame inside its slot is
-    // never sampled (windows are enumerated from the frame's own width and height), so it is left as it is
+    // never sampled (windows are enumerated from the frame's own width and height), so it is left as it is.
+    // Only the first chunk's copies are issued here: launch_scan issues chunk i+1 right after the scan of
+    // chunk i, so the host-side cost of thousands of small copy calls hides behind the running scan too.
     if (!c->d_dims.ensure(b.n_frames)) return false;
     std::vector<int2> dims(b.n_frames);
     for (int f = 0; f < b.n_frames; f++) dims[f] = make_int2(std::max(R.mixed[f].width, 0), std::max(R.mixed[f].height, 0));
     CU_OK(cudaMemcpyAsync(c->d_dims.p, dims.data(), dims.size() * sizeof(int2), cudaMemcpyHostToDevice, c->copy_stream));
-    for (int ch = 0; ch < R.nchunks; ch++) {
-      const int f0 = (int)((long long)b.n_frames * ch / R.nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / R.nchunks);
-      for (int f = f0; f < f1; f++) {
-        const jdaB200Frame &fr = R.mixed[f];
-        if (fr.width <= 0 || fr.height <= 0) continue;
-        CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * R.fstride, R.pitch, fr.data, fr.pitch > 0 ? fr.pitch : fr.width,
-                                fr.width, fr.height, cudaMemcpyHostToDevice, c->copy_stream));
-      }
-      CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
-    }
+    R.chunks_copied = 0;
+    if (!copy_mixed_chunk(R, 0)) return false;
     if (!R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[0], 0));
     R.d_frames = c->d_frames.p;
     return true;
@@ -642,15 +654,16 @@ bool launch_scan(Run &R) {
         return false;
       }
     }
+    if (R.mixed && !copy_mixed_chunk(R, ch)) return false;  // no-op unless an earlier chunk was empty
     if (R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[ch], 0));
     if (R.tracing) {
       if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
-      else if (c->nw >= 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+      else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
       else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
     } else if (c->nw == 1) {
       k2_scan<1, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
-    } else if (c->nw == 8) {
-      k2_scan<8, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+    } else if (R.mixed) {  // per-frame window grids (always 4 windows per lane: the tuning knob is for A/B runs)
+      k2_scan<4, false, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
     } else if (c->nw == 4) {
       k2_scan<4, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
     } else {
@@ -658,6 +671,7 @@ bool launch_scan(Run &R) {
     }
     CU_OK(cudaGetLastError());
     st.scan_launches++;
+    if (R.mixed && R.host_chunks && !copy_mixed_chunk(R, ch + 1)) return false;
   }
   return true;
 }

@@ -67,8 +67,8 @@ struct ScanParams {
   size_t frame_stride;
   int pitch, W, H, n_frames;
   int frame_base;                // index of frames[0] inside the caller's batch (chunked launches)
-  const int2 *frame_dims;        // mixed-size batches: (width, height) of every frame of the caller's batch inside its
-                                 // W x H canvas slot; NULL = every frame is W x H
+  const int2 *frame_dims;        // mixed-size batches (k2_scan<.., MIXED = true>): (width, height) of every frame of
+                                 // the caller's batch inside its W x H canvas slot
   int n_levels, K, table_bytes;
   const uint8_t *tables;         // n_levels x table_bytes (padded to 128)
   const Stage0Norm *norms;       // kMaxNorm entries
@@ -462,10 +462,11 @@ __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int car
 // Windows of tile (x0w, y0w) that exist in `frame`: the level's own nx x ny grid, or -- in a mixed-size batch,
 // where tiles are enumerated over the canvas -- the grid of the frame's own width and height (c/jda.c:320-339 run
 // on that frame alone).  false = no window of this tile exists in the frame.
+template <bool MIXED>
 __device__ __forceinline__ bool tile_extent(const ScanParams &P, const LevelInfo &lv, int frame, int x0w, int y0w,
                                             int &cw, int &ch) {
   int nx = lv.nx, ny = lv.ny;
-  if (P.frame_dims) {
+  if constexpr (MIXED) {
     const int2 d = __ldg(P.frame_dims + frame + P.frame_base);
     if (d.x < lv.win || d.y < lv.win) return false;
     nx = (d.x - lv.win) / lv.step + 1;
@@ -554,7 +555,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
   __syncwarp();
 }
 
-template <int NW, bool TRACE>
+template <int NW, bool TRACE, bool MIXED = false>
 __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ int s_skip;
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
             if (it2 < total && P.use_tma) {
               const int f = it2 / tiles_per_frame, r = it2 - f * tiles_per_frame;
               const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
-              if (tile_extent(P, lv, f, tx * tw, ty * lv.th, cw, ch)) {
+              if (tile_extent<MIXED>(P, lv, f, tx * tw, ty * lv.th, cw, ch)) {
                 mbar_expect_tx(gbar, (uint32_t)(lv.box_w * lv.box_h));
                 tma_load_3d(gtile_s, &P.maps[li], (tx * tw * lv.step) & ~15, ty * lv.th * lv.step, f, gbar);
               }
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
           const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
           x0w = tx * tw; y0w = ty * lv.th;
         }
-        loaded = tile_extent(P, lv, frame, x0w, y0w, cw, ch);  // same answer in every thread of the group
+        loaded = tile_extent<MIXED>(P, lv, frame, x0w, y0w, cw, ch);  // same answer in every thread of the group
         if (!loaded) continue;                                  // mixed-size batch: the tile lies outside this frame
         const int px0 = (x0w * lv.step) & ~15, py0 = y0w * lv.step;
         const int xs = x0w * lv.step - px0;
@@ -670,7 +671,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
       const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
       const int x0w = tx * tw, y0w = ty * lv.th;
       int cw, ch;
-      if (!tile_extent(P, lv, frame, x0w, y0w, cw, ch)) continue;  // mixed-size batch: outside this frame
+      if (!tile_extent<MIXED>(P, lv, frame, x0w, y0w, cw, ch)) continue;  // mixed-size batch: outside this frame
       if (lv.use_smem) {
         // box origin: x rounded down to 16 bytes (TMA alignment), the windows sit `xs` bytes into the tile
         const int px0 = (x0w * lv.step) & ~15, py0 = y0w * lv.step;

@@ -92,7 +92,7 @@ def test_trace_generic_kernel_only(casc, oracle, oracle_shipped):
 
 
 @pytest.mark.parametrize("stragglers", ["1", "0"])
-@pytest.mark.parametrize("nw", ["1", "2", "4", "8"])
+@pytest.mark.parametrize("nw", ["1", "2", "4"])
 def test_scan_kernel_variants(oracle, oracle_shipped, nw, stragglers):
     """windows per lane (ILP width) and straggler mode on/off are scheduling choices only."""
     os.environ["JDA_B200_NW"] = nw
