@@ -299,6 +299,7 @@ double estimate_wavefronts(int win, int step, int tw, int th, int pitch) {
   return cnt ? tot / cnt : 1.0;
 }
 
+const char *kDefaultPitchExtra = "";
 int g_min_tile_windows = 64;
 int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflict model (measured: no gain, r1)
 
@@ -310,6 +311,24 @@ int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflic
 int g_latency_tile_windows = 256;
 int g_max_span = -1;  // -1: by mode (throughput plan: up to 4 warps' buffers; latency plan: the whole block's)
 
+// Extra tile pitch per window size.  The pitch decides how a tile's window rows fold onto the 32 banks, i.e. how
+// often the pixel reads of a compacted packet (windows from several rows) collide; the exact model in
+// tests/design_sims/sim_exact_banks.py ranks the candidates.  JDA_B200_PITCH_EXTRA="24:16,30:32" overrides (A/B).
+int pitch_extra(int win) {
+  static const char *env = getenv("JDA_B200_PITCH_EXTRA");
+  const char *p = env ? env : kDefaultPitchExtra;
+  while (*p) {
+    char *q;
+    const long w = strtol(p, &q, 10);
+    if (*q != ':') break;
+    const long e = strtol(q + 1, &q, 10);
+    if (w == win) return (int)(e / 16 * 16);
+    p = (*q == ',') ? q + 1 : q;
+    if (*q != ',') break;
+  }
+  return 0;
+}
+
 // best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
 int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2_LIST_CAP) {
   double best_cost = 1e30;
@@ -320,7 +339,7 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2
     // TMA wants the box to start on a 16-byte boundary in x: tiles whose x origin (tx * tw * step) is not
     // a multiple of 16 start their box at the aligned address below it and carry up to 15 spare bytes
     const int slack = ((tw * L.step) % 16 == 0) ? 0 : 15;
-    const int bw0 = (((tw - 1) * L.step + L.win + slack) + 15) & ~15;
+    const int bw0 = ((((tw - 1) * L.step + L.win + slack) + 15) & ~15) + pitch_extra(L.win);
     for (int bw = bw0; bw <= std::min(256, bw0 + (g_tune_pitch ? 80 : 0)); bw += 16) {
       const int bh_max = std::min(256, tile_bytes / bw);
       if (bh_max < L.win) continue;
