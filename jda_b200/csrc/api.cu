@@ -119,6 +119,9 @@ struct Context {
   // scratch
   DevBuf<uint8_t> d_frames, d_hq, d_trace_leaf;
   DevBuf<int2> d_dims;             // mixed-size batches: (width, height) per frame
+  DevBuf<uint8_t> d_packed;        // mixed-size batches: frames as they lie in host memory, back to back
+  DevBuf<UnpackFrame> d_unpack;
+  std::vector<UnpackFrame> h_unpack;
   DevBuf<uint4> d_surv;
   DevBuf<float> d_shape0;
   DevBuf<uint8_t> d_surv_leaves;
@@ -248,7 +251,7 @@ void ctx_free(Context *c) {
     cudaFreeHost(c->h_counters);
     cudaFreeHost(c->h_eager);
     cudaFreeHost(c->h_stage);
-    c->d_tables.release(); c->d_dims.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
+    c->d_tables.release(); c->d_dims.release(); c->d_packed.release(); c->d_unpack.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
     c->d_surv.release(); c->d_shape0.release(); c->d_surv_leaves.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
@@ -453,6 +456,12 @@ bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int ma
   return true;
 }
 
+// bytes of a host frame from its first to its last pixel (rows `pitch` apart)
+inline size_t frame_bytes(const jdaB200Frame &f) {
+  if (f.width <= 0 || f.height <= 0) return 0;
+  return (size_t)(f.pitch > 0 ? f.pitch : f.width) * (f.height - 1) + f.width;
+}
+
 struct TraceOut {
   int *n = nullptr;
   float *s = nullptr;
@@ -492,17 +501,33 @@ struct Run {
 // Frames to HBM.  Device input is used in place; host input goes into a 16-byte-pitched store: large batches
 // in kMaxChunks pieces on the copy stream (the scan of chunk i then overlaps the copy of chunk i+1), a small
 // pageable input repacked through pinned staging (the driver's pageable path costs more than a one-frame detect).
-// mixed-size batch: host -> canvas slots for the frames of chunk `ch` (each chunk once per call)
+// mixed-size batch: host -> canvas slots for the frames of chunk `ch` (each chunk once per call).  Every frame is
+// copied as one contiguous blob into the packed staging area (frames that are neighbours in host memory share a
+// copy), then k0_unpack spreads the chunk over its canvas slots; all on the copy stream.
 bool copy_mixed_chunk(Run &R, int ch) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;
   if (ch >= R.nchunks || ch < R.chunks_copied) return true;
   const int f0 = (int)((long long)b.n_frames * ch / R.nchunks), f1 = (int)((long long)b.n_frames * (ch + 1) / R.nchunks);
-  for (int f = f0; f < f1; f++) {
-    const jdaB200Frame &fr = R.mixed[f];
-    if (fr.width <= 0 || fr.height <= 0) continue;
-    CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * R.fstride, R.pitch, fr.data, fr.pitch > 0 ? fr.pitch : fr.width,
-                            fr.width, fr.height, cudaMemcpyHostToDevice, c->copy_stream));
+  const UnpackFrame *tab = c->h_unpack.data();
+  int run0 = f0;
+  for (int f = f0; f <= f1; f++) {
+    // [run0, f) is a run of frames that are contiguous in host memory (and therefore in the staging area)
+    const bool extend = f < f1 && f > run0 && tab[f].src_off == tab[f - 1].src_off + frame_bytes(R.mixed[f - 1]) &&
+                        R.mixed[f].data == R.mixed[f - 1].data + frame_bytes(R.mixed[f - 1]);
+    if (extend) continue;
+    if (f > run0) {
+      const size_t bytes = tab[f - 1].src_off + frame_bytes(R.mixed[f - 1]) - tab[run0].src_off;
+      if (bytes > 0)
+        CU_OK(cudaMemcpyAsync(c->d_packed.p + tab[run0].src_off, R.mixed[run0].data, bytes, cudaMemcpyHostToDevice,
+                              c->copy_stream));
+    }
+    run0 = f;
+  }
+  if (f1 > f0) {
+    dim3 grid((b.height + 7) / 8, f1 - f0);
+    k0_unpack<<<grid, 128, 0, c->copy_stream>>>(c->d_packed.p, c->d_unpack.p, f0, c->d_frames.p, R.fstride, R.pitch);
+    CU_OK(cudaGetLastError());
   }
   CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
   R.chunks_copied = ch + 1;
@@ -537,6 +562,20 @@ bool stage_frames(Run &R, const unsigned char *frames) {
     std::vector<int2> dims(b.n_frames);
     for (int f = 0; f < b.n_frames; f++) dims[f] = make_int2(std::max(R.mixed[f].width, 0), std::max(R.mixed[f].height, 0));
     CU_OK(cudaMemcpyAsync(c->d_dims.p, dims.data(), dims.size() * sizeof(int2), cudaMemcpyHostToDevice, c->copy_stream));
+    // staging layout: host neighbours stay neighbours (one copy per run), everything else starts 16-byte aligned
+    c->h_unpack.resize(b.n_frames);
+    size_t off = 0;
+    for (int f = 0; f < b.n_frames; f++) {
+      const jdaB200Frame &fr = R.mixed[f];
+      const bool adjacent = f > 0 && frame_bytes(R.mixed[f - 1]) > 0 && fr.data == R.mixed[f - 1].data + frame_bytes(R.mixed[f - 1]);
+      if (!adjacent) off = (off + 15) & ~(size_t)15;
+      c->h_unpack[f] = UnpackFrame{(unsigned long long)off, std::max(fr.width, 0), std::max(fr.height, 0),
+                                   fr.pitch > 0 ? fr.pitch : fr.width, 0};
+      off += frame_bytes(fr);
+    }
+    if (!c->d_packed.ensure(off + 16) || !c->d_unpack.ensure(b.n_frames)) return false;
+    CU_OK(cudaMemcpyAsync(c->d_unpack.p, c->h_unpack.data(), (size_t)b.n_frames * sizeof(UnpackFrame), cudaMemcpyHostToDevice,
+                          c->copy_stream));
     R.chunks_copied = 0;
     if (!copy_mixed_chunk(R, 0)) return false;
     if (!R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[0], 0));

@@ -205,6 +205,26 @@ __global__ void k1_resize(const uint8_t *__restrict__ frames, size_t frame_strid
   dst[o] = (uint8_t)__float2int_rz(v);
 }
 
+// ------------------------------------------------------------------------------ k0: unpack
+//
+// Mixed-size batches arrive as one contiguous blob per frame (rows of a few hundred bytes make a pitched
+// host->device copy crawl: one DMA descriptor per row); this kernel moves every frame from the packed staging
+// area into its 16-byte-pitched canvas slot.  blockIdx.y = frame (relative to f0), blockIdx.x = group of 8 rows.
+struct UnpackFrame {
+  unsigned long long src_off;  // byte offset of the frame inside the packed staging area
+  int width, height, src_pitch, pad;
+};
+
+__global__ void k0_unpack(const uint8_t *__restrict__ packed, const UnpackFrame *__restrict__ tab, int f0,
+                          uint8_t *__restrict__ frames, size_t frame_stride, int pitch) {
+  const UnpackFrame fr = tab[f0 + blockIdx.y];
+  const uint8_t *src = packed + fr.src_off;
+  uint8_t *dst = frames + (size_t)(f0 + blockIdx.y) * frame_stride;
+  const int r0 = blockIdx.x * 8, r1 = min(r0 + 8, fr.height);
+  for (int r = r0; r < r1; r++)
+    for (int x = threadIdx.x; x < fr.width; x += blockDim.x) dst[(size_t)r * pitch + x] = src[(size_t)r * fr.src_pitch + x];
+}
+
 // ------------------------------------------------------------------------------ k2: stage-0 scan
 //
 // One persistent block per SM.  The block keeps the current level's stage-0 table (K x 96 B) in
