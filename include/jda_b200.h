@@ -128,6 +128,53 @@ JDA_API int jdaB200DetectMixed(void *cascador, const jdaB200Frame *frames, int n
                                int max_size, float th, int t_limit, int flags, jdaResult *results,
                                jdaB200Stats *stats /* may be NULL */);
 
+/* ---- the reference's double-precision C++ detector ------------------------------------
+ * JoinCascador::Detect with fddb.method = 1 (src/jda/cascador.cpp:310-376, 431-477): fixed pixel step, window
+ * ladder win = int(win * scale) from fddb.minimum_size, JoinCascador::Validate per window in double precision with
+ * round()ed pixel coordinates (data.cpp:18-58), no final score threshold, multimap NMS (cascador.cpp:387-429),
+ * results in pick order.  Scope: models whose nodes are all at scale 0 and face.similarity_transform = false (the
+ * shipped model and config.json); anything else is refused with an error.  A handle created from a float-flavour
+ * file runs the exactly widened values. */
+typedef struct {
+  int n;
+  int landmark_n;
+  int *rects;     /* int[4n]: x, y, width, height (cv::Rect) */
+  double *scores; /* double[n] */
+  double *shapes; /* double[2*landmark_n*n], image pixels */
+} jdaB200ResultF64;
+
+/* the fddb.* keys of config.json that JoinCascador::Detect reads (src/jda/common.cpp:178-188) */
+typedef struct {
+  int minimum_size; /* fddb.minimum_size (model/config.json: 20) */
+  int step;         /* fddb.step         (5)                     */
+  double scale;     /* fddb.scale        (1.2)                   */
+  double overlap;   /* fddb.overlap      (0.3)                   */
+  int nms;          /* fddb.nms          (true)                  */
+  int flags;        /* 0, or JDA_B200_NO_STAGE0_SCAN: every window through the double-precision kernel */
+} jdaB200CppParams;
+
+/* n_frames equally sized host frames (8-bit gray, stride == width, frame f at frames + f*width*height).
+ * results[f] is what JoinCascador::Detect returns for frame f (release with jdaB200ResultF64Release).
+ * Returns 0, or a negative value on failure (results then have n = -1). */
+JDA_API int jdaB200JoinCascadorDetect(void *cascador, const unsigned char *frames, int n_frames, int width, int height,
+                                      const jdaB200CppParams *params, jdaB200ResultF64 *results,
+                                      jdaB200Stats *stats /* may be NULL */);
+JDA_API void jdaB200ResultF64Release(jdaB200ResultF64 *results, int n);
+
+/* per-window trace of JoinCascador::Validate (scan order, one frame): carts evaluated (its `n`) and the score at
+ * exit; every window runs through the double-precision kernel.  Returns the window count or a negative value. */
+JDA_API long long jdaB200JoinCascadorTrace(void *cascador, const unsigned char *frame, int width, int height,
+                                           const jdaB200CppParams *params, int *carts_evaluated, double *exit_score);
+
+/* Stage 0 of the double-precision detector is prefiltered by the float32 scan kernel with every cart threshold
+ * lowered by margins[k] >= |float32 running score - double running score| over all windows; survivors are then
+ * evaluated exactly in double from cart 0, so the filter never decides a result.  Writes the K margins (host
+ * only; for tests).  Returns K, 0 when this model runs without the prefilter, negative on failure. */
+JDA_API int jdaB200JoinCascadorFilterMargins(void *cascador, double *margins, int cap);
+
+/* window sizes detectMultiScale1 visits for a (w, h) frame (cascador.cpp:335,372-373); host only */
+JDA_API int jdaB200JoinCascadorLevels(int width, int height, int minimum_size, double scale, int *wins, int cap);
+
 /* jdaResultRelease for a whole array of results (one call instead of n). */
 JDA_API void jdaB200ResultsRelease(jdaResult *results, int n);
 

@@ -45,6 +45,17 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ResultF64(C.Structure):
+    _fields_ = [("n", C.c_int), ("landmark_n", C.c_int), ("rects", C.POINTER(C.c_int)),
+                ("scores", C.POINTER(C.c_double)), ("shapes", C.POINTER(C.c_double))]
+
+
+class CppParams(C.Structure):
+    """the fddb.* keys JoinCascador::Detect reads (src/jda/common.cpp:178-188); defaults = model/config.json"""
+    _fields_ = [("minimum_size", C.c_int), ("step", C.c_int), ("scale", C.c_double), ("overlap", C.c_double),
+                ("nms", C.c_int), ("flags", C.c_int)]
+
+
 class Frame(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_int)]
 
@@ -86,6 +97,17 @@ def lib():
     L.jdaB200DetectMixed.restype = ci
     L.jdaB200DetectMixed.argtypes = [vp, C.POINTER(Frame), ci, cf, ci, ci, cf, ci, ci, C.POINTER(_Result),
                                      C.POINTER(Stats)]
+    L.jdaB200JoinCascadorDetect.restype = ci
+    L.jdaB200JoinCascadorDetect.argtypes = [vp, vp, ci, ci, ci, C.POINTER(CppParams), C.POINTER(ResultF64),
+                                            C.POINTER(Stats)]
+    L.jdaB200ResultF64Release.restype = None
+    L.jdaB200ResultF64Release.argtypes = [C.POINTER(ResultF64), ci]
+    L.jdaB200JoinCascadorTrace.restype = C.c_longlong
+    L.jdaB200JoinCascadorTrace.argtypes = [vp, ub, ci, ci, C.POINTER(CppParams), C.POINTER(ci), C.POINTER(C.c_double)]
+    L.jdaB200JoinCascadorFilterMargins.restype = ci
+    L.jdaB200JoinCascadorFilterMargins.argtypes = [vp, C.POINTER(C.c_double), ci]
+    L.jdaB200JoinCascadorLevels.restype = ci
+    L.jdaB200JoinCascadorLevels.argtypes = [ci, ci, ci, C.c_double, C.POINTER(ci), ci]
     L.jdaB200ResultsRelease.restype = None
     L.jdaB200ResultsRelease.argtypes = [C.POINTER(_Result), ci]
     L.jdaB200SetDevice.restype = ci
@@ -120,7 +142,8 @@ EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSeri
            "jdaB200SetDevice", "jdaB200SetStream", "jdaB200ModelDims", "jdaB200LastError",
            "jdaB200DeviceCount", "jdaB200Levels", "jdaB200CountWindows", "jdaB200Nms",
            "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan", "jdaB200ResultsRelease",
-           "jdaB200DetectMixed"]
+           "jdaB200DetectMixed", "jdaB200JoinCascadorDetect", "jdaB200ResultF64Release",
+           "jdaB200JoinCascadorTrace", "jdaB200JoinCascadorLevels", "jdaB200JoinCascadorFilterMargins"]
 
 
 def last_error():
@@ -147,6 +170,17 @@ def describe_plan(w, h, scale=1.25, min_size=24, max_size=-1, latency=False):
     lib().jdaB200DescribePlan(w, h, scale, min_size, max_size, buf, -4096 if latency else 4096)
     keys = ["win", "step", "nx", "ny", "tw", "th", "box_w", "box_h", "smem", "windows", "span"]
     return [dict(zip(keys, map(int, ln.split()))) for ln in buf.value.decode().splitlines()]
+
+
+def levels_cpp(w, h, minimum_size=20, scale=1.2):
+    """window sizes of the C++ detector's detectMultiScale1 (cascador.cpp:335,372-373)"""
+    buf = (C.c_int * 64)()
+    n = lib().jdaB200JoinCascadorLevels(w, h, minimum_size, scale, buf, 64)
+    return list(buf[:min(n, 64)])
+
+
+def count_windows_cpp(w, h, minimum_size=20, step=5, scale=1.2):
+    return sum(((w - s) // step + 1) * ((h - s) // step + 1) for s in levels_cpp(w, h, minimum_size, scale)) if step > 0 else 0
 
 
 def nms(boxes, scores):
@@ -285,6 +319,58 @@ class Cascador:
         if rc != 0:
             raise RuntimeError("jdaB200DetectMixed failed: " + last_error())
         return self._unpack_results(res, n, unpack)
+
+    def detect_cpp(self, frames, minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True, flags=0):
+        """jdaB200JoinCascadorDetect: the reference's double-precision C++ detector (JoinCascador::Detect,
+        fddb.method = 1).  frames: one [h,w] u8 image or a batch [n,h,w].  Returns (rects[k,4] i32 = x y w h,
+        scores[k] f64, shapes[k,2L] f64 in image pixels) -- a list of those for a batch."""
+        a = np.ascontiguousarray(frames, np.uint8)
+        single = a.ndim == 2
+        if single:
+            a = a[None]
+        n, h, w = a.shape
+        prm = CppParams(minimum_size, step, scale, overlap, 1 if nms else 0, flags)
+        res = (ResultF64 * max(n, 1))()
+        st = Stats()
+        rc = lib().jdaB200JoinCascadorDetect(self._h, C.c_void_p(a.ctypes.data), n, w, h, C.byref(prm), res, C.byref(st))
+        self.last_stats = st.as_dict()
+        if rc != 0:
+            raise RuntimeError("jdaB200JoinCascadorDetect failed: " + last_error())
+        D = 2 * self.L
+        out = []
+        for i in range(n):
+            k = res[i].n
+            if k > 0:
+                out.append((np.ctypeslib.as_array(res[i].rects, shape=(k, 4)).copy(),
+                            np.ctypeslib.as_array(res[i].scores, shape=(k,)).copy(),
+                            np.ctypeslib.as_array(res[i].shapes, shape=(k, D)).copy()))
+            else:
+                out.append((np.zeros((0, 4), np.int32), np.zeros((0,), np.float64), np.zeros((0, D), np.float64)))
+        lib().jdaB200ResultF64Release(res, n)
+        return out[0] if single else out
+
+    def filter_margins_cpp(self):
+        """per-cart margins of the float32 stage-0 prefilter of the double-precision detector (None: no prefilter)"""
+        buf = np.zeros(self.K, np.float64)
+        n = lib().jdaB200JoinCascadorFilterMargins(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), self.K)
+        if n < 0:
+            raise RuntimeError("jdaB200JoinCascadorFilterMargins failed: " + last_error())
+        return buf if n > 0 else None
+
+    def trace_cpp(self, img, minimum_size=20, step=5, scale=1.2):
+        """JoinCascador::Validate per window in scan order: (carts evaluated, exit score f64)"""
+        a = np.ascontiguousarray(img, np.uint8)
+        h, w = a.shape
+        nwin = count_windows_cpp(w, h, minimum_size, step, scale)
+        tn = np.zeros(max(nwin, 1), np.int32)
+        ts = np.zeros(max(nwin, 1), np.float64)
+        prm = CppParams(minimum_size, step, scale, 0.3, 1, 0)
+        n = lib().jdaB200JoinCascadorTrace(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, C.byref(prm),
+                                           tn.ctypes.data_as(C.POINTER(C.c_int)), ts.ctypes.data_as(C.POINTER(C.c_double)))
+        if n < 0:
+            raise RuntimeError("jdaB200JoinCascadorTrace failed: " + last_error())
+        assert n == nwin, (n, nwin)
+        return tn[:nwin], ts[:nwin]
 
     def detect_many(self, frames, group=False, **kw):
         """frames of mixed sizes (e.g. FDDB-shaped), results in input order.

@@ -20,6 +20,7 @@
 #include "../../include/jda_b200.h"
 #include "host_model.hpp"
 #include "kernels.cuh"
+#include "kernels_f64.cuh"
 
 using namespace jda;
 
@@ -75,6 +76,8 @@ struct Geometry {
   int w = 0, h = 0, min_size = 0, max_size = 0;
   float scale = 0.f;
   bool latency = false;  // which tile plan (see plan_level)
+  int step64 = 0;        // double-precision detector: fixed step and double scale factor (0 = the C path's ladder)
+  double factor64 = 0.;
   int n_levels = 0;
   LevelInfo lv[kMaxLevels];
   long long windows_per_frame = 0;
@@ -137,6 +140,22 @@ struct Context {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t surv_cap = 0, hit_cap = 0;
   jdaB200Stats last;
+  // double-precision detector (JoinCascador::Detect, method 1): model kept as doubles, its own geometry and tables
+  std::string path;
+  bool path_dbl = false;
+  HostModelD md;
+  bool md_failed = false;
+  NodeRecD *d_nodes64 = nullptr;
+  double *d_leaf64 = nullptr, *d_cart64 = nullptr, *d_w64 = nullptr, *d_mean64 = nullptr;
+  Geometry geo64;
+  DevBuf<uint8_t> d_tables64;
+  Stage0Norm *d_norms64 = nullptr;
+  bool filter64_ok = false;        // stage 0 may be prefiltered by k2_scan (margins exist, <= kMaxNorm normalised carts)
+  std::vector<double> margins64;
+  DevBuf<double> d_hits64, d_trace_s64;
+  DevBuf<int> d_trace_n64;
+  size_t hit64_cap = 0;
+  std::vector<double> h_hits64;
   int nw = 4;
   int stragglers = 1;
   std::vector<short> sched;
@@ -248,6 +267,9 @@ void ctx_free(Context *c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_nodes); cudaFree(c->d_leaf); cudaFree(c->d_cart); cudaFree(c->d_w); cudaFree(c->d_mean);
     cudaFree(c->d_norms); cudaFree(c->d_counters);
+    cudaFree(c->d_nodes64); cudaFree(c->d_leaf64); cudaFree(c->d_cart64); cudaFree(c->d_w64); cudaFree(c->d_mean64);
+    cudaFree(c->d_norms64);
+    c->d_tables64.release(); c->d_hits64.release(); c->d_trace_s64.release(); c->d_trace_n64.release();
     cudaFreeHost(c->h_counters);
     cudaFreeHost(c->h_eager);
     cudaFreeHost(c->h_stage);
@@ -480,6 +502,9 @@ struct Run {
   const jdaB200Batch *b;
   const jdaB200Frame *mixed;  // non-NULL: frames of different sizes, each in its own slot of a b->width x b->height canvas
   const TraceOut *trace;
+  const Geometry *geo;        // the scan geometry of this call and its stage-0 tables
+  const uint8_t *tables;
+  const Stage0Norm *norms;
   bool timing, tracing;
   bool latency_plan;   // <= kLatencyFrames frames: latency tile plan, no cohort-staged stage 0
   bool use_scan;       // stage 0 from the LUT scan (k2_scan); false: every window through k3_cascade
@@ -651,7 +676,7 @@ bool prepare_trace(Run &R) {
 bool launch_scan(Run &R) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;
-  const Geometry &g = c->geo;
+  const Geometry &g = *R.geo;
   const HostModel &m = c->m;
   jdaB200Stats &st = c->last;
   ScanParams P;
@@ -659,7 +684,7 @@ bool launch_scan(Run &R) {
   for (int i = 0; i < g.n_levels; i++) P.lv[i] = g.lv[i];
   P.frame_stride = R.fstride; P.pitch = R.pitch; P.W = b.width; P.H = b.height;
   P.n_levels = g.n_levels; P.K = m.K; P.table_bytes = g.table_bytes;
-  P.tables = c->d_tables.p; P.norms = c->d_norms;
+  P.tables = R.tables; P.norms = R.norms;
   P.windows_per_frame = g.windows_per_frame;
   P.n_sched = (int)c->sched.size();
   for (int i = 0; i < P.n_sched; i++) P.sched[i] = c->sched[i];
@@ -740,7 +765,7 @@ bool launch_scan(Run &R) {
 bool launch_cascade(Run &R) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;
-  const Geometry &g = c->geo;
+  const Geometry &g = *R.geo;
   const HostModel &m = c->m;
   jdaB200Stats &st = c->last;
   if (R.staged0) {
@@ -857,6 +882,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   R.latency_plan = b.n_frames <= kLatencyFrames;
   if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, R.latency_plan)) return false;
   const Geometry &g = c->geo;
+  R.geo = &c->geo; R.tables = c->d_tables.p; R.norms = c->d_norms;
   st.n_levels = g.n_levels;
   st.windows = g.windows_per_frame * b.n_frames;
   if (mixed) {  // each frame has the windows c/jda.c:320-339 enumerates for its own size
@@ -921,6 +947,261 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   }
   set_err("survivor / hit queues kept overflowing");
   return false;
+}
+
+// =============================================================================== double-precision detector
+//
+// JoinCascador::Detect with fddb.method = 1 (src/jda/cascador.cpp:310-376, 431-477) on the device:
+//   frames -> HBM (stage_frames) -> k2_scan with the f64-derived stage-0 tables as a conservative prefilter
+//   (host_model_f64.hpp: stage0_filter_margins) -> k4_cascade_f64 re-evaluates every survivor exactly, in double,
+//   from cart 0 -> D2H -> scan order -> multimap NMS + relocation on the host.
+// Models / settings the prefilter cannot serve (no finished stage 0, > kMaxNorm normalised carts, unusable
+// margins, JDA_B200_NO_STAGE0_SCAN) run every window through k4_cascade_f64 (dense mode).
+
+struct Hit64 {
+  int frame;
+  uint32_t key;
+  int x, y, win, carts;
+  double score;
+  const double *shape;
+};
+
+// host half: the model as doubles + the prefilter margins (no device needed)
+bool ensure_model64_host(Context *c) {
+  if (c->md.loaded) return true;
+  if (c->md_failed) { set_err("the double-precision model could not be loaded earlier"); return false; }
+  std::string err;
+  if (!load_model_f64(c->path.c_str(), c->path_dbl, c->md, err)) {
+    c->md_failed = true;
+    set_err("double-precision detector: %s", err.c_str());
+    return false;
+  }
+  if (c->md.any_scaled) {
+    c->md.loaded = false; c->md_failed = true;
+    set_err("double-precision detector: the model has scale != 0 nodes; they sample cv::resize'd planes "
+            "(cascador.cpp:330-331), which this library does not reproduce");
+    return false;
+  }
+  const HostModelD &m = c->md;
+  c->filter64_ok = m.stage >= 1 && count_normed_stage0(m) <= kMaxNorm && stage0_filter_margins(m, c->margins64);
+  return true;
+}
+
+bool ensure_model64(Context *c) {
+  if (c->d_nodes64) return true;
+  if (!ensure_model64_host(c)) return false;
+  const HostModelD &m = c->md;
+  CU_OK(cudaMalloc(&c->d_nodes64, m.nodes.size() * sizeof(NodeRecD)));
+  CU_OK(cudaMalloc(&c->d_leaf64, m.leaf.size() * 8));
+  CU_OK(cudaMalloc(&c->d_cart64, m.cart3.size() * 8));
+  CU_OK(cudaMalloc(&c->d_w64, m.w.size() * 8));
+  CU_OK(cudaMalloc(&c->d_mean64, m.mean_shape.size() * 8));
+  CU_OK(cudaMalloc(&c->d_norms64, kMaxNorm * sizeof(Stage0Norm)));
+  CU_OK(cudaMemcpy(c->d_nodes64, m.nodes.data(), m.nodes.size() * sizeof(NodeRecD), cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(c->d_leaf64, m.leaf.data(), m.leaf.size() * 8, cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(c->d_cart64, m.cart3.data(), m.cart3.size() * 8, cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(c->d_w64, m.w.data(), m.w.size() * 8, cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(c->d_mean64, m.mean_shape.data(), m.mean_shape.size() * 8, cudaMemcpyHostToDevice));
+  CU_OK(cudaFuncSetAttribute(k4_cascade_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(K4_WARPS * (kMaxDim * 8 + ((m.K + 15) & ~15)))));
+  return true;
+}
+
+bool ensure_geometry64(Context *c, int w, int h, int minimum_size, int step, double factor, bool latency) {
+  Geometry &g = c->geo64;
+  if (g.valid && g.w == w && g.h == h && g.min_size == minimum_size && g.step64 == step && g.factor64 == factor &&
+      g.latency == latency)
+    return true;
+  g.valid = false;
+  g.w = w; g.h = h; g.min_size = minimum_size; g.max_size = 0; g.scale = 0.f; g.step64 = step; g.factor64 = factor;
+  g.latency = latency;
+  int wins[kMaxLevels + 1];
+  const int n = enumerate_levels_f64(w, h, minimum_size, factor, wins, kMaxLevels + 1);
+  if (n > kMaxLevels) { set_err("more than %d pyramid levels (scale too close to 1)", kMaxLevels); return false; }
+  g.n_levels = n;
+  g.table_bytes = (c->md.K * kCartBytes + 127) & ~127;
+  long long base = 0;
+  for (int i = 0; i < n; i++) {
+    LevelInfo &L = g.lv[i];
+    memset(&L, 0, sizeof L);
+    L.win = wins[i];
+    L.step = step;
+    if (L.win >= 2048) { set_err("windows of %d px exceed the 2047 px limit", L.win); return false; }
+    L.nx = (w - L.win) / step + 1;
+    L.ny = (h - L.win) / step + 1;
+    if (L.nx > 8191 || L.ny > 8191) { set_err("frame too large for 13-bit window indices"); return false; }
+    plan_level(L, latency);
+    L.table_off = i * g.table_bytes;
+    L.win_base = base;
+    base += (long long)L.nx * L.ny;
+  }
+  g.windows_per_frame = base;
+  if (n > 0 && c->filter64_ok) {
+    std::vector<uint8_t> tab((size_t)n * g.table_bytes, 0);
+    Stage0Norm norms[kMaxNorm];
+    memset(norms, 0, sizeof norms);
+    for (int i = 0; i < n; i++)
+      build_stage0_table_f64(c->md, c->margins64, g.lv[i].win, g.lv[i].use_smem ? g.lv[i].box_w : 0,
+                             tab.data() + (size_t)i * g.table_bytes, norms);
+    if (!c->d_tables64.ensure(tab.size())) return false;
+    CU_OK(cudaMemcpyAsync(c->d_tables64.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, c->stream()));
+    CU_OK(cudaMemcpyAsync(c->d_norms64, norms, sizeof norms, cudaMemcpyHostToDevice, c->stream()));
+    CU_OK(cudaStreamSynchronize(c->stream()));
+  }
+  g.valid = true;
+  return true;
+}
+
+// One batch of equally sized host frames through the double-precision detector; `hits` comes back in scan order.
+bool run_device64(Context *c, const unsigned char *frames, int n_frames, int width, int height,
+                  const jdaB200CppParams &prm, std::vector<Hit64> &hits, int *trace_n, double *trace_s, bool timing) {
+  hits.clear();
+  jdaB200Stats &st = c->last;
+  memset(&st, 0, sizeof st);
+  if (n_frames <= 0) return true;
+  if (width <= 0 || height <= 0) { set_err("bad frame size"); return false; }
+  if (prm.step <= 0 || prm.minimum_size <= 0) { set_err("fddb.step and fddb.minimum_size must be positive"); return false; }
+  if (!ctx_init(c) || !ensure_model64(c)) return false;
+  const HostModelD &m = c->md;
+  jdaB200Batch b;
+  memset(&b, 0, sizeof b);
+  b.n_frames = n_frames; b.width = width; b.height = height; b.pitch = width; b.frame_stride = (size_t)width * height;
+  Run R;
+  memset(&R, 0, sizeof R);
+  R.c = c; R.b = &b; R.timing = timing;
+  R.latency_plan = n_frames <= kLatencyFrames;
+  if (!ensure_geometry64(c, width, height, prm.minimum_size, prm.step, prm.scale, R.latency_plan)) return false;
+  const Geometry &g = c->geo64;
+  R.geo = &g; R.tables = c->d_tables64.p; R.norms = c->d_norms64;
+  st.n_levels = g.n_levels;
+  st.windows = g.windows_per_frame * n_frames;
+  if (g.n_levels == 0) return true;
+  const bool tracing = trace_n || trace_s;
+  R.s = c->stream();
+  R.D = m.D();
+  R.leaf_pad = (m.K + 15) & ~15;
+  R.total_windows = st.windows;
+  R.use_scan = c->filter64_ok && !(prm.flags & JDA_B200_NO_STAGE0_SCAN) && !tracing;
+  cudaStream_t s = R.s;
+  if (timing) CU_OK(cudaEventRecord(c->ev[0], s));
+  if (!stage_frames(R, frames)) return false;
+  if (timing) CU_OK(cudaEventRecord(c->ev[1], s));
+  if (tracing) {
+    if (!c->d_trace_n64.ensure(R.total_windows) || !c->d_trace_s64.ensure(R.total_windows)) return false;
+    CU_OK(cudaMemsetAsync(c->d_trace_n64.p, 0, R.total_windows * 4, s));
+    CU_OK(cudaMemsetAsync(c->d_trace_s64.p, 0, R.total_windows * 8, s));
+  }
+  if (c->surv_cap == 0) c->surv_cap = 1 << 16;
+  c->surv_cap = std::max(c->surv_cap, (size_t)n_frames * 1024);
+  if (c->hit64_cap == 0) c->hit64_cap = 1 << 14;
+  c->hit64_cap = std::max(c->hit64_cap, (size_t)n_frames * 512);
+  const int rec = kHit64Header + R.D;
+  for (int attempt = 0; attempt < 4; attempt++) {
+    if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits64.ensure(c->hit64_cap * rec)) return false;
+    if (R.use_scan && !c->d_surv_leaves.ensure(c->surv_cap * R.leaf_pad)) return false;
+    CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
+    if (timing) CU_OK(cudaEventRecord(c->ev[2], s));
+    if (R.use_scan && !launch_scan(R)) return false;
+    if (!R.use_scan && R.host_chunks)  // dense mode reads every frame: wait for the whole copy
+      CU_OK(cudaStreamWaitEvent(s, c->ev_copy[R.nchunks - 1], 0));
+    if (timing) CU_OK(cudaEventRecord(c->ev[3], s));
+    Cascade64Params Q;
+    memset(&Q, 0, sizeof Q);
+    Q.frames = R.d_frames; Q.frame_stride = R.fstride; Q.pitch = R.pitch;
+    Q.nodes = c->d_nodes64; Q.leaf = c->d_leaf64; Q.cart3 = c->d_cart64; Q.w = c->d_w64; Q.mean_shape = c->d_mean64;
+    Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.stage = m.stage; Q.cart_last = m.cart;
+    Q.n_levels = g.n_levels;
+    for (int i = 0; i < g.n_levels; i++) {
+      Q.lv_win[i] = g.lv[i].win; Q.lv_step[i] = g.lv[i].step; Q.lv_nx[i] = g.lv[i].nx; Q.lv_ny[i] = g.lv[i].ny;
+      Q.lv_base[i] = g.lv[i].win_base;
+    }
+    Q.windows_per_frame = g.windows_per_frame;
+    Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
+    Q.dense = R.use_scan ? 0 : 1; Q.dense_total = R.total_windows;
+    Q.hits = c->d_hits64.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit64_cap;
+    Q.rec_doubles = rec;
+    Q.work_counter = c->d_counters + kCntWork;
+    Q.trace_n = tracing ? c->d_trace_n64.p : nullptr;
+    Q.trace_s = tracing ? c->d_trace_s64.p : nullptr;
+    k4_cascade_f64<<<c->sm_count * 8, K4_WARPS * 32, K4_WARPS * (kMaxDim * 8 + ((m.K + 15) & ~15)), s>>>(Q);
+    CU_OK(cudaGetLastError());
+    st.cascade_launches++;
+    if (timing) CU_OK(cudaEventRecord(c->ev[4], s));
+    CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaStreamSynchronize(s));
+    const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
+    if ((R.use_scan && ns > c->surv_cap) || nh > c->hit64_cap) {
+      if (ns > c->surv_cap) c->surv_cap = ns + ns / 4;
+      if (nh > c->hit64_cap) c->hit64_cap = nh + nh / 4;
+      continue;
+    }
+    st.stage0_survivors = R.use_scan ? (long long)ns : 0;
+    st.raw_hits = (long long)nh;
+    c->h_hits64.resize(std::max(nh, (size_t)1) * rec);
+    if (nh) CU_OK(cudaMemcpyAsync(c->h_hits64.data(), c->d_hits64.p, nh * rec * 8, cudaMemcpyDeviceToHost, s));
+    if (trace_n) CU_OK(cudaMemcpyAsync(trace_n, c->d_trace_n64.p, R.total_windows * 4, cudaMemcpyDeviceToHost, s));
+    if (trace_s) CU_OK(cudaMemcpyAsync(trace_s, c->d_trace_s64.p, R.total_windows * 8, cudaMemcpyDeviceToHost, s));
+    if (timing) CU_OK(cudaEventRecord(c->ev[5], s));
+    CU_OK(cudaStreamSynchronize(s));
+    hits.resize(nh);
+    for (size_t i = 0; i < nh; i++) {
+      const double *r = c->h_hits64.data() + i * rec;
+      const int *ri = reinterpret_cast<const int *>(r);
+      hits[i] = Hit64{ri[0], (uint32_t)ri[1], ri[2], ri[3], ri[4], ri[5], r[3], r + kHit64Header};
+    }
+    std::sort(hits.begin(), hits.end(), [](const Hit64 &a, const Hit64 &b2) {
+      return a.frame != b2.frame ? a.frame < b2.frame : a.key < b2.key;
+    });
+    if (timing) {
+      cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[R.host_chunks ? R.nchunks - 1 : 0]);
+      cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
+      cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);
+      cudaEventElapsedTime(&st.ms_d2h, c->ev[4], c->ev[5]);
+    }
+    return true;
+  }
+  set_err("survivor / hit queues kept overflowing");
+  return false;
+}
+
+jdaB200ResultF64 empty_result64(int L, int n) {
+  jdaB200ResultF64 r;
+  r.n = n; r.landmark_n = L; r.rects = nullptr; r.scores = nullptr; r.shapes = nullptr;
+  return r;
+}
+
+// cascador.cpp:445-474: nms (or every hit), then shape = rect.xy + shape * rect.wh, output in pick order
+jdaB200ResultF64 finish_frame64(const HostModelD &m, const Hit64 *h, int n, const jdaB200CppParams &prm) {
+  const int D = m.D();
+  std::vector<int> rects(4 * (size_t)n);
+  std::vector<double> sc(n);
+  for (int i = 0; i < n; i++) {
+    rects[4 * i] = h[i].x; rects[4 * i + 1] = h[i].y; rects[4 * i + 2] = h[i].win; rects[4 * i + 3] = h[i].win;
+    sc[i] = h[i].score;
+  }
+  std::vector<int> picked;
+  if (prm.nms) picked = nms_f64(n, rects.data(), sc.data(), prm.overlap);
+  else { picked.resize(n); for (int i = 0; i < n; i++) picked[i] = i; }
+  const int k = (int)picked.size();
+  jdaB200ResultF64 r = empty_result64(m.L, 0);
+  r.rects = (int *)malloc(sizeof(int) * 4 * (k > 0 ? k : 1));
+  r.scores = (double *)malloc(sizeof(double) * (k > 0 ? k : 1));
+  r.shapes = (double *)malloc(sizeof(double) * D * (k > 0 ? k : 1));
+  if (!r.rects || !r.scores || !r.shapes) {
+    free(r.rects); free(r.scores); free(r.shapes);
+    return empty_result64(m.L, -1);
+  }
+  for (int i = 0; i < k; i++) {
+    const Hit64 &hi = h[picked[i]];
+    r.rects[4 * i] = hi.x; r.rects[4 * i + 1] = hi.y; r.rects[4 * i + 2] = hi.win; r.rects[4 * i + 3] = hi.win;
+    r.scores[i] = hi.score;
+    for (int j = 0; j < m.L; j++) {
+      r.shapes[(size_t)i * D + 2 * j] = hi.x + hi.shape[2 * j] * hi.win;
+      r.shapes[(size_t)i * D + 2 * j + 1] = hi.y + hi.shape[2 * j + 1] * hi.win;
+    }
+  }
+  r.n = k;
+  return r;
 }
 
 jdaResult empty_result(int L, int n) {
@@ -1098,6 +1379,8 @@ void *create(const char *path, bool dbl) {
     return nullptr;
   }
   memset(&c->last, 0, sizeof c->last);
+  c->path = path;
+  c->path_dbl = dbl;
   return c;
 }
 
@@ -1160,6 +1443,76 @@ int jdaB200DetectMixed(void *cascador, const jdaB200Frame *frames, int n_frames,
   }
   if (n_frames == 0) return 0;
   return detect_mixed(c, frames, n_frames, scale, min_size, max_size, th, t_limit, flags, results, stats);
+}
+
+int jdaB200JoinCascadorDetect(void *cascador, const unsigned char *frames, int n_frames, int width, int height,
+                              const jdaB200CppParams *params, jdaB200ResultF64 *results, jdaB200Stats *stats) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !params || n_frames < 0 || (n_frames > 0 && (!frames || !results))) {
+    set_err("null argument");
+    return -2;
+  }
+  if (n_frames == 0) return 0;
+  std::lock_guard<std::mutex> lock(c->mu);
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  std::vector<Hit64> hits;
+  bool ok = !(params->nms && !(params->overlap < 1.));  // a box would not suppress itself: endless loop in the reference
+  if (!ok) set_err("fddb.overlap must be < 1 when nms is on");
+  ok = ok && run_device64(c, frames, n_frames, width, height, *params, hits, nullptr, nullptr, stats != nullptr);
+  if (!ok) {
+    for (int f = 0; f < n_frames; f++) results[f] = empty_result64(c->md.L ? c->md.L : c->m.L, -1);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return -1;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  size_t i = 0;
+  long long dets = 0;
+  for (int f = 0; f < n_frames; f++) {
+    size_t j = i;
+    while (j < hits.size() && hits[j].frame == f) j++;
+    results[f] = finish_frame64(c->md, hits.data() + i, (int)(j - i), *params);
+    dets += results[f].n > 0 ? results[f].n : 0;
+    i = j;
+  }
+  c->last.detections = dets;
+  c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = c->last;
+  if (prev_dev >= 0) cudaSetDevice(prev_dev);
+  return 0;
+}
+
+void jdaB200ResultF64Release(jdaB200ResultF64 *results, int n) {
+  if (!results) return;
+  for (int i = 0; i < n; i++) {
+    free(results[i].rects); free(results[i].scores); free(results[i].shapes);
+    results[i].rects = nullptr; results[i].scores = nullptr; results[i].shapes = nullptr; results[i].n = 0;
+  }
+}
+
+long long jdaB200JoinCascadorTrace(void *cascador, const unsigned char *frame, int width, int height,
+                                   const jdaB200CppParams *params, int *carts_evaluated, double *exit_score) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !frame || !params || (!carts_evaluated && !exit_score)) return -2;
+  std::lock_guard<std::mutex> lock(c->mu);
+  std::vector<Hit64> hits;
+  // pass both pointers: run_device64 traces when either is set
+  if (!run_device64(c, frame, 1, width, height, *params, hits, carts_evaluated, exit_score, false)) return -1;
+  return c->last.windows;
+}
+
+int jdaB200JoinCascadorFilterMargins(void *cascador, double *margins, int cap) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c) return -2;
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (!ensure_model64_host(c)) return -1;
+  if (!c->filter64_ok) return 0;
+  for (int k = 0; k < c->md.K && k < cap && margins; k++) margins[k] = c->margins64[k];
+  return c->md.K;
+}
+
+int jdaB200JoinCascadorLevels(int width, int height, int minimum_size, double scale, int *wins, int cap) {
+  return enumerate_levels_f64(width, height, minimum_size, scale, wins, cap);
 }
 
 void jdaB200ResultsRelease(jdaResult *results, int n) {

@@ -202,3 +202,94 @@ class Oracle:
                                ts.ctypes.data_as(C.POINTER(C.c_float)), lp, w0, w1)
         assert n == nwin, (n, nwin)
         return tn[:nwin], ts[:nwin], lv
+
+
+ORACLE_CPP_SO = os.path.join(HERE, "libjda_oracle_cpp.so")
+
+
+class OracleCpp:
+    """Restatement of the reference's double-precision C++ detector (JoinCascador::Detect, fddb.method = 1),
+    oracle/jda_oracle_cpp.c.  PARITY UNPINNED: the C++ detector cannot be built in this image."""
+
+    # model/config.json "fddb": minimum_size 20, step 5, scale 1.2, overlap 0.3, nms true
+    DEFAULTS = dict(minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True)
+
+    def __init__(self, path=ORACLE_CPP_SO):
+        if not os.path.exists(path):
+            build()
+        L = self.lib = C.CDLL(path)
+        L.jcpp_load.restype = C.c_void_p
+        L.jcpp_load.argtypes = [C.c_char_p, C.c_int]
+        L.jcpp_free.argtypes = [C.c_void_p]
+        L.jcpp_free.restype = None
+        L.jcpp_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.jcpp_dims.restype = None
+        L.jcpp_levels.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.c_int]
+        L.jcpp_count_windows.restype = C.c_longlong
+        L.jcpp_count_windows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.jcpp_nms.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_int)]
+        L.jcpp_detect.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                  C.c_double, C.c_int, C.POINTER(C.POINTER(C.c_int)),
+                                  C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double)),
+                                  C.POINTER(C.c_longlong)]
+        L.jcpp_release.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.jcpp_release.restype = None
+        L.jcpp_trace.restype = C.c_longlong
+        L.jcpp_trace.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.POINTER(C.c_int), C.POINTER(C.c_double)]
+
+    def load(self, path, double=True):
+        return self.lib.jcpp_load(os.fsencode(path), 1 if double else 0)
+
+    def release(self, h):
+        self.lib.jcpp_free(h)
+
+    def dims(self, h):
+        d = (C.c_int * 7)()
+        self.lib.jcpp_dims(h, d)
+        return dict(zip(("T", "K", "L", "depth", "stage", "cart", "any_scaled"), d))
+
+    def levels(self, w, h, minimum_size=20, scale=1.2):
+        buf = (C.c_int * 256)()
+        n = self.lib.jcpp_levels(w, h, minimum_size, scale, buf, 256)
+        return list(buf[:min(n, 256)])
+
+    def count_windows(self, w, h, minimum_size=20, step=5, scale=1.2):
+        return int(self.lib.jcpp_count_windows(w, h, minimum_size, step, scale))
+
+    def nms(self, rects, scores, overlap=0.3):
+        rects = np.ascontiguousarray(rects, np.int32)
+        scores = np.ascontiguousarray(scores, np.float64)
+        picked = np.zeros(max(len(scores), 1), np.int32)
+        n = self.lib.jcpp_nms(len(scores), rects.ctypes.data_as(C.POINTER(C.c_int)),
+                              scores.ctypes.data_as(C.POINTER(C.c_double)), overlap,
+                              picked.ctypes.data_as(C.POINTER(C.c_int)))
+        return picked[:max(n, 0)].copy()
+
+    def detect(self, h, img, minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True):
+        """(rects[n,4] i32 = x y w h, scores[n] f64, shapes[n,2L] f64 in image pixels, carts evaluated)"""
+        a, p, w, hh = _img(img)
+        r, s, sh = C.POINTER(C.c_int)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+        carts = C.c_longlong(0)
+        n = self.lib.jcpp_detect(h, p, w, hh, minimum_size, step, scale, overlap, 1 if nms else 0,
+                                 C.byref(r), C.byref(s), C.byref(sh), C.byref(carts))
+        if n < 0:
+            raise RuntimeError("jcpp_detect refused the model or the arguments")
+        D = 2 * self.dims(h)["L"]
+        if n > 0:
+            out = (np.ctypeslib.as_array(r, shape=(n, 4)).copy(), np.ctypeslib.as_array(s, shape=(n,)).copy(),
+                   np.ctypeslib.as_array(sh, shape=(n, D)).copy())
+        else:
+            out = (np.zeros((0, 4), np.int32), np.zeros((0,), np.float64), np.zeros((0, D), np.float64))
+        self.lib.jcpp_release(r, s, sh)
+        return out + (int(carts.value),)
+
+    def trace(self, h, img, minimum_size=20, step=5, scale=1.2):
+        a, p, w, hh = _img(img)
+        nwin = self.count_windows(w, hh, minimum_size, step, scale)
+        tn = np.zeros(max(nwin, 1), np.int32)
+        ts = np.zeros(max(nwin, 1), np.float64)
+        n = self.lib.jcpp_trace(h, p, w, hh, minimum_size, step, scale, tn.ctypes.data_as(C.POINTER(C.c_int)),
+                                ts.ctypes.data_as(C.POINTER(C.c_double)))
+        assert n == nwin, (n, nwin)
+        return tn[:nwin], ts[:nwin]

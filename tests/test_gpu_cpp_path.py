@@ -1,0 +1,158 @@
+"""CUDA path of the reference's double-precision C++ detector (jdaB200JoinCascadorDetect: JoinCascador::Detect with
+fddb.method = 1) against its CPU restatement oracle/jda_oracle_cpp.c, through the C ABI.
+
+Bar: bit-exact.  Rects are integers; scores and landmarks are the same double operations in the same order, so
+they are compared as raw 64-bit patterns.  The oracle itself is PARITY UNPINNED (see its header): these tests show
+the kernels compute what the restatement computes, not that the restatement is the reference.
+"""
+import numpy as np
+import pytest
+
+from jda_b200 import api, synth
+from tests.conftest import SHIPPED_F32
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def _same(got, want):
+    (r1, s1, p1), (r2, s2, p2) = got[:3], want[:3]
+    assert r1.shape == r2.shape, (r1.shape, r2.shape)
+    np.testing.assert_array_equal(r1, r2)
+    np.testing.assert_array_equal(_bits(s1), _bits(s2))
+    np.testing.assert_array_equal(_bits(p1), _bits(p2))
+
+
+@pytest.fixture(scope="module")
+def ocpp():
+    from oracle import pyoracle
+    return pyoracle.OracleCpp()
+
+
+@pytest.fixture(scope="module")
+def ocpp_shipped(ocpp):
+    h = ocpp.load(SHIPPED_F32, double=False)
+    yield h
+    ocpp.release(h)
+
+
+@pytest.fixture(scope="module")
+def casc():
+    c = api.Cascador(SHIPPED_F32, double=False)
+    yield c
+    c.close()
+
+
+def test_known_answer_config_json_settings(casc, ocpp, ocpp_shipped):
+    img = synth.face_canvas()
+    got = casc.detect_cpp(img)
+    assert got[0].tolist() == [[400, 290, 112, 112], [55, 40, 230, 230]]
+    _same(got, ocpp.detect(ocpp_shipped, img))
+    st = casc.last_stats
+    assert st["windows"] == 140215 and st["scan_launches"] == 1 and st["raw_hits"] == 365
+    assert st["stage0_survivors"] >= 365                      # the prefilter passes a superset of the true survivors
+
+
+@pytest.mark.parametrize("frame", ["faces", "noise", "blur", "facemix", "odd"])
+def test_raw_hits_and_nms_match_oracle(casc, ocpp, ocpp_shipped, frame):
+    img = {"faces": synth.face_canvas, "noise": lambda: synth.noise_frame(4), "blur": lambda: synth.blur_frame(2),
+           "facemix": lambda: synth.facemix_frame(11), "odd": lambda: synth.facemix_frame(12, 333, 251)}[frame]()
+    for kw in (dict(nms=False), dict(), dict(minimum_size=30, step=3, scale=1.3, overlap=0.5)):
+        _same(casc.detect_cpp(img, **kw), ocpp.detect(ocpp_shipped, img, **kw))
+
+
+def test_per_window_trace_double_kernel(casc, ocpp, ocpp_shipped):
+    """every window through k4_cascade_f64: carts evaluated (Validate's n) and the exit score, bit for bit"""
+    for img in (synth.facemix_frame(21, 200, 150), synth.face_canvas()):
+        tn, ts = casc.trace_cpp(img)
+        on, os_ = ocpp.trace(ocpp_shipped, img)
+        np.testing.assert_array_equal(tn, on)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+
+
+def test_prefilter_equals_dense_double_evaluation(casc, ocpp, ocpp_shipped):
+    """the float32 scan is only a filter: with it (default) and without it (every window in double) the answers
+    are the same bits"""
+    frames = synth.make_frames("facemix", 5, 320, 240, seed0=40)
+    a = casc.detect_cpp(frames, nms=False)
+    sa = dict(casc.last_stats)
+    b = casc.detect_cpp(frames, nms=False, flags=api.NO_STAGE0_SCAN)
+    sb = dict(casc.last_stats)
+    assert sa["scan_launches"] == 1 and sb["scan_launches"] == 0 and sa["raw_hits"] == sb["raw_hits"]
+    for x, y, f in zip(a, b, frames):
+        _same(x, y)
+        _same(x, ocpp.detect(ocpp_shipped, f, nms=False))
+
+
+def test_batch_and_chunked_batch(casc, ocpp, ocpp_shipped):
+    frames = synth.make_frames("facemix", 130, 160, 120, seed0=70)      # >= 128 frames: chunked copies + scans
+    frames[5, 6:114, 20:131] = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "face_111x108.npy"))
+    got = casc.detect_cpp(frames)
+    assert casc.last_stats["scan_launches"] == 4
+    assert casc.last_stats["windows"] == 130 * api.count_windows_cpp(160, 120)
+    assert sum(len(g[1]) for g in got) >= 1
+    for i in (0, 5, 64, 129):
+        _same(got[i], ocpp.detect(ocpp_shipped, frames[i]))
+
+
+SYN = [dict(seed=1, mode="passall"), dict(seed=2, mode="reject"),
+       dict(seed=5, mode="reject", norm_every=7)]      # > 32 normalised carts: no prefilter, dense double evaluation
+
+
+@pytest.mark.parametrize("cfg", SYN, ids=lambda c: "seed%d" % c["seed"])
+def test_synthetic_double_models(ocpp, tmp_path, cfg):
+    path = synth.write_model(str(tmp_path / "syn.model"), **cfg)
+    c = api.Cascador(path, double=True)
+    h = ocpp.load(path, True)
+    assert (c.filter_margins_cpp() is None) == (cfg.get("norm_every") == 7)
+    for img in (synth.blur_frame(9, 96, 80), synth.noise_frame(5, 70, 61)):
+        for kw in (dict(nms=False), dict(minimum_size=24, step=4, scale=1.25, overlap=0.3)):
+            _same(c.detect_cpp(img, **kw), ocpp.detect(h, img, **kw))
+        tn, ts = c.trace_cpp(img)
+        on, os_ = ocpp.trace(h, img)
+        np.testing.assert_array_equal(tn, on)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+    c.close(); ocpp.release(h)
+
+
+def test_training_snapshot_header(ocpp, tmp_path):
+    """a model whose header stops inside a stage (cascador.cpp:199-209): full stages, then carts 0..cart, no regression"""
+    q = synth.write_model(str(tmp_path / "rej.model"), seed=2, mode="reject")
+    for stage, cart in ((2, 17), (0, 40), (0, -1), (4, 539)):
+        b = bytearray(open(q, "rb").read())
+        b[20:24] = stage.to_bytes(4, "little"); b[24:28] = cart.to_bytes(4, "little", signed=True)
+        p = tmp_path / ("snap_%d_%d.model" % (stage, cart))
+        p.write_bytes(bytes(b))
+        c = api.Cascador(str(p), double=True)
+        h = ocpp.load(str(p), True)
+        img = synth.blur_frame(13, 90, 77)
+        _same(c.detect_cpp(img, nms=False), ocpp.detect(h, img, nms=False))
+        tn, ts = c.trace_cpp(img)
+        on, os_ = ocpp.trace(h, img)
+        np.testing.assert_array_equal(tn, on)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+        c.close(); ocpp.release(h)
+
+
+def test_refusals_and_edges(casc, ocpp, ocpp_shipped, tmp_path):
+    p = synth.write_model(str(tmp_path / "scaled.model"), seed=3, scales=(0, 1, 2), coord_max=0.45)
+    c = api.Cascador(p, double=True)
+    with pytest.raises(RuntimeError, match="scale != 0"):
+        c.detect_cpp(synth.noise_frame(0, 64, 48))
+    c.close()
+    with pytest.raises(RuntimeError):
+        casc.detect_cpp(synth.noise_frame(0, 64, 48), step=0)
+    with pytest.raises(RuntimeError):
+        casc.detect_cpp(synth.noise_frame(0, 64, 48), overlap=1.0)
+    tiny = synth.noise_frame(1, 19, 40)                      # smaller than fddb.minimum_size: no window
+    got = casc.detect_cpp(tiny)
+    assert len(got[1]) == 0 and casc.last_stats["windows"] == 0
+    one = synth.blur_frame(2, 20, 20)                        # exactly one window
+    _same(casc.detect_cpp(one, nms=False), ocpp.detect(ocpp_shipped, one, nms=False))
+    assert len(casc.detect_cpp(synth.noise_frame(1), scale=1.0)[1]) == 0     # endless loop in the reference: no detections
+    # the float C path on the same handle is untouched by the double path's state
+    img = synth.face_canvas()
+    assert casc.detect(img)[0].tolist() == [[396, 308, 110], [63, 21, 213]]

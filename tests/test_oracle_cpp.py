@@ -1,0 +1,185 @@
+"""The restatement of the reference's double-precision C++ detector (oracle/jda_oracle_cpp.c: JoinCascador::Detect,
+fddb.method = 1) and the host logic of its CUDA counterpart.  No GPU needed.
+
+PARITY UNPINNED: the C++ detector cannot be built in this image (OpenCV C++ headers, jsmnpp config), the reference
+ships no golden vectors for it.  What is checked here: the restatement against independent restatements of its
+pieces (multimap NMS, window ladder), its known answers as regression pins, and the error bound that lets the
+float32 scan kernel prefilter stage 0 of the double path.
+"""
+import numpy as np
+import pytest
+
+from jda_b200 import api, synth
+from tests.conftest import SHIPPED_F32
+
+
+@pytest.fixture(scope="module")
+def ocpp():
+    from oracle import pyoracle
+    return pyoracle.OracleCpp()
+
+
+@pytest.fixture(scope="module")
+def ocpp_shipped(ocpp):
+    h = ocpp.load(SHIPPED_F32, double=False)
+    assert h
+    yield h
+    ocpp.release(h)
+
+
+def test_header_and_scope(ocpp, ocpp_shipped, tmp_path):
+    d = ocpp.dims(ocpp_shipped)
+    assert (d["T"], d["K"], d["L"], d["depth"]) == (5, 540, 27, 4)
+    assert (d["stage"], d["cart"]) == (5, -1)      # the float writer's T+1 quirk (c/jda.c:662) normalised
+    assert d["any_scaled"] == 0                    # the shipped model never samples the h / q planes
+    # a double-flavour file with the same values loads to the same model -> same answers
+    wide = synth.widen_f32_model(SHIPPED_F32, str(tmp_path / "wide.model"))
+    h2 = ocpp.load(wide, double=True)
+    img = synth.facemix_frame(3, 200, 150)
+    a, b = ocpp.detect(ocpp_shipped, img, nms=False), ocpp.detect(h2, img, nms=False)
+    for x, y in zip(a[:3], b[:3]):
+        np.testing.assert_array_equal(x, y)
+    ocpp.release(h2)
+    # models with scale != 0 nodes need cv::resize'd planes: refused
+    p = synth.write_model(str(tmp_path / "scaled.model"), seed=3, scales=(0, 1, 2), coord_max=0.45)
+    h3 = ocpp.load(p, True)
+    with pytest.raises(RuntimeError):
+        ocpp.detect(h3, img)
+    ocpp.release(h3)
+
+
+@pytest.mark.parametrize("w,h,mn,sc", [(640, 480, 20, 1.2), (450, 333, 20, 1.2), (1920, 1080, 20, 1.2),
+                                       (640, 480, 30, 1.3), (19, 100, 20, 1.2), (20, 20, 20, 1.2),
+                                       (640, 480, 20, 1.0), (640, 480, 20, 1.04), (640, 480, 0, 1.2)])
+def test_window_ladder(ocpp, w, h, mn, sc):
+    """detectMultiScale1: win = int(win * factor) from fddb.minimum_size while it fits (cascador.cpp:335,372-373)"""
+    want = []
+    win = mn
+    if mn > 0 and sc > 1.0:
+        while win <= w and win <= h:
+            want.append(win)
+            nxt = int(win * sc)
+            if nxt <= win:
+                break
+            win = nxt
+    assert ocpp.levels(w, h, mn, sc) == want == api.levels_cpp(w, h, mn, sc)
+    assert ocpp.count_windows(w, h, mn, 5, sc) == api.count_windows_cpp(w, h, mn, 5, sc)
+
+
+def _multimap_nms(rects, scores, overlap):
+    """cascador.cpp:387-429 with a literal multimap stand-in: list of (score, idx) kept sorted, equal keys in
+    insertion order; take the last, erase everything with IoU > overlap (itself included)."""
+    m = []
+    for i, s in enumerate(scores):
+        j = len(m)
+        while j > 0 and m[j - 1][0] > s:
+            j -= 1
+        m.insert(j, (s, i))
+    picked = []
+    while m:
+        last = m[-1][1]
+        picked.append(last)
+        keep = []
+        for s, idx in m:
+            x1 = max(rects[idx][0], rects[last][0]); y1 = max(rects[idx][1], rects[last][1])
+            x2 = min(rects[idx][0] + rects[idx][2], rects[last][0] + rects[last][2])
+            y2 = min(rects[idx][1] + rects[idx][3], rects[last][1] + rects[last][3])
+            w, h = max(0.0, float(x2 - x1)), max(0.0, float(y2 - y1))
+            a1, a2 = float(rects[idx][2] * rects[idx][3]), float(rects[last][2] * rects[last][3])
+            if not (w * h / (a1 + a2 - w * h) > overlap):
+                keep.append((s, idx))
+        m = keep
+    return picked
+
+
+def test_nms_against_literal_multimap(ocpp):
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 2, 9, 60, 250):
+        size = rng.integers(20, 120, n)
+        rects = np.stack([rng.integers(0, 200, n), rng.integers(0, 200, n), size, size], 1).astype(np.int32)
+        scores = rng.normal(0, 1, n)
+        if n:
+            scores[rng.integers(0, n, n // 3)] = 0.25     # ties: the multimap keeps insertion order
+        for ov in (0.3, 0.0, 0.9):
+            assert list(ocpp.nms(rects, scores, ov)) == _multimap_nms(rects.tolist(), scores.tolist(), ov)
+
+
+def test_known_answers_regression_pin(ocpp, ocpp_shipped):
+    """what the restatement finds on the reference's own face image with model/config.json's fddb settings
+    (minimum_size 20, step 5, scale 1.2, overlap 0.3): pins the restatement against accidental change"""
+    img = synth.face_canvas()
+    rects, scores, shapes, carts = ocpp.detect(ocpp_shipped, img)
+    assert rects.tolist() == [[400, 290, 112, 112], [55, 40, 230, 230]]
+    np.testing.assert_allclose(scores, [2.08002624, 2.04335326], rtol=0, atol=5e-9)
+    assert shapes.shape == (2, 54) and carts == 4475389
+    # landmarks lie inside (a slightly grown copy of) their boxes
+    for r, s in zip(rects, shapes):
+        assert (s[0::2] > r[0] - 0.2 * r[2]).all() and (s[0::2] < r[0] + 1.2 * r[2]).all()
+        assert (s[1::2] > r[1] - 0.2 * r[3]).all() and (s[1::2] < r[1] + 1.2 * r[3]).all()
+    raw = ocpp.detect(ocpp_shipped, img, nms=False)
+    assert len(raw[1]) == 365 and (np.diff(raw[0][:, 2]) >= 0).all()      # scan order: window size ascending
+    tn, ts = ocpp.trace(ocpp_shipped, img)
+    assert len(tn) == 140215 == ocpp.count_windows(640, 480) and int(tn.sum()) == carts
+    assert int((tn == 2700).sum()) == 365                                    # faces ran every cart of every stage
+
+
+def _stage0_tables(path=SHIPPED_F32):
+    raw = open(path, "rb").read()
+    cart = np.frombuffer(raw, np.uint8, 540 * 268, 28 + 216).reshape(540, 268)
+    leaf = cart[:, 224:256].copy().view(np.float32).astype(np.float64)
+    tms = cart[:, 256:268].copy().view(np.float32).astype(np.float64)
+    return leaf, tms
+
+
+def test_prefilter_margins_bound_float_vs_double_scores():
+    """the float32 scan kernel may drop a window at cart k only if its float score is below th_k - margin_k;
+    margin_k must bound |float32 score - double score| for every leaf sequence.  Checked on random, extreme and
+    alternating leaf paths of the shipped stage 0 (float path = k2_scan's arithmetic, double path = Validate's)."""
+    c = api.Cascador(SHIPPED_F32, double=False)
+    margins = c.filter_margins_cpp()
+    c.close()
+    assert margins is not None and len(margins) == 540 and (margins > 0).all() and margins.max() < 0.05
+    leaf, tms = _stage0_tables()
+    rng = np.random.default_rng(0)
+    n = 4000
+    paths = rng.integers(0, 8, (n, 540))
+    paths[0] = np.abs(leaf).argmax(1); paths[1] = leaf.argmax(1); paths[2] = leaf.argmin(1)
+    paths[3] = np.where(np.arange(540) % 2, leaf.argmax(1), leaf.argmin(1))
+    s32 = np.zeros(n, np.float32)
+    s64 = np.zeros(n, np.float64)
+    worst = 0.0
+    for k in range(540):
+        lf = leaf[k][paths[:, k]]
+        s32 = (s32 + lf.astype(np.float32)).astype(np.float32)
+        s64 = s64 + lf
+        mean, sd = tms[k, 1], tms[k, 2]
+        if np.float32(mean) != 0 or np.float32(sd) != 1:
+            s32 = ((s32 - np.float32(mean)).astype(np.float32) / np.float32(sd)).astype(np.float32)
+        s64 = (s64 - mean) / sd
+        err = np.abs(s32.astype(np.float64) - s64).max()
+        assert err <= margins[k], (k, err, margins[k])
+        worst = max(worst, err / margins[k])
+    assert worst < 0.5     # the bound is conservative by construction (factor 4)
+
+
+def test_synthetic_double_models(ocpp, tmp_path):
+    """full-precision double models: pass-all (every window is a face), rejecting, and a training snapshot whose
+    header stops inside stage 2 (cascador.cpp:199-209)"""
+    img = synth.blur_frame(9, 96, 80)
+    p = synth.write_model(str(tmp_path / "pass.model"), seed=1, mode="passall")
+    h = ocpp.load(p, True)
+    r, s, sh, carts = ocpp.detect(h, img, nms=False)
+    nwin = ocpp.count_windows(96, 80)
+    assert len(s) == nwin and carts == nwin * 2700
+    ocpp.release(h)
+    q = synth.write_model(str(tmp_path / "rej.model"), seed=2, mode="reject")
+    b = bytearray(open(q, "rb").read())
+    b[20:24] = (2).to_bytes(4, "little"); b[24:28] = (17).to_bytes(4, "little", signed=True)
+    snap = tmp_path / "snap.model"
+    snap.write_bytes(bytes(b))
+    h = ocpp.load(str(snap), True)
+    d = ocpp.dims(h)
+    assert (d["stage"], d["cart"]) == (2, 17)
+    tn, ts = ocpp.trace(h, img)
+    assert tn.max() <= 2 * 540 + 18
+    ocpp.release(h)
