@@ -396,6 +396,31 @@ def main():
                                             "h2d_ms": st4["ms_h2d"], "host_nms_ms": st4["ms_host"],
                                             "h2d_bytes": int(o), "per_shape_batches_windows_per_s": wins4 / dtg,
                                             "distinct_shapes": len({f.shape for f in fr})}
+        # the reference's double-precision C++ detector (JoinCascador::Detect, fddb.method 1,
+        # config.json's fddb settings: min 20, step 5, scale 1.2) -- host frames in, 256 VGA frames per call; the
+        # CPU figure beside it is the oracle's C restatement on one core (the C++ detector itself cannot be built here)
+        fcpp = tile_batch(frame_pool(32, "mix", 13000), 256, 0)
+        wcpp = api.count_windows_cpp(W, H)
+        c.detect_cpp(fcpp[:8])
+        c.detect_cpp(fcpp)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            c.detect_cpp(fcpp)
+        dtc = (time.perf_counter() - t0) / 3
+        stc = dict(c.last_stats)
+        from oracle import pyoracle
+        oc = pyoracle.OracleCpp()
+        hc = oc.load(MODEL, double=False)
+        t0 = time.perf_counter()
+        for i in range(4):
+            oc.detect(hc, fcpp[i])
+        dto = (time.perf_counter() - t0) / 4
+        oc.release(hc)
+        ex["cpp_f64_detector_vga_256_frames"] = {"windows_per_frame": wcpp, "windows_per_s": 256 * wcpp / dtc,
+                                                 "ms_per_call": dtc * 1e3, "k2_prefilter_ms": stc["ms_scan"],
+                                                 "k4_f64_ms": stc["ms_cascade"],
+                                                 "prefilter_survivors": stc["stage0_survivors"], "faces_pre_nms": stc["raw_hits"],
+                                                 "cpu_port_1core_windows_per_s": wcpp / dto}
         out["other_configs"] = ex
     if rank == 0:
         print(json.dumps(out), flush=True)

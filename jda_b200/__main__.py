@@ -4,6 +4,10 @@ are GUI/OpenCV demos and are not rebuilt).
   python -m jda_b200 info    MODEL [--float] [--size WxH] [--max-size N]
   python -m jda_b200 convert MODEL_DOUBLE OUT_FLOAT32          (jdaCascadorSerializeTo, c/jda.c:644-716)
   python -m jda_b200 detect  MODEL IMAGE... [--float] [--fddb-out FILE] [--scale S --min-size N --max-size N --th T]
+  python -m jda_b200 detect  MODEL IMAGE... --cpp [--fddb-min 20 --fddb-step 5 --fddb-scale 1.2 --overlap 0.3 --no-nms]
+
+`--cpp` runs the reference's double-precision C++ detector (JoinCascador::Detect, fddb.method = 1 -- what src/test.cpp's
+FDDB runner itself calls) with the fddb.* settings of config.json instead of the C library's jdaDetect.
 
 `detect` reads gray images (.npy u8 arrays, binary .pgm, or anything cv2 can open when cv2 is present) and, with
 --fddb-out, writes the result-file format of the reference's FDDB runner (src/test.cpp:153,163):
@@ -54,6 +58,10 @@ def main(argv=None):
     p.add_argument("--fddb-out"); p.add_argument("--scale", type=float, default=1.25)
     p.add_argument("--min-size", type=int, default=24); p.add_argument("--max-size", type=int, default=-1)
     p.add_argument("--th", type=float, default=0.0)
+    p.add_argument("--cpp", action="store_true", help="JoinCascador::Detect (double precision, fddb.method 1)")
+    p.add_argument("--fddb-min", type=int, default=20); p.add_argument("--fddb-step", type=int, default=5)
+    p.add_argument("--fddb-scale", type=float, default=1.2); p.add_argument("--overlap", type=float, default=0.3)
+    p.add_argument("--no-nms", action="store_true")
     a = ap.parse_args(argv)
 
     if a.cmd == "convert":
@@ -74,13 +82,17 @@ def main(argv=None):
                        ("shared memory, %d warp(s) per tile" % q["span"]) if q["smem"] else "global memory"))
         return 0
     frames = [read_gray(p) for p in a.images]
-    res = c.detect_many(frames, scale=a.scale, min_size=a.min_size, max_size=a.max_size, th=a.th)
+    if a.cpp:
+        res = c.detect_cpp_many(frames, minimum_size=a.fddb_min, step=a.fddb_step, scale=a.fddb_scale, overlap=a.overlap,
+                                nms=not a.no_nms)
+    else:
+        res = c.detect_many(frames, scale=a.scale, min_size=a.min_size, max_size=a.max_size, th=a.th)
     out = open(a.fddb_out, "w") if a.fddb_out else sys.stdout
     for path, (boxes, scores, shapes) in zip(a.images, res):
         name = os.path.splitext(path)[0]
         out.write("%s\n%d\n" % (name, len(scores)))
         for b, s in zip(boxes, scores):
-            out.write("%d %d %d %d %f\n" % (b[0], b[1], b[2], b[2], s))
+            out.write("%d %d %d %d %f\n" % (b[0], b[1], b[2], b[3] if a.cpp else b[2], s))  # test.cpp:163: "%d %d %d %d %lf"
     if a.fddb_out:
         out.close()
     return 0

@@ -357,6 +357,18 @@ class Cascador:
             raise RuntimeError("jdaB200JoinCascadorFilterMargins failed: " + last_error())
         return buf if n > 0 else None
 
+    def detect_cpp_many(self, frames, **kw):
+        """detect_cpp on frames of mixed sizes: one batch call per distinct shape, results in input order"""
+        groups = {}
+        for i, f in enumerate(frames):
+            groups.setdefault(tuple(f.shape), []).append(i)
+        out = [None] * len(frames)
+        for shape, idx in groups.items():
+            res = self.detect_cpp(np.stack([np.ascontiguousarray(frames[i], np.uint8) for i in idx]), **kw)
+            for i, r in zip(idx, res):
+                out[i] = r
+        return out
+
     def trace_cpp(self, img, minimum_size=20, step=5, scale=1.2):
         """JoinCascador::Validate per window in scan order: (carts evaluated, exit score f64)"""
         a = np.ascontiguousarray(img, np.uint8)

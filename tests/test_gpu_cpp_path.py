@@ -156,3 +156,20 @@ def test_refusals_and_edges(casc, ocpp, ocpp_shipped, tmp_path):
     # the float C path on the same handle is untouched by the double path's state
     img = synth.face_canvas()
     assert casc.detect(img)[0].tolist() == [[396, 308, 110], [63, 21, 213]]
+
+
+def test_cli_fddb_runner_uses_the_cpp_detector(tmp_path, ocpp, ocpp_shipped):
+    """src/test.cpp:73-235 (the FDDB runner) calls JoinCascador::Detect and writes `x y w h score` per face"""
+    from jda_b200.__main__ import main
+    img, small = synth.face_canvas(), synth.facemix_frame(8, 300, 200)
+    np.save(tmp_path / "a.npy", img)
+    np.save(tmp_path / "b.npy", small)
+    out = tmp_path / "fold-01-out.txt"
+    assert main(["detect", SHIPPED_F32, str(tmp_path / "a.npy"), str(tmp_path / "b.npy"), "--float", "--cpp",
+                 "--fddb-out", str(out)]) == 0
+    lines = out.read_text().split("\n")
+    r, s, _, _ = ocpp.detect(ocpp_shipped, img)
+    assert lines[0] == str(tmp_path / "a") and lines[1] == "2"
+    assert lines[2] == "%d %d %d %d %f" % (r[0][0], r[0][1], r[0][2], r[0][3], s[0])
+    r2, s2, _, _ = ocpp.detect(ocpp_shipped, small)
+    assert lines[4] == str(tmp_path / "b") and lines[5] == str(len(s2))
