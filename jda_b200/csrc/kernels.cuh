@@ -375,6 +375,7 @@ __device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, i
       alive[j] = alive[j] && !(s[j] < cth);
     }
   }
+  __syncwarp();  // every lane has read its list entries of this group before any lane overwrites one (in-place list)
 #pragma unroll
   for (int j = 0; j < NWG; j++) {
     const unsigned m = __ballot_sync(0xffffffffu, alive[j]);
