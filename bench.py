@@ -303,6 +303,19 @@ def main():
                                    "~1.8 B/window (see DESIGN.md)",
                            "carts_per_window": carts_pw, "algorithmic_bytes_per_window": bytes_pw,
                            "k2_windows_per_s": B * WINDOWS_PER_FRAME / k2_s}
+        # The unit that actually binds k2_scan is the shared-memory data pipe: 1 wavefront / clk / SM (measured:
+        # tools/probes/lds_probe.cu -> profiles/r1g_lds_probe.txt).  Wavefronts per window come from the committed ncu
+        # capture of this workload (profiles/r1b_metrics_k2_k3.txt: 2.479e9 shared wavefronts for 256 frames, of
+        # which 1.004e9 are bank-conflict replays); the rate is this run's.
+        wf_per_window = 2.479392042e9 / (256 * WINDOWS_PER_FRAME)
+        sm_hz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+        wf_rate = wf_per_window * B * WINDOWS_PER_FRAME / k2_s
+        out["roofline_onchip"] = {"bound": "shared-memory data pipe (LSU wavefronts)", "kernel": "k2_scan",
+                                  "achieved": wf_rate / 1e12, "peak": 148 * sm_hz / 1e12, "unit": "Twavefronts/s",
+                                  "frac": wf_rate / (148 * sm_hz),
+                                  "wavefronts_per_window": wf_per_window, "bank_conflict_share": 1.003793761 / 2.479392042,
+                                  "peak_source": "1 wavefront/clk/SM measured by tools/probes/lds_probe.cu x 148 SMs x SM clock",
+                                  "note": "wavefronts/window from the committed ncu capture of the same workload, rate from this run"}
         if not a.no_cpu_baseline and world == 1:  # the reported CPU baseline is an N=1 item
             cores = os.cpu_count() or 1
             n = max(8, min(2 * cores, 256))
