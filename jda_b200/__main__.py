@@ -6,6 +6,14 @@ are GUI/OpenCV demos and are not rebuilt).
   python -m jda_b200 detect  MODEL IMAGE... [--float] [--fddb-out FILE] [--scale S --min-size N --max-size N --th T]
   python -m jda_b200 detect  MODEL IMAGE... --cpp [--fddb-min 20 --fddb-step 5 --fddb-scale 1.2 --overlap 0.3 --no-nms]
 
+  python -m jda_b200 fddb    MODEL FDDB_DIR [--float] [--c-api] [--folds 1-10]
+
+`fddb` is the reference's FDDB runner (src/test.cpp:73-235) without the drawing: for every fold it reads
+FDDB_DIR/FDDB-folds/FDDB-fold-XX.txt, opens FDDB_DIR/images/<path>.jpg (unreadable images are skipped like there),
+converts BGR -> gray, runs the detector over all images of the fold in one batch and writes
+FDDB_DIR/result/fold-XX-out.txt in the evaluator's format.  Default detector: JoinCascador::Detect (double precision,
+config.json's fddb settings) as in the reference; --c-api uses jdaDetect's semantics instead.
+
 `--cpp` runs the reference's double-precision C++ detector (JoinCascador::Detect, fddb.method = 1 -- what src/test.cpp's
 FDDB runner itself calls) with the fddb.* settings of config.json instead of the C library's jdaDetect.
 
@@ -45,6 +53,38 @@ def read_gray(path):
     return np.ascontiguousarray(a, np.uint8)
 
 
+def run_fddb(c, a):
+    """src/test.cpp:96-224 without the drawing"""
+    import cv2
+    lo, _, hi = a.folds.partition("-")
+    os.makedirs(os.path.join(a.fddb_dir, "result"), exist_ok=True)
+    total = 0
+    for i in range(int(lo), int(hi or lo) + 1):
+        fold = os.path.join(a.fddb_dir, "FDDB-folds", "FDDB-fold-%02d.txt" % i)
+        names, frames = [], []
+        for path in open(fold).read().split():
+            img = cv2.imread(os.path.join(a.fddb_dir, "images", path + ".jpg"))          # test.cpp:126
+            if img is None:
+                print("Can not open %s, Skip it" % path)
+                continue
+            names.append(path)
+            frames.append(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))                         # test.cpp:132
+        if a.c_api:
+            res = [(np.column_stack([b, b[:, 2]]) if len(b) else np.zeros((0, 4), np.int32), s, p)
+                   for b, s, p in c.detect_many(frames)]
+        else:
+            res = c.detect_cpp_many(frames, minimum_size=a.fddb_min, step=a.fddb_step, scale=a.fddb_scale,
+                                    overlap=a.overlap, nms=not a.no_nms)
+        with open(os.path.join(a.fddb_dir, "result", "fold-%02d-out.txt" % i), "w") as out:
+            for path, (rects, scores, _) in zip(names, res):
+                out.write("%s\n%d\n" % (path, len(scores)))                            # test.cpp:153
+                for r, sc in zip(rects, scores):
+                    out.write("%d %d %d %d %f\n" % (r[0], r[1], r[2], r[3], sc))        # test.cpp:163
+        total += len(names)
+        print("fold %02d: %d images, %d detections" % (i, len(names), sum(len(r[1]) for r in res)))
+    return 0
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m jda_b200")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -59,6 +99,13 @@ def main(argv=None):
     p.add_argument("--min-size", type=int, default=24); p.add_argument("--max-size", type=int, default=-1)
     p.add_argument("--th", type=float, default=0.0)
     p.add_argument("--cpp", action="store_true", help="JoinCascador::Detect (double precision, fddb.method 1)")
+    p.add_argument("--fddb-min", type=int, default=20); p.add_argument("--fddb-step", type=int, default=5)
+    p.add_argument("--fddb-scale", type=float, default=1.2); p.add_argument("--overlap", type=float, default=0.3)
+    p.add_argument("--no-nms", action="store_true")
+    p = sub.add_parser("fddb")
+    p.add_argument("model"); p.add_argument("fddb_dir"); p.add_argument("--float", action="store_true")
+    p.add_argument("--c-api", action="store_true", help="jdaDetect semantics instead of JoinCascador::Detect")
+    p.add_argument("--folds", default="1-10")
     p.add_argument("--fddb-min", type=int, default=20); p.add_argument("--fddb-step", type=int, default=5)
     p.add_argument("--fddb-scale", type=float, default=1.2); p.add_argument("--overlap", type=float, default=0.3)
     p.add_argument("--no-nms", action="store_true")
@@ -81,6 +128,8 @@ def main(argv=None):
                       (q["win"], q["step"], q["nx"], q["ny"], q["tw"], q["th"], q["box_w"], q["box_h"],
                        ("shared memory, %d warp(s) per tile" % q["span"]) if q["smem"] else "global memory"))
         return 0
+    if a.cmd == "fddb":
+        return run_fddb(c, a)
     frames = [read_gray(p) for p in a.images]
     if a.cpp:
         res = c.detect_cpp_many(frames, minimum_size=a.fddb_min, step=a.fddb_step, scale=a.fddb_scale, overlap=a.overlap,

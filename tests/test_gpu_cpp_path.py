@@ -173,3 +173,26 @@ def test_cli_fddb_runner_uses_the_cpp_detector(tmp_path, ocpp, ocpp_shipped):
     assert lines[2] == "%d %d %d %d %f" % (r[0][0], r[0][1], r[0][2], r[0][3], s[0])
     r2, s2, _, _ = ocpp.detect(ocpp_shipped, small)
     assert lines[4] == str(tmp_path / "b") and lines[5] == str(len(s2))
+
+
+def test_fddb_runner_layout(tmp_path, ocpp, ocpp_shipped):
+    """python -m jda_b200 fddb: folds in, result/fold-XX-out.txt out (src/test.cpp:96-224), both detectors"""
+    cv2 = pytest.importorskip("cv2")
+    from jda_b200.__main__ import main
+    root = tmp_path / "fddb"
+    (root / "FDDB-folds").mkdir(parents=True)
+    (root / "images" / "2002" / "07").mkdir(parents=True)
+    imgs = {"2002/07/img_1": synth.face_canvas(), "2002/07/img_2": synth.facemix_frame(5, 410, 300)}
+    for k, v in imgs.items():
+        assert cv2.imwrite(str(root / "images" / (k + ".jpg")), cv2.cvtColor(v, cv2.COLOR_GRAY2BGR), [cv2.IMWRITE_JPEG_QUALITY, 97])
+    (root / "FDDB-folds" / "FDDB-fold-01.txt").write_text("2002/07/img_1\n2002/07/missing\n2002/07/img_2\n")
+    assert main(["fddb", SHIPPED_F32, str(root), "--float", "--folds", "1"]) == 0
+    lines = (root / "result" / "fold-01-out.txt").read_text().split("\n")
+    gray = cv2.cvtColor(cv2.imread(str(root / "images" / "2002/07/img_1.jpg")), cv2.COLOR_BGR2GRAY)   # what the runner saw
+    r, s, _, _ = ocpp.detect(ocpp_shipped, gray)
+    assert lines[0] == "2002/07/img_1" and lines[1] == str(len(s)) and len(s) >= 2
+    assert lines[2] == "%d %d %d %d %f" % (r[0][0], r[0][1], r[0][2], r[0][3], s[0])
+    assert lines[2 + len(s)] == "2002/07/img_2"                     # the unreadable image was skipped
+    assert main(["fddb", SHIPPED_F32, str(root), "--float", "--folds", "1", "--c-api"]) == 0
+    lines = (root / "result" / "fold-01-out.txt").read_text().split("\n")
+    assert lines[0] == "2002/07/img_1" and int(lines[1]) >= 2 and len(lines[2].split()) == 5
