@@ -199,13 +199,18 @@ def main():
 
     from jda_b200 import shard
 
+    gather = shard.RecordGather(5 + 2 * c.L, device="cuda") if dist_on else None
+
     def gather_records(res):
-        """the one exchange step of the path: NCCL all-gather of the fixed-stride detection records
-        (frame, x, y, size, score, 54 landmark floats) so every rank holds the job-wide table."""
+        """the one exchange step of the path: a single NCCL all-gather of the fixed-stride detection records
+        (frame, x, y, size, score, 54 landmark floats) so every rank holds the job-wide table.  It is launched
+        asynchronously and collected when the next batch's results are in (it runs under that batch's scan); the
+        last one of a timed region is collected before the region ends."""
         if not dist_on:
             return None
-        rec = shard.pack_records(res, frame0=rank * B, landmark_n=c.L)
-        return shard.all_gather_records(rec, device="cuda")
+        table = gather.finish()
+        gather.start(shard.pack_records(res, frame0=rank * B, landmark_n=c.L))
+        return table
 
     def step_resident(i):
         d = dev[i & 1]
@@ -224,6 +229,8 @@ def main():
         sampler = ClockSampler(local) if sample_clocks else None
         for i in range(warmup):
             step_fn(i)
+        if gather is not None:
+            gather.finish()
         torch.cuda.synchronize()
         if dist_on:
             dist.barrier()
@@ -239,6 +246,8 @@ def main():
                       "detections"):
                 acc[k] += st[k]
             acc["launches"] += st["scan_launches"] + st["cascade_launches"] + st["resize_launches"]
+        if gather is not None:
+            gather.finish()       # the last batch's exchange completes inside the timed region
         e1.record(stream)
         torch.cuda.synchronize()
         if dist_on:

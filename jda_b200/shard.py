@@ -64,3 +64,60 @@ def all_gather_records(rec, device=None, group=None):
     dist.all_gather_into_tensor(allr, mine, group=group)
     allr = allr.cpu().numpy().reshape(world, mx, width)
     return np.concatenate([allr[r, :int(cnts_h[r])] for r in range(world)], axis=0)
+
+
+class RecordGather:
+    """The exchange step as ONE collective per batch that can run under the next batch's scan.
+
+    Every rank sends a fixed-capacity block [cap + 1, width]: row 0 carries its record count, rows 1.. the records.
+    start() uploads the block and launches the all-gather asynchronously (NCCL runs it on its own stream while the
+    caller goes on to scan the next batch); finish() waits, reads the job-wide table back and returns it ordered by
+    (rank, local order) = global frame order.  A batch with more records than `cap` on some rank is rare (the
+    capacity doubles past the largest count seen): finish() then repeats the exchange synchronously with a larger
+    block, so the result never depends on the capacity."""
+
+    def __init__(self, width, device=None, group=None, cap=256):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.width, self.group, self.cap = width, group, cap
+        self.dev = torch.device(device) if device is not None else torch.device("cpu")
+        self.world = dist.get_world_size(group)
+        self.pending = None
+        self.exchanges = 0
+
+    def _launch(self, rec, cap, async_op):
+        torch = self.torch
+        host = torch.zeros((cap + 1, self.width), dtype=torch.float32)
+        if self.dev.type == "cuda":
+            host = host.pin_memory()
+        n = min(rec.shape[0], cap)
+        host[0, 0] = float(rec.shape[0])     # exact up to 2^24 records per rank
+        if n:
+            host[1:n + 1] = torch.from_numpy(np.ascontiguousarray(rec[:n], np.float32))
+        send = host.to(self.dev, non_blocking=True)
+        recv = torch.empty((self.world * (cap + 1), self.width), dtype=torch.float32, device=self.dev)
+        work = self.dist.all_gather_into_tensor(recv, send, group=self.group, async_op=async_op)
+        self.exchanges += 1
+        return dict(rec=rec, cap=cap, host=host, send=send, recv=recv, work=work)
+
+    def start(self, rec):
+        assert self.pending is None, "finish() the previous exchange first"
+        self.pending = self._launch(rec, self.cap, True)
+
+    def finish(self):
+        p, self.pending = self.pending, None
+        if p is None:
+            return None
+        while True:
+            if p["work"] is not None:
+                p["work"].wait()
+            allr = p["recv"].cpu().numpy().reshape(self.world, p["cap"] + 1, self.width)
+            counts = allr[:, 0, 0].astype(np.int64)
+            if counts.max() <= p["cap"]:
+                self.cap = max(self.cap, 1 << int(np.ceil(np.log2(max(int(counts.max()) * 2, 1)))))
+                return np.concatenate([allr[r, 1:1 + int(counts[r])] for r in range(self.world)], axis=0)
+            # some rank overflowed its block: every rank sees the same counts, so every rank repeats the exchange
+            cap = 1 << int(np.ceil(np.log2(int(counts.max()) * 2)))
+            self.cap = max(self.cap, cap)
+            p = self._launch(p["rec"], cap, False)

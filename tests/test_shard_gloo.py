@@ -56,6 +56,19 @@ def _worker(rank, world, port, out_dir):
     rec = shard.pack_records(local, frame0=lo)
     table = shard.all_gather_records(rec)
     np.save(os.path.join(out_dir, "table_%d.npy" % rank), table)
+    # the one-collective exchange: same table; a block that is too small is repeated with a larger one
+    g = shard.RecordGather(rec.shape[1], cap=256)
+    g.start(rec)
+    t2 = g.finish()
+    assert g.exchanges == 1 and g.finish() is None
+    np.testing.assert_array_equal(t2.view(np.uint32), table.view(np.uint32))
+    small = shard.RecordGather(rec.shape[1], cap=1)
+    small.start(rec)
+    t3 = small.finish()
+    assert small.exchanges == 2 and small.cap >= 2
+    np.testing.assert_array_equal(t3.view(np.uint32), table.view(np.uint32))
+    small.start(rec[:0])                       # an empty contribution from every rank
+    assert small.finish().shape == (0, rec.shape[1])
     o.release(h)
     dist.destroy_process_group()
 
