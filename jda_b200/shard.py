@@ -24,17 +24,15 @@ def pack_records(results, frame0=0, landmark_n=27):
     """list of (boxes, scores, shapes) per local frame -> [n, 5 + 2L] float32 records.
     Integers up to 2^24 (frame ids, pixel coordinates) are exact in float32."""
     D = 2 * landmark_n
-    n = sum(len(r[1]) for r in results)
+    counts = np.fromiter((len(r[1]) for r in results), np.int64, len(results))
+    n = int(counts.sum())
     rec = np.zeros((n, HEADER + D), np.float32)
-    o = 0
-    for f, (boxes, scores, shapes) in enumerate(results):
-        k = len(scores)
-        if k:
-            rec[o:o + k, 0] = frame0 + f
-            rec[o:o + k, 1:4] = boxes
-            rec[o:o + k, 4] = scores
-            rec[o:o + k, HEADER:] = shapes
-            o += k
+    if n:
+        hit = [r for r, k in zip(results, counts) if k]
+        rec[:, 0] = np.repeat(np.arange(len(results)) + frame0, counts)
+        rec[:, 1:4] = np.concatenate([r[0] for r in hit])
+        rec[:, 4] = np.concatenate([r[1] for r in hit])
+        rec[:, HEADER:] = np.concatenate([r[2] for r in hit])
     return rec
 
 
@@ -85,12 +83,16 @@ class RecordGather:
         self.world = dist.get_world_size(group)
         self.pending = None
         self.exchanges = 0
+        self._host = {}
 
     def _launch(self, rec, cap, async_op):
         torch = self.torch
-        host = torch.zeros((cap + 1, self.width), dtype=torch.float32)
-        if self.dev.type == "cuda":
-            host = host.pin_memory()
+        host = self._host.get(cap)
+        if host is None:      # one pinned staging block per capacity, reused by every batch
+            host = torch.zeros((cap + 1, self.width), dtype=torch.float32)
+            if self.dev.type == "cuda":
+                host = host.pin_memory()
+            self._host[cap] = host
         n = min(rec.shape[0], cap)
         host[0, 0] = float(rec.shape[0])     # exact up to 2^24 records per rank
         if n:
