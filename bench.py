@@ -200,17 +200,36 @@ def main():
     from jda_b200 import shard
 
     gather = shard.RecordGather(5 + 2 * c.L, device="cuda") if dist_on else None
+    exchange = {"pool": None, "fut": None}
+    if dist_on:
+        from concurrent.futures import ThreadPoolExecutor
+        exchange["pool"] = ThreadPoolExecutor(1)
+        exchange["pool"].submit(torch.cuda.set_device, local).result()
 
-    def gather_records(res):
-        """the one exchange step of the path: a single NCCL all-gather of the fixed-stride detection records
-        (frame, x, y, size, score, 54 landmark floats) so every rank holds the job-wide table.  It is launched
-        asynchronously and collected when the next batch's results are in (it runs under that batch's scan); the
-        last one of a timed region is collected before the region ends."""
-        if not dist_on:
-            return None
+    def _exchange(res):
         table = gather.finish()
         gather.start(shard.pack_records(res, frame0=rank * B, landmark_n=c.L))
         return table
+
+    def exchange_wait():
+        """collect what is still in flight: the helper thread's work, then the last all-gather"""
+        if exchange["fut"] is not None:
+            exchange["fut"].result()
+            exchange["fut"] = None
+        if gather is not None:
+            gather.finish()
+
+    def gather_records(res):
+        """the one exchange step of the path: a single NCCL all-gather of the fixed-stride detection records
+        (frame, x, y, size, score, 54 landmark floats) so every rank holds the job-wide table.  Packing, the
+        asynchronous launch and the collection of the previous batch's table run on a helper thread while the main
+        thread is already inside the next batch's detect call (which releases the GIL); whatever is still in
+        flight at the end of a timed region is collected before the region ends."""
+        if not dist_on:
+            return
+        if exchange["fut"] is not None:
+            exchange["fut"].result()
+        exchange["fut"] = exchange["pool"].submit(_exchange, res)
 
     def step_resident(i):
         d = dev[i & 1]
@@ -229,8 +248,7 @@ def main():
         sampler = ClockSampler(local) if sample_clocks else None
         for i in range(warmup):
             step_fn(i)
-        if gather is not None:
-            gather.finish()
+        exchange_wait()
         torch.cuda.synchronize()
         if dist_on:
             dist.barrier()
@@ -246,8 +264,7 @@ def main():
                       "detections"):
                 acc[k] += st[k]
             acc["launches"] += st["scan_launches"] + st["cascade_launches"] + st["resize_launches"]
-        if gather is not None:
-            gather.finish()       # the last batch's exchange completes inside the timed region
+        exchange_wait()           # the last batch's exchange completes inside the timed region
         e1.record(stream)
         torch.cuda.synchronize()
         if dist_on:
@@ -443,6 +460,7 @@ def main():
         print(json.dumps(out), flush=True)
     c.close()
     if dist_on:
+        exchange["pool"].shutdown()
         dist.destroy_process_group()
 
 
