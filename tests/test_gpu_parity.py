@@ -272,6 +272,8 @@ def test_mixed_sizes_edge_cases(casc, oracle, oracle_shipped):
                                                        kw.get("min_size", 24), kw.get("max_size", -1)) for f in frames)
         for f, g in zip(frames, got):
             _same(g, oracle.detect(oracle_shipped, np.ascontiguousarray(f), **kw))
+    for g, f in zip(casc.detect_mixed(frames, th=-0.5, flags=api.NO_TMA), frames):     # tiles filled by plain loads
+        _same(g, oracle.detect(oracle_shipped, np.ascontiguousarray(f), th=-0.5))
     assert casc.detect_mixed([]) == []
     got = casc.detect_mixed([tiny])
     assert len(got) == 1 and len(got[0][1]) == 0
