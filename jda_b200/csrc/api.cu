@@ -224,7 +224,7 @@ bool ctx_init(Context *c) {
             cudaSuccess && q == cudaDriverEntryPointSuccess)
       c->encode = (EncodeTiledFn)fn;
   }
-  const size_t s2 = k2_smem_bytes((c->m.K * kCartBytes + 127) & ~127);
+  const size_t s2 = k2_smem_bytes(std::min((c->m.K * kCartBytes + 127) & ~127, kMaxStage0TableBytes));  // larger K: no scan kernel
   CU_OK(cudaFuncSetAttribute(k2_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
@@ -232,7 +232,9 @@ bool ctx_init(Context *c) {
   CU_OK(cudaFuncSetAttribute(k2_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-  CU_OK(cudaFuncSetAttribute(k3_stage0, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CU_OK(cudaFuncSetAttribute(k3_stage0<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)k3s_smem_bytes(c->m.K, c->m.D())));
+  CU_OK(cudaFuncSetAttribute(k3_stage0<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)k3s_smem_bytes(c->m.K, c->m.D())));
   const size_t s3 = k3_smem_bytes(c->m.K);
   CU_OK(cudaFuncSetAttribute(k3_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
@@ -775,7 +777,8 @@ bool launch_cascade(Run &R) {
     S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
     S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)c->surv_cap;
     S.out_shape = c->d_shape0.p;
-    k3_stage0<<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
+    if (R.D <= 64) k3_stage0<1><<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
+    else k3_stage0<2><<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
     CU_OK(cudaGetLastError());
     st.cascade_launches++;
   }
@@ -983,7 +986,8 @@ bool ensure_model64_host(Context *c) {
     return false;
   }
   const HostModelD &m = c->md;
-  c->filter64_ok = m.stage >= 1 && count_normed_stage0(m) <= kMaxNorm && stage0_filter_margins(m, c->margins64);
+  c->filter64_ok = m.stage >= 1 && count_normed_stage0(m) <= kMaxNorm && m.K * kCartBytes <= kMaxStage0TableBytes &&
+                   stage0_filter_margins(m, c->margins64);
   return true;
 }
 

@@ -27,6 +27,8 @@ constexpr int kLeaves = 8;      // leaves per cart
 constexpr int kMaxLevels = 20;  // pyramid levels per geometry
 constexpr int kMaxDim = 128;    // 2 * landmark_n upper bound
 constexpr int kMaxNorm = 32;    // stage-0 carts with non-trivial (mean, std) the scan kernel can hold
+constexpr int kCartBytes = 104;  // stage-0 table record of one cart (layout below, at build_stage0_table)
+constexpr int kMaxStage0TableBytes = 88 * 1024;  // K <= 866: the table + 12 x 11 KB of warp scratch fit 227 KB
 
 // 32-byte node record as the cascade kernel reads it (two 16-byte loads)
 struct alignas(16) NodeRec {
@@ -132,7 +134,8 @@ inline bool load_model(const char *path, bool dbl, HostModel &m, std::string &er
   }
   for (int k = 0; k < m.K; k++)
     if (m.cart[k * 4 + 1] != 0.f || m.cart[k * 4 + 2] != 1.f) norm0++;
-  m.stage0_lut_ok = !s0_scaled && norm0 <= kMaxNorm;
+  // the scan kernel keeps one level's table (K x kCartBytes) in shared memory next to its tile buffers
+  m.stage0_lut_ok = !s0_scaled && norm0 <= kMaxNorm && m.K * kCartBytes <= kMaxStage0TableBytes;
   return true;
 }
 
@@ -217,7 +220,7 @@ inline long long count_windows(int w, int h, float scale, int min_size, int max_
 //   [56..88)  8 leaf scores (f32)
 //   [88]      cart threshold (f32)
 //   [92]      0, or 1 + index into the norm table when (mean, std) != (0, 1)
-constexpr int kCartBytes = 104;
+
 
 struct Stage0Norm { float mean, std; };
 

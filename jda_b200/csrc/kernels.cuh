@@ -975,6 +975,9 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
+// HALVES = ceil(2L / 64): coordinate pairs per lane.  L <= 32 (the shipped L = 27) needs one, so the second,
+// fully predicated-off pass over every row is compiled out (it was 20 % of the kernel's instructions).
+template <int HALVES>
 __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constant__ Stage0Params P) {
   extern __shared__ __align__(16) uint8_t smem0[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -997,11 +1000,11 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
       for (int i = lane; i < kpad / 4; i += 32) dst[i] = __ldg(src + i);
     }
     // ---- regression gather over staged chunks of w[0]
-    float2 acc[K3S_PER_WARP][2];
+    float2 acc[K3S_PER_WARP][HALVES];
 #pragma unroll
     for (int s = 0; s < K3S_PER_WARP; s++)
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
+      for (int h = 0; h < HALVES; h++) {
         const int p = lane + 32 * h;
         acc[s][h] = (2 * p + 1 < D) ? make_float2(P.mean_shape[2 * p], P.mean_shape[2 * p + 1]) : make_float2(0.f, 0.f);
       }
@@ -1039,7 +1042,7 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
             const uint32_t leaf = (lq[cl >> 2] >> (8 * (cl & 3))) & 0xffu;
             const float2 *row = reinterpret_cast<const float2 *>(rb + (cl * kLeaves + leaf) * D);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < HALVES; h++) {
               const int p = lane + 32 * h;
               if (2 * p + 1 < D) {
                 const float2 v = row[p];
@@ -1057,7 +1060,7 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
       const int e = c0 + warp * K3S_PER_WARP + s;
       if (e < total) {
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < HALVES; h++) {
           const int p = lane + 32 * h;
           if (2 * p + 1 < D) reinterpret_cast<float2 *>(P.out_shape + (size_t)e * D)[p] = acc[s][h];
         }

@@ -118,6 +118,22 @@ def test_synthetic_double_models(ocpp, tmp_path, cfg):
     c.close(); ocpp.release(h)
 
 
+@pytest.mark.parametrize("dims", [dict(T=2, K=33, L=5), dict(T=3, K=96, L=40), dict(T=2, K=1000, L=8)],
+                         ids=lambda d: "T%d_K%d_L%d" % (d["T"], d["K"], d["L"]))
+def test_model_dimensions_from_the_header(ocpp, tmp_path, dims):
+    path = synth.write_model(str(tmp_path / "dims.model"), seed=11 + dims["K"], mode="reject", norm_every=270 if dims["K"] > 900 else 10, **dims)
+    c = api.Cascador(path, double=True)
+    h = ocpp.load(path, True)
+    for img in (synth.blur_frame(9, 96, 80), synth.facemix_frame(3, 200, 150)):
+        _same(c.detect_cpp(img, nms=False), ocpp.detect(h, img, nms=False))
+        _same(c.detect_cpp(img), ocpp.detect(h, img))
+    tn, ts = c.trace_cpp(synth.noise_frame(5, 70, 61))
+    on, os_ = ocpp.trace(h, synth.noise_frame(5, 70, 61))
+    np.testing.assert_array_equal(tn, on)
+    np.testing.assert_array_equal(_bits(ts), _bits(os_))
+    c.close(); ocpp.release(h)
+
+
 def test_training_snapshot_header(ocpp, tmp_path):
     """a model whose header stops inside a stage (cascador.cpp:199-209): full stages, then carts 0..cart, no regression"""
     q = synth.write_model(str(tmp_path / "rej.model"), seed=2, mode="reject")

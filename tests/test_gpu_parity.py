@@ -193,6 +193,40 @@ def test_synthetic_models(oracle, tmp_path, cfg):
     c.close(); oracle.release(ho)
 
 
+DIMS = [dict(T=2, K=33, L=5), dict(T=3, K=96, L=40), dict(T=1, K=540, L=27), dict(T=6, K=64, L=16),
+        dict(T=2, K=1000, L=8)]        # K = 1000: the stage-0 table does not fit shared memory -> generic kernel only
+
+
+@pytest.mark.parametrize("dims", DIMS, ids=lambda d: "T%d_K%d_L%d" % (d["T"], d["K"], d["L"]))
+@pytest.mark.parametrize("mode", ["reject", "passall"])
+def test_model_dimensions_from_the_header(oracle, tmp_path, dims, mode):
+    """T, K, landmark_n come from the model header, not from compile-time macros
+    (c/jda.c:24-32 fixes them at 5 / 540 / 27).  Oracle = the restatement, which reads the header too."""
+    if mode == "passall" and dims["K"] * dims["T"] > 1200:
+        pytest.skip("pass-all on a deep model is covered by the default dimensions")
+    path = synth.write_model(str(tmp_path / "dims.model"), seed=7 + dims["K"], mode=mode, norm_every=270 if dims["K"] > 900 else 10, **dims)
+    c = api.Cascador(path, double=True)
+    ho = oracle.load(path, True)
+    assert (c.T, c.K, c.L) == (dims["T"], dims["K"], dims["L"]) == oracle.dims(ho)[:3]
+    frames = [synth.blur_frame(9, 96, 80), synth.noise_frame(5, 70, 61), synth.facemix_frame(3, 200, 150)]
+    for img in frames:
+        for kw in (dict(th=-1e30), dict(scale=1.3, min_size=30, max_size=60, th=0.0)):
+            _same(c.detect(img, **kw), oracle.detect(ho, img, **kw))
+    batch = synth.make_frames("facemix", 9, 120, 90, seed0=5)      # > 4 frames: throughput plan + staged stage 0
+    for g, f in zip(c.detect_batch(batch, th=-1e30, flags=api.RAW_HITS), batch):
+        ob, osc, osh, _ = oracle.detect_raw(ho, f, th=-1e30)
+        _same(g, (ob, osc, osh))
+    tn, ts, lv = c.trace(frames[0], leaf_range=(0, 300))
+    on, os_, olv = oracle.trace(ho, frames[0], leaf_range=(0, 300))
+    np.testing.assert_array_equal(tn, on)
+    np.testing.assert_array_equal(_bits(ts), _bits(os_))
+    np.testing.assert_array_equal(lv, olv)
+    out = tmp_path / "rt.model"
+    c.save_f32(str(out)); oracle.save_f32(ho, str(tmp_path / "rt_o.model"))
+    assert out.read_bytes() == (tmp_path / "rt_o.model").read_bytes()
+    c.close(); oracle.release(ho)
+
+
 def test_against_reference_library_directly(reflib, tmp_path):
     path = synth.write_model(str(tmp_path / "syn.model"), seed=21, mode="reject")
     c = api.Cascador(path, double=True)
