@@ -208,7 +208,7 @@ def main():
 
     def _exchange(res):
         table = gather.finish()
-        gather.start(shard.pack_records(res, frame0=rank * B, landmark_n=c.L))
+        gather.start(shard.pack_records_flat(*res, frame0=rank * B))
         return table
 
     def exchange_wait():
@@ -233,13 +233,13 @@ def main():
 
     def step_resident(i):
         d = dev[i & 1]
-        res = c.detect_batch(None, device_ptr=d.data_ptr(), shape=(B, H, W), **ARGS)
+        res = c.detect_batch(None, device_ptr=d.data_ptr(), shape=(B, H, W), flat=True, **ARGS)
         gather_records(res)
         return c.last_stats
 
     def step_e2e(i):
         hbuf = host[i & 1].numpy()
-        res = c.detect_batch(hbuf, **ARGS)
+        res = c.detect_batch(hbuf, flat=True, **ARGS)
         gather_records(res)
         return c.last_stats
 

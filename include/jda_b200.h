@@ -111,6 +111,24 @@ typedef struct {
 JDA_API int jdaB200DetectBatch(void *cascador, const unsigned char *frames, const jdaB200Batch *batch,
                                jdaResult *results, jdaB200Stats *stats /* may be NULL */);
 
+/* jdaB200DetectBatch with ONE result for the whole batch: counts[n_frames] detections per frame, then the
+ * detections of all frames back to back (frame order, scan order inside a frame) in three arrays -- four
+ * allocations per call instead of three per frame, and a shape FFI hosts can wrap without a per-frame loop.
+ * Same NMS / relocation / flags as jdaB200DetectBatch.  On failure n_frames = -1 and the arrays are NULL. */
+typedef struct {
+  int n_frames;
+  int total;      /* sum of counts */
+  int landmark_n;
+  int *counts;    /* int[n_frames]            */
+  int *bboxes;    /* int[3 * total]           */
+  float *scores;  /* float[total]             */
+  float *shapes;  /* float[2*landmark_n*total] */
+} jdaB200FlatResult;
+
+JDA_API int jdaB200DetectBatchFlat(void *cascador, const unsigned char *frames, const jdaB200Batch *batch,
+                                   jdaB200FlatResult *result, jdaB200Stats *stats /* may be NULL */);
+JDA_API void jdaB200FlatResultRelease(jdaB200FlatResult *result);
+
 /* Frames of different sizes in one call (reference: test.cpp:73-235 feeds FDDB images of all shapes one by one to
  * the detector; here they share one launch).  Host memory only.  pitch = 0 means pitch == width. */
 typedef struct {

@@ -56,6 +56,11 @@ class CppParams(C.Structure):
                 ("nms", C.c_int), ("flags", C.c_int)]
 
 
+class FlatResult(C.Structure):
+    _fields_ = [("n_frames", C.c_int), ("total", C.c_int), ("landmark_n", C.c_int), ("counts", C.POINTER(C.c_int)),
+                ("bboxes", C.POINTER(C.c_int)), ("scores", C.POINTER(C.c_float)), ("shapes", C.POINTER(C.c_float))]
+
+
 class Frame(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_int)]
 
@@ -94,6 +99,10 @@ def lib():
     L.jdaResultRelease.argtypes = [_Result]
     L.jdaB200DetectBatch.restype = ci
     L.jdaB200DetectBatch.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(_Result), C.POINTER(Stats)]
+    L.jdaB200DetectBatchFlat.restype = ci
+    L.jdaB200DetectBatchFlat.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(FlatResult), C.POINTER(Stats)]
+    L.jdaB200FlatResultRelease.restype = None
+    L.jdaB200FlatResultRelease.argtypes = [C.POINTER(FlatResult)]
     L.jdaB200DetectMixed.restype = ci
     L.jdaB200DetectMixed.argtypes = [vp, C.POINTER(Frame), ci, cf, ci, ci, cf, ci, ci, C.POINTER(_Result),
                                      C.POINTER(Stats)]
@@ -143,7 +152,8 @@ EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSeri
            "jdaB200DeviceCount", "jdaB200Levels", "jdaB200CountWindows", "jdaB200Nms",
            "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan", "jdaB200ResultsRelease",
            "jdaB200DetectMixed", "jdaB200JoinCascadorDetect", "jdaB200ResultF64Release",
-           "jdaB200JoinCascadorTrace", "jdaB200JoinCascadorLevels", "jdaB200JoinCascadorFilterMargins"]
+           "jdaB200JoinCascadorTrace", "jdaB200JoinCascadorLevels", "jdaB200JoinCascadorFilterMargins",
+           "jdaB200DetectBatchFlat", "jdaB200FlatResultRelease"]
 
 
 def last_error():
@@ -251,7 +261,7 @@ class Cascador:
         return _unpack(res)
 
     def detect_batch(self, frames, scale=1.25, min_size=24, max_size=-1, th=0.0, t_limit=0, flags=0,
-                     device_ptr=None, shape=None, pitch=None, frame_stride=None, unpack=True):
+                     device_ptr=None, shape=None, pitch=None, frame_stride=None, unpack=True, flat=False):
         """frames: [n,h,w] u8 numpy array (host), or device_ptr + shape=(n,h,w) for frames resident
         in HBM (any allocator: torch .data_ptr(), cudaMalloc ...).  Returns a list of
         (boxes, scores, shapes) per frame, or just the detection count when unpack=False."""
@@ -270,6 +280,24 @@ class Cascador:
             frame_stride = pitch * h if frame_stride is None else frame_stride
             flags |= DEVICE_INPUT
         b = Batch(n, w, h, pitch, frame_stride, scale, min_size, max_size, th, t_limit, flags)
+        if flat:
+            # jdaB200DetectBatchFlat: (counts[n], boxes[total,3], scores[total], shapes[total,2L]), frame order
+            fr = FlatResult()
+            st = Stats()
+            rc = L.jdaB200DetectBatchFlat(self._h, C.c_void_p(ptr), C.byref(b), C.byref(fr), C.byref(st))
+            self.last_stats = st.as_dict()
+            if rc != 0:
+                raise RuntimeError("jdaB200DetectBatchFlat failed: " + last_error())
+            tot, D = fr.total, 2 * fr.landmark_n
+            counts = np.ctypeslib.as_array(fr.counts, shape=(max(n, 1),))[:n].copy()
+            if tot:
+                out = (counts, np.ctypeslib.as_array(fr.bboxes, shape=(tot, 3)).copy(),
+                       np.ctypeslib.as_array(fr.scores, shape=(tot,)).copy(),
+                       np.ctypeslib.as_array(fr.shapes, shape=(tot, D)).copy())
+            else:
+                out = (counts, np.zeros((0, 3), np.int32), np.zeros((0,), np.float32), np.zeros((0, D), np.float32))
+            L.jdaB200FlatResultRelease(C.byref(fr))
+            return out
         res = (_Result * n)()
         st = Stats()
         rc = L.jdaB200DetectBatch(self._h, C.c_void_p(ptr), C.byref(b), res, C.byref(st))

@@ -1263,24 +1263,84 @@ long long finish_frames(Context *c, const std::vector<HitRec> &hits, int n_frame
   return dets;
 }
 
+// hits (sorted by frame, scan order inside a frame) -> one flat result for the whole batch: three arrays instead of
+// three per frame.  NMS and relocation per frame exactly as finish_frame does them.
+bool finish_flat(Context *c, const std::vector<HitRec> &hits, int n_frames, bool raw, jdaB200FlatResult *out) {
+  const HostModel &m = c->m;
+  const int D = m.D();
+  out->n_frames = n_frames; out->landmark_n = m.L; out->total = 0;
+  out->counts = (int *)calloc(n_frames > 0 ? n_frames : 1, sizeof(int));
+  std::vector<uint8_t> keep(hits.size() > 0 ? hits.size() : 1, 1);
+  std::vector<int> box;
+  std::vector<float> sc;
+  size_t i = 0, total = 0;
+  for (int f = 0; f < n_frames && out->counts; f++) {
+    size_t j = i;
+    while (j < hits.size() && hits[j].frame == f) j++;
+    const int n = (int)(j - i);
+    if (n > 0 && !raw) {
+      box.resize(3 * (size_t)n); sc.resize(n);
+      for (int q = 0; q < n; q++) {
+        box[3 * q] = hits[i + q].x; box[3 * q + 1] = hits[i + q].y; box[3 * q + 2] = hits[i + q].win;
+        sc[q] = hits[i + q].score;
+      }
+      nms(n, box.data(), sc.data(), keep.data() + i);
+    }
+    int kept = 0;
+    for (int q = 0; q < n; q++) kept += keep[i + q];
+    out->counts[f] = kept;
+    total += kept;
+    i = j;
+  }
+  out->bboxes = (int *)malloc(sizeof(int) * 3 * (total > 0 ? total : 1));
+  out->scores = (float *)malloc(sizeof(float) * (total > 0 ? total : 1));
+  out->shapes = (float *)malloc(sizeof(float) * D * (total > 0 ? total : 1));
+  if (!out->counts || !out->bboxes || !out->scores || !out->shapes) {
+    free(out->counts); free(out->bboxes); free(out->scores); free(out->shapes);
+    out->counts = nullptr; out->bboxes = nullptr; out->scores = nullptr; out->shapes = nullptr;
+    out->n_frames = -1;
+    set_err("out of host memory");
+    return false;
+  }
+  size_t o = 0;
+  for (size_t q = 0; q < hits.size(); q++) {
+    if (!keep[q]) continue;
+    const HitRec &h = hits[q];
+    out->bboxes[3 * o] = h.x; out->bboxes[3 * o + 1] = h.y; out->bboxes[3 * o + 2] = h.win;
+    out->scores[o] = h.score;
+    if (raw) memcpy(out->shapes + o * D, h.shape, sizeof(float) * D);
+    else relocate(h.shape, out->shapes + o * D, m.L, h.x, h.y, h.win);
+    o++;
+  }
+  out->total = (int)total;
+  return true;
+}
+
 int detect_batch(Context *c, const unsigned char *frames, const jdaB200Batch &b, jdaResult *results,
-                 jdaB200Stats *stats) {
+                 jdaB200Stats *stats, jdaB200FlatResult *flat = nullptr) {
   std::lock_guard<std::mutex> lock(c->mu);
   int prev_dev = -1;
   cudaGetDevice(&prev_dev);
   std::vector<HitRec> hits;
   const bool ok = run_device(c, frames, b, hits, nullptr, stats != nullptr);
   if (!ok) {
-    for (int f = 0; f < b.n_frames; f++) results[f] = empty_result(c->m.L, -1);
+    for (int f = 0; f < b.n_frames && results; f++) results[f] = empty_result(c->m.L, -1);
+    if (flat) { memset(flat, 0, sizeof *flat); flat->n_frames = -1; flat->landmark_n = c->m.L; }
     if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return -1;
   }
   const auto t0 = std::chrono::steady_clock::now();
-  c->last.detections = finish_frames(c, hits, b.n_frames, (b.flags & JDA_B200_RAW_HITS) != 0, results, nullptr);
+  bool fin = true;
+  if (flat) {
+    fin = finish_flat(c, hits, b.n_frames, (b.flags & JDA_B200_RAW_HITS) != 0, flat);
+    c->last.detections = fin ? flat->total : 0;
+  } else {
+    c->last.detections = finish_frames(c, hits, b.n_frames, (b.flags & JDA_B200_RAW_HITS) != 0, results, nullptr);
+  }
   c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (stats) *stats = c->last;
   if (prev_dev >= 0) cudaSetDevice(prev_dev);
-  return 0;
+  return fin ? 0 : -1;
 }
 
 void add_stats(jdaB200Stats &a, const jdaB200Stats &b) {
@@ -1517,6 +1577,23 @@ int jdaB200JoinCascadorFilterMargins(void *cascador, double *margins, int cap) {
 
 int jdaB200JoinCascadorLevels(int width, int height, int minimum_size, double scale, int *wins, int cap) {
   return enumerate_levels_f64(width, height, minimum_size, scale, wins, cap);
+}
+
+int jdaB200DetectBatchFlat(void *cascador, const unsigned char *frames, const jdaB200Batch *batch,
+                           jdaB200FlatResult *result, jdaB200Stats *stats) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !batch || !result || (!frames && batch->n_frames > 0)) {
+    set_err("null argument");
+    return -2;
+  }
+  return detect_batch(c, frames, *batch, nullptr, stats, result);
+}
+
+void jdaB200FlatResultRelease(jdaB200FlatResult *r) {
+  if (!r) return;
+  free(r->counts); free(r->bboxes); free(r->scores); free(r->shapes);
+  r->counts = nullptr; r->bboxes = nullptr; r->scores = nullptr; r->shapes = nullptr;
+  r->total = 0;
 }
 
 void jdaB200ResultsRelease(jdaResult *results, int n) {

@@ -36,6 +36,17 @@ def pack_records(results, frame0=0, landmark_n=27):
     return rec
 
 
+def pack_records_flat(counts, boxes, scores, shapes, frame0=0):
+    """the same records from a flat batch result (api.Cascador.detect_batch(flat=True) / jdaB200DetectBatchFlat)"""
+    n = len(scores)
+    rec = np.empty((n, HEADER + shapes.shape[1]), np.float32)
+    rec[:, 0] = np.repeat(np.arange(len(counts)) + frame0, counts)
+    rec[:, 1:4] = boxes
+    rec[:, 4] = scores
+    rec[:, HEADER:] = shapes
+    return rec
+
+
 def unpack_records(rec):
     """records -> (frame ids, boxes i32, scores, shapes)."""
     return (rec[:, 0].astype(np.int64), rec[:, 1:4].astype(np.int32), rec[:, 4].copy(),

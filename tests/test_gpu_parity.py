@@ -253,6 +253,23 @@ def test_batch_equals_per_frame(casc, oracle, oracle_shipped):
         _same(res[f], oracle.detect(oracle_shipped, frames[f], max_size=192, th=-0.5))
 
 
+def test_flat_batch_result_equals_per_frame_results(casc):
+    """jdaB200DetectBatchFlat: one result for the batch = the per-frame jdaResults back to back"""
+    from jda_b200 import shard
+    frames = synth.make_frames("facemix", 24, 320, 240, seed0=60)
+    for kw in (dict(th=-0.5), dict(th=0.0, flags=api.RAW_HITS | api.NO_FINAL_TH, t_limit=2)):
+        per = casc.detect_batch(frames, **kw)
+        counts, boxes, scores, shapes = casc.detect_batch(frames, flat=True, **kw)
+        assert counts.tolist() == [len(r[1]) for r in per] and counts.sum() == len(scores) >= 3
+        _same((boxes, scores, shapes), (np.concatenate([r[0] for r in per]), np.concatenate([r[1] for r in per]),
+                                        np.concatenate([r[2] for r in per])))
+        a = shard.pack_records(per, frame0=100, landmark_n=casc.L)
+        b = shard.pack_records_flat(counts, boxes, scores, shapes, frame0=100)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    empty = casc.detect_batch(synth.make_frames("noise", 3, 64, 48), flat=True)
+    assert empty[0].tolist() == [0, 0, 0] and empty[1].shape == (0, 3) and empty[3].shape == (0, 54)
+
+
 def test_device_resident_frames(casc):
     import torch
     frames = synth.make_frames("facemix", 6, seed0=60)

@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
     import ctypes
     hdr = open(os.path.join(ROOT, "include", "jda_b200.h")).read()
     declared = re.findall(r"JDA_API\s+[\w\s\*]+?\b(jda\w+)\s*\(", hdr)
-    assert len(declared) >= 20 and set(declared) == set(api.EXPORTS)
+    assert len(declared) >= 27 and set(declared) == set(api.EXPORTS)
     L = ctypes.CDLL(api.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
