@@ -525,9 +525,6 @@ struct Run {
   size_t hq_stride;
 };
 
-// Frames to HBM.  Device input is used in place; host input goes into a 16-byte-pitched store: large batches
-// in kMaxChunks pieces on the copy stream (the scan of chunk i then overlaps the copy of chunk i+1), a small
-// pageable input repacked through pinned staging (the driver's pageable path costs more than a one-frame detect).
 // mixed-size batch: host -> canvas slots for the frames of chunk `ch` (each chunk once per call).  Every frame is
 // copied as one contiguous blob into the packed staging area (frames that are neighbours in host memory share a
 // copy), then k0_unpack spreads the chunk over its canvas slots; all on the copy stream.
@@ -561,6 +558,9 @@ bool copy_mixed_chunk(Run &R, int ch) {
   return true;
 }
 
+// Frames to HBM.  Device input is used in place; host input goes into a 16-byte-pitched store: large batches
+// in kMaxChunks pieces on the copy stream (the scan of chunk i then overlaps the copy of chunk i+1), a small
+// pageable input repacked through pinned staging (the driver's pageable path costs more than a one-frame detect).
 bool stage_frames(Run &R, const unsigned char *frames) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;

@@ -34,6 +34,9 @@ def test_pack_unpack_roundtrip():
     np.testing.assert_array_equal(boxes, np.concatenate([r[0] for r in res]))
     np.testing.assert_array_equal(scores, np.concatenate([r[1] for r in res]))
     np.testing.assert_array_equal(shapes, np.concatenate([r[2] for r in res]))
+    # the flat batch result (jdaB200DetectBatchFlat) packs to the same records
+    flat = shard.pack_records_flat(np.array([len(r[1]) for r in res]), boxes, scores, shapes, frame0=2840)
+    np.testing.assert_array_equal(flat.view(np.uint32), rec.view(np.uint32))
 
 
 def _frames():
