@@ -327,7 +327,7 @@ double estimate_wavefronts(int win, int step, int tw, int th, int pitch) {
 }
 
 const char *kDefaultPitchExtra = "";
-int g_min_tile_windows = 64;
+int g_min_tile_windows = 128;  // a tile with fewer windows per warp pools buffers instead (win 46 on VGA: -1.8 % scan time, r1n)
 int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflict model (measured: no gain, r1)
 
 // Per-level tile shapes.  A level runs from private shared-memory tiles when a tile of at least
@@ -390,7 +390,7 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2
   return best_windows;
 }
 
-// Per-level tile shapes.  A level runs from shared-memory tiles when a tile of at least 64 windows
+// Per-level tile shapes.  A level runs from shared-memory tiles when a tile of at least 128 windows
 // (with its 16-byte-granular pixel box) fits a warp's 8 KB buffer -- or, for coarser levels, the
 // buffers of 2 or 4 neighbouring warps (only every 2nd / 4th warp then works on that level).  Levels
 // that fit neither read pixels from global memory in "virtual" tiles of 32 x 16 windows.
