@@ -320,9 +320,9 @@ def main():
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak,
                            # dram__bytes_read+write of k2_scan from the committed ncu capture
-                           # (profiles/r1_final_metrics_k2_k3.txt: 106.0 MB read + 26.1 MB written for a 256-frame
+                           # (profiles/r1p_metrics_k2_k3.txt: 110.1 MB read + 27.8 MB written for a 256-frame
                            # launch: the frames, the tables, the survivors' leaf records), scaled to B frames
-                           "traffic": (106.0e6 + 26.1e6) / 256 * B, "kernel": "k2_scan",
+                           "traffic": (110.1e6 + 27.8e6) / 256 * B, "kernel": "k2_scan",
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                            "note": "logical (algorithmic touched) bytes: 118 B x carts/window + 216 B; data is "
                                    "served from shared memory/L2 so frac may exceed 1; compulsory DRAM is "
@@ -331,15 +331,15 @@ def main():
                            "k2_windows_per_s": B * WINDOWS_PER_FRAME / k2_s}
         # The unit that actually binds k2_scan is the shared-memory data pipe: 1 wavefront / clk / SM (measured:
         # tools/probes/lds_probe.cu -> profiles/r1g_lds_probe.txt).  Wavefronts per window come from the committed ncu
-        # capture of this workload (profiles/r1b_metrics_k2_k3.txt: 2.479e9 shared wavefronts for 256 frames, of
-        # which 1.004e9 are bank-conflict replays); the rate is this run's.
-        wf_per_window = 2.479392042e9 / (256 * WINDOWS_PER_FRAME)
+        # capture of this workload (profiles/r1p_metrics_k2_k3.txt: 2.412e9 shared wavefronts for 256 frames, of
+        # which 0.951e9 are bank-conflict replays); the rate is this run's.
+        wf_per_window = 2.411590994e9 / (256 * WINDOWS_PER_FRAME)
         sm_hz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
         wf_rate = wf_per_window * B * WINDOWS_PER_FRAME / k2_s
         out["roofline_onchip"] = {"bound": "shared-memory data pipe (LSU wavefronts)", "kernel": "k2_scan",
                                   "achieved": wf_rate / 1e12, "peak": 148 * sm_hz / 1e12, "unit": "Twavefronts/s",
                                   "frac": wf_rate / (148 * sm_hz),
-                                  "wavefronts_per_window": wf_per_window, "bank_conflict_share": 1.003793761 / 2.479392042,
+                                  "wavefronts_per_window": wf_per_window, "bank_conflict_share": 0.950957148 / 2.411590994,
                                   "peak_source": "1 wavefront/clk/SM measured by tools/probes/lds_probe.cu x 148 SMs x SM clock",
                                   "note": "wavefronts/window from the committed ncu capture of the same workload, rate from this run"}
         if not a.no_cpu_baseline and world == 1:  # the reported CPU baseline is an N=1 item
