@@ -163,6 +163,7 @@ struct Context {
 };
 
 constexpr size_t kEagerHits = 64;
+constexpr double kLevelWeightExp = 0.0;  // 0: the flat 1.0 / 1.4 / 2.2 weights
 constexpr int kLatencyFrames = 4;  // batches this small use the latency tile plan
 constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntWork = kCntSurv + kMaxChunks, kCntHit = kCntWork + kMaxChunks,
               kCntTotal = kCntHit + 1;
@@ -703,7 +704,11 @@ bool launch_scan(Run &R) {
     double w[kMaxLevels], tot = 0;
     for (int i = 0; i < g.n_levels; i++) {
       const LevelInfo &L = g.lv[g.n_levels - 1 - i];
-      w[i] = (double)L.nx * L.ny * (L.use_smem ? (L.span == 1 ? 1.0 : 1.4) : 2.2);
+      // cost per window grows with the window size (coarse windows survive deeper and their tiles hold fewer windows
+      // per warp): measured per level in profiles/r1m_level_probe.txt, ~ (win / 24)^1.6, global-memory levels x1.6
+      static const double e = getenv("JDA_B200_LEVEL_WEIGHT_EXP") ? atof(getenv("JDA_B200_LEVEL_WEIGHT_EXP")) : kLevelWeightExp;
+      w[i] = (double)L.nx * L.ny * (e > 0 ? std::pow(L.win / 24.0, e) * (L.use_smem ? 1.0 : 1.6)
+                                          : (L.use_smem ? (L.span == 1 ? 1.0 : 1.4) : 2.2));
       tot += w[i];
     }
     double acc = 0;
