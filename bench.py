@@ -320,9 +320,10 @@ def main():
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak,
                            # dram__bytes_read+write of k2_scan from the committed ncu capture
-                           # (profiles/r1p_metrics_k2_k3.txt: 110.1 MB read + 27.8 MB written for a 256-frame
-                           # launch: the frames, the tables, the survivors' leaf records), scaled to B frames
-                           "traffic": (110.1e6 + 27.8e6) / 256 * B, "kernel": "k2_scan",
+                           # (profiles/r1s_metrics_k2_k3.txt: 84.4 MB read + 24.5 MB written for a 256-frame
+                           # launch: the frames, the tables, the survivors' leaf records; 110 + 28 MB in the r1p
+                           # capture -- how much of the batch is still in L2 varies), scaled to B frames
+                           "traffic": (84.4e6 + 24.5e6) / 256 * B, "kernel": "k2_scan",
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                            "note": "logical (algorithmic touched) bytes: 118 B x carts/window + 216 B; data is "
                                    "served from shared memory/L2 so frac may exceed 1; compulsory DRAM is "
@@ -331,7 +332,7 @@ def main():
                            "k2_windows_per_s": B * WINDOWS_PER_FRAME / k2_s}
         # The unit that actually binds k2_scan is the shared-memory data pipe: 1 wavefront / clk / SM (measured:
         # tools/probes/lds_probe.cu -> profiles/r1g_lds_probe.txt).  Wavefronts per window come from the committed ncu
-        # capture of this workload (profiles/r1p_metrics_k2_k3.txt: 2.412e9 shared wavefronts for 256 frames, of
+        # capture of this workload (profiles/r1s_metrics_k2_k3.txt: 2.412e9 shared wavefronts for 256 frames, of
         # which 0.951e9 are bank-conflict replays); the rate is this run's.
         wf_per_window = 2.411590994e9 / (256 * WINDOWS_PER_FRAME)
         sm_hz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
