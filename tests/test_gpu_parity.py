@@ -339,8 +339,7 @@ def test_mixed_sizes_edge_cases(casc, oracle, oracle_shipped):
 
 
 def test_mixed_sizes_large_batch_chunked(casc, oracle, oracle_shipped):
-    """>= 128 mixed frames: the per-frame copies are split in chunks that overlap the scans; sampled frames vs oracle,
-    and a model that cannot use the canvas path (scaled nodes) falls back to per-shape batches with the same API"""
+    """>= 128 mixed frames: the per-frame copies are split in chunks that overlap the scans; sampled frames vs oracle"""
     shapes = [synth.fddb_shape(s) for s in range(7)]
     frames = [synth.facemix_frame(800 + i, *[d // 2 for d in shapes[i % 7]]) for i in range(140)]
     got = casc.detect_mixed(frames, th=-0.5)
@@ -351,6 +350,27 @@ def test_mixed_sizes_large_batch_chunked(casc, oracle, oracle_shipped):
     again = casc.detect_mixed(frames[::-1], th=-0.5)
     for a, b in zip(got, again[::-1]):
         _same(a, b)
+
+
+def test_mixed_sizes_without_the_canvas_path(casc, oracle, oracle_shipped, tmp_path):
+    """models / flags that cannot share a canvas launch (h / q planes differ per frame size, or no stage-0 scan):
+    jdaB200DetectMixed then runs one batch per distinct shape internally -- same API, same answers"""
+    frames = [synth.blur_frame(9, 96, 80), synth.noise_frame(5, 70, 61), synth.blur_frame(10, 96, 80),
+              synth.facemix_frame(4, 120, 90), synth.noise_frame(2, 20, 30)]
+    path = synth.write_model(str(tmp_path / "scaled.model"), seed=3, mode="reject", scales=(0, 1, 2), coord_max=0.45)
+    c = api.Cascador(path, double=True)
+    ho = oracle.load(path, True)
+    got = c.detect_mixed(frames, th=-1e30)
+    assert c.last_stats["scan_launches"] == 0 and c.last_stats["cascade_launches"] >= 3
+    assert c.last_stats["windows"] == sum(api.count_windows(f.shape[1], f.shape[0]) for f in frames)
+    for g, f in zip(got, frames):
+        _same(g, oracle.detect(ho, f, th=-1e30))
+    c.close(); oracle.release(ho)
+    big = [synth.facemix_frame(41, 300, 200), synth.facemix_frame(43, 130, 380), synth.facemix_frame(41, 300, 200)]
+    got = casc.detect_mixed(big, th=-0.5, flags=api.NO_STAGE0_SCAN)
+    assert casc.last_stats["scan_launches"] == 0
+    for g, f in zip(got, big):
+        _same(g, oracle.detect(oracle_shipped, f, th=-0.5))
 
 
 def test_chunked_host_batch_equals_resident(casc, oracle, oracle_shipped):
