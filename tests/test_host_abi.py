@@ -101,6 +101,14 @@ def test_detect_without_gpu_fails_loudly():
     with pytest.raises(RuntimeError, match="no CUDA device"):
         c.detect_mixed([synth.noise_frame(0, 64, 48), synth.noise_frame(1, 50, 70)])
     assert c.detect_mixed([]) == []          # nothing to do: no device needed, no failure
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        c.detect_batch(synth.make_frames("noise", 2, 64, 48), flat=True)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        c.detect_cpp(synth.noise_frame(0, 64, 48))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        c.trace_cpp(synth.noise_frame(0, 64, 48))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        c.trace(synth.noise_frame(0, 64, 48))
     c.close()
 
 
