@@ -179,7 +179,6 @@ int chunk_begin(int n_frames, int ch, int nchunks) {
 }
 
 size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * K2_WARP_BYTES; }
-size_t k2g_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2G_WARPS * sizeof(WarpLists); }
 size_t k3s_smem_bytes(int K, int D) {
   return (size_t)K3S_COHORT * ((K + 15) & ~15) + (size_t)2 * K3S_CHUNK * kLeaves * D * 4;
 }
@@ -241,11 +240,6 @@ bool ctx_init(Context *c) {
   CU_OK(cudaFuncSetAttribute(k2_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-  {
-    const size_t sg = k2g_smem_bytes(std::min((c->m.K * kCartBytes + 127) & ~127, kMaxStage0TableBytes));
-    CU_OK(cudaFuncSetAttribute(k2g_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg));
-    CU_OK(cudaFuncSetAttribute(k2g_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg));
-  }
   CU_OK(cudaFuncSetAttribute(k2_scan<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
@@ -353,8 +347,6 @@ int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflic
 // the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
 // pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
 int g_latency_tile_windows = 256;
-constexpr int kSplitGlobalDefault = 0;
-int g_split_global = kSplitGlobalDefault;  // 1: global-memory levels get small virtual tiles and their own kernel (k2g_scan)
 int g_max_span = -1;  // -1: by mode (throughput plan: up to 4 warps' buffers; latency plan: the whole block's)
 
 // Extra tile pitch per window size.  The pitch decides how a tile's window rows fold onto the 32 banks, i.e. how
@@ -417,10 +409,6 @@ void plan_level(LevelInfo &L, bool latency) {
   if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
   if (const char *e = getenv("JDA_B200_TUNE_PITCH")) g_tune_pitch = atoi(e);
   if (const char *e = getenv("JDA_B200_MAX_SPAN")) g_max_span = std::max(1, atoi(e));
-  {
-    const char *e = getenv("JDA_B200_SPLIT_GLOBAL");
-    g_split_global = e ? (atoi(e) ? 1 : 0) : kSplitGlobalDefault;
-  }
   if (const char *e = getenv("JDA_B200_LATENCY_TILE")) g_latency_tile_windows = std::max(64, std::min(K2_LIST_CAP, atoi(e)));
   // Two plans.  Throughput (many frames in flight): coarse levels pool at most 4 warps' buffers, what is
   // left reads global memory in 512-window virtual tiles -- measured fastest on 128+ frame batches.
@@ -450,7 +438,7 @@ void plan_level(LevelInfo &L, bool latency) {
     }
     L = pick;
   }
-  if (!L.use_smem) { L.tw_log2 = 5; L.th = (latency || g_split_global) ? 4 : K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0; }  // global-memory virtual tiles
+  if (!L.use_smem) { L.tw_log2 = 5; L.th = latency ? 4 : K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0; }  // global-memory virtual tiles
   const int tw = 1 << L.tw_log2;
   L.ntx = (L.nx + tw - 1) / tw;
   L.nty = (L.ny + L.th - 1) / L.th;
@@ -722,10 +710,6 @@ bool launch_scan(Run &R) {
   int n_smem = 0;
   for (int i = 0; i < g.n_levels; i++) n_smem += g.lv[i].use_smem;
   st.levels_smem = n_smem;
-  // the global-memory levels go to their own high-occupancy kernel in batch mode (not when tracing: the trace
-  // instantiation keeps everything in k2_scan; not for a handful of frames: the latency plan pools whole blocks)
-  const bool split = g_split_global && !R.tracing && !R.latency_plan && n_smem < g.n_levels && n_smem > 0;
-  P.split_global = split ? 1 : 0;
   {  // share of the scan work per level, in processing order (coarse -> fine)
     double w[kMaxLevels], tot = 0;
     for (int i = 0; i < g.n_levels; i++) {
@@ -735,7 +719,6 @@ bool launch_scan(Run &R) {
       static const double e = getenv("JDA_B200_LEVEL_WEIGHT_EXP") ? atof(getenv("JDA_B200_LEVEL_WEIGHT_EXP")) : kLevelWeightExp;
       w[i] = (double)L.nx * L.ny * (e > 0 ? std::pow(L.win / 24.0, e) * (L.use_smem ? 1.0 : 1.6)
                                           : (L.use_smem ? (L.span == 1 ? 1.0 : 1.4) : 2.2));
-      if (split && !L.use_smem) w[i] = 0;  // k2g_scan's levels
       tot += w[i];
     }
     double acc = 0;
@@ -773,13 +756,6 @@ bool launch_scan(Run &R) {
     }
     if (R.mixed && !copy_mixed_chunk(R, ch)) return false;  // no-op unless an earlier chunk was empty
     if (R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[ch], 0));
-    if (split) {
-      const size_t sg = k2g_smem_bytes(g.table_bytes);
-      if (R.mixed) k2g_scan<2, true><<<grid, K2G_WARPS * 32, sg, R.s>>>(P);
-      else k2g_scan<2, false><<<grid, K2G_WARPS * 32, sg, R.s>>>(P);
-      CU_OK(cudaGetLastError());
-      st.scan_launches++;
-    }
     if (R.tracing) {
       if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
       else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);

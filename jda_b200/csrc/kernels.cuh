@@ -83,7 +83,6 @@ struct ScanParams {
   short sched[K2_MAX_SCHED];     // cart index at which each phase ends; last == K
   int use_tma;
   int stragglers;                // 1: finish nearly empty tiles in cart-parallel straggler mode
-  int split_global;              // 1: the global-memory levels are scanned by k2g_scan, k2_scan skips them
   float level_cum[kMaxLevels];   // cumulative share of the scan work in processing order (coarse -> fine)
   // trace (TRACE instantiation only)
   int *trace_n;
@@ -609,7 +608,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
     if (pos >= P.n_levels) pos -= P.n_levels;
     const int li = P.n_levels - 1 - pos;
     const LevelInfo &lv = P.lv[li];
-    if (P.split_global && !lv.use_smem) continue;  // k2g_scan's levels (uniform across the block)
     const int tiles_per_frame = lv.ntx * lv.nty;
     const unsigned total = (unsigned)tiles_per_frame * (unsigned)P.n_frames;
     __syncthreads();  // everyone is done with the previous level's table
@@ -723,58 +721,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
         scan_tile<false, NW, TRACE>(P, lv, li, smem, norm_off, tile_off, wl->lscore, wl->lwid, frame, x0w,
                                     y0w, cw, ch, lane);
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------ k2g: global-memory levels
-//
-// The coarsest levels (windows too large for a shared-memory tile: >= 110 px on VGA, 1.9 % of the windows) read
-// their pixels from global memory; inside k2_scan they are ~1 ms chains of dependent L1/L2 reads at 12 warps per
-// SM and take ~11 % of the scan's warp-time (profiles/r1m_level_probe.txt).  This kernel scans only those levels
-// with what they need -- the level's table and the per-warp window lists, no tile buffers -- so 32 warps instead of 12
-// fit an SM and hide that latency, in small virtual tiles (32 x 4 windows) so that every warp gets several.
-// Same scan_tile code, same survivor queue; k2_scan skips these levels when ScanParams::split_global is set.
-constexpr int K2G_WARPS = 32;  // 62 registers per thread at NW = 2: a full 1024-thread block fits the register file
-
-template <int NW, bool MIXED>
-__global__ void __launch_bounds__(K2G_WARPS * 32, 1) k2g_scan(const __grid_constant__ ScanParams P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ int s_skip;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t table_sz = (uint32_t)(P.table_bytes + 127) & ~127u;
-  const uint32_t norm_off = table_sz;
-  WarpLists *wl = reinterpret_cast<WarpLists *>(smem + table_sz + 256u) + warp;
-  for (int i = threadIdx.x; i < kMaxNorm * 2; i += blockDim.x)
-    reinterpret_cast<float *>(smem + norm_off)[i] = reinterpret_cast<const float *>(P.norms)[i];
-  for (int li = P.n_levels - 1; li >= 0; --li) {  // coarse -> fine
-    const LevelInfo &lv = P.lv[li];
-    if (lv.use_smem) continue;
-    const int tiles_per_frame = lv.ntx * lv.nty;
-    const unsigned total = (unsigned)tiles_per_frame * (unsigned)P.n_frames;
-    __syncthreads();  // everyone is done with the previous level's table
-    if (threadIdx.x == 0) s_skip = *reinterpret_cast<volatile unsigned *>(&P.tile_counters[li]) >= total;
-    __syncthreads();
-    if (s_skip) continue;
-    {
-      const uint4 *src = reinterpret_cast<const uint4 *>(P.tables + lv.table_off);
-      uint4 *dst = reinterpret_cast<uint4 *>(smem);
-      for (int i = threadIdx.x; i < (int)(table_sz / 16); i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    const int tw = 1 << lv.tw_log2;
-    for (;;) {
-      unsigned item = 0;
-      if (lane == 0) item = atomicAdd(&P.tile_counters[li], 1u);
-      item = __shfl_sync(0xffffffffu, item, 0);
-      if (item >= total) break;
-      const int frame = item / tiles_per_frame;
-      const int r = item - frame * tiles_per_frame;
-      const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
-      const int x0w = tx * tw, y0w = ty * lv.th;
-      int cw, ch;
-      if (!tile_extent<MIXED>(P, lv, frame, x0w, y0w, cw, ch)) continue;
-      scan_tile<false, NW, false>(P, lv, li, smem, norm_off, 0u, wl->lscore, wl->lwid, frame, x0w, y0w, cw, ch, lane);
     }
   }
 }

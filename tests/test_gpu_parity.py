@@ -119,35 +119,6 @@ def test_scan_kernel_variants(oracle, oracle_shipped, nw, stragglers):
         del os.environ["JDA_B200_STRAGGLERS"]
 
 
-@pytest.mark.parametrize("split", ["1", "0"])
-def test_global_memory_levels_kernel(oracle, oracle_shipped, split):
-    """JDA_B200_SPLIT_GLOBAL: the levels whose windows do not fit a shared-memory tile are scanned by k2g_scan
-    (32 warps per SM, small virtual tiles) instead of inside k2_scan -- a scheduling choice, same bits"""
-    os.environ["JDA_B200_SPLIT_GLOBAL"] = split
-    try:
-        c = api.Cascador(SHIPPED_F32, double=False)
-        frames = synth.make_frames("facemix", 7, 640, 480, seed0=20)        # full ladder: 7 global-memory levels
-        frames[2] = synth.face_canvas()
-        for g, f in zip(c.detect_batch(frames, th=0.0, flags=api.RAW_HITS | api.NO_FINAL_TH, t_limit=1), frames):
-            ob, osc, osh, st = oracle.detect_raw(oracle_shipped, f, t_limit=1, use_th=False)
-            _same(g, (ob, osc, osh))
-        assert c.last_stats["scan_launches"] == (2 if split == "1" else 1)
-        for g, f in zip(c.detect_batch(frames, th=-0.5), frames):
-            _same(g, oracle.detect(oracle_shipped, f, th=-0.5))
-        mixed = [synth.facemix_frame(41, 300, 200), synth.facemix_frame(43, 130, 380), synth.noise_frame(3, 23, 40),
-                 synth.facemix_frame(44, 450, 229), synth.facemix_frame(45, 229, 450), synth.blur_frame(5, 24, 24)]
-        for g, f in zip(c.detect_mixed(mixed, th=-0.5), mixed):
-            _same(g, oracle.detect(oracle_shipped, f, th=-0.5))
-        big = synth.make_frames("noise", 130, 200, 150, seed0=300)            # chunked host batch: 4 x 2 launches
-        got = c.detect_batch(big, th=-1.0)
-        assert c.last_stats["scan_launches"] == (8 if split == "1" else 4)
-        for i in (0, 64, 129):
-            _same(got[i], oracle.detect(oracle_shipped, big[i], th=-1.0))
-        c.close()
-    finally:
-        del os.environ["JDA_B200_SPLIT_GLOBAL"]
-
-
 def test_tile_origins_not_multiple_of_16(oracle, oracle_shipped):
     """Tiles whose x origin is not 16-byte aligned (8-wide tiles at step 5: origin 40*tx): the TMA box starts
     at the aligned address below and the windows are addressed with the remainder."""
