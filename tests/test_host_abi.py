@@ -140,3 +140,48 @@ def test_cli_convert_and_info(tmp_path, capsys):
     assert main(["info", str(out), "--float", "--size", "640x480", "--max-size", "192"]) == 0
     txt = capsys.readouterr().out
     assert "169236 candidate windows" in txt and "T=5 K=540 landmarks=27" in txt
+
+
+REF_HEADER_DIR = "/root/reference/c"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_HEADER_DIR, "jda.h")), reason="reference header not present on this box")
+def test_c_program_built_against_the_reference_header_runs_on_our_library(tmp_path):
+    """drop-in at the link level: a C99 program compiled against the REFERENCE's own c/jda.h (not ours) links to
+    libjda_b200.so and its host-only calls behave -- load, serialise (byte-identical), release, NULL safety"""
+    import subprocess
+    src = tmp_path / "prog.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "jda.h"
+int main(int argc, char **argv) {
+  void *c = jdaCascadorCreateFloat(argv[1]);
+  if (!c) return 2;
+  jdaCascadorSerializeTo(c, argv[2]);
+  jdaCascadorRelease(c);
+  jdaCascadorRelease(NULL);
+  if (jdaCascadorCreateDouble("/nonexistent/model") != NULL) return 3;
+  jdaResult r; r.n = 0; r.landmark_n = 27; r.bboxes = NULL; r.shapes = NULL; r.scores = NULL;
+  jdaResultRelease(r);
+  printf("sizeof(jdaResult)=%d\n", (int)sizeof(jdaResult));
+  return 0;
+}
+''')
+    exe = tmp_path / "prog"
+    libdir = os.path.dirname(api.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", REF_HEADER_DIR, str(src), "-o", str(exe),
+                    "-L", libdir, "-l:" + os.path.basename(api.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    out = tmp_path / "rt.model"
+    p = subprocess.run([str(exe), SHIPPED_F32, str(out)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "sizeof(jdaResult)=32" in p.stdout
+    assert out.read_bytes() == open(SHIPPED_F32, "rb").read()
+
+
+def test_our_header_is_plain_c(tmp_path):
+    """include/jda_b200.h compiles as C99 and as C++ with nothing but the standard headers"""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+        subprocess.run(["gcc", "-x", lang, std, "-Wall", "-Werror", "-fsyntax-only", "-I", inc,
+                        os.path.join(inc, "jda_b200.h")], check=True)
