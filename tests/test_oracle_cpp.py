@@ -3,8 +3,9 @@ fddb.method = 1) and the host logic of its CUDA counterpart.  No GPU needed.
 
 PARITY UNPINNED: the C++ detector cannot be built in this image (OpenCV C++ headers, jsmnpp config), the reference
 ships no golden vectors for it.  What is checked here: the restatement against independent restatements of its
-pieces (multimap NMS, window ladder), its known answers as regression pins, and the error bound that lets the
-float32 scan kernel prefilter stage 0 of the double path.
+pieces (multimap NMS, window ladder) and of the whole of Validate (a from-scratch Python restatement that parses the
+model file itself: per-window cart counts, exit scores and landmarks agree bit for bit), its known answers as
+regression pins, and the error bound that lets the float32 scan kernel prefilter stage 0 of the double path.
 """
 import numpy as np
 import pytest
@@ -183,3 +184,83 @@ def test_synthetic_double_models(ocpp, tmp_path):
     tn, ts = ocpp.trace(h, img)
     assert tn.max() <= 2 * 540 + 18
     ocpp.release(h)
+
+
+def _py_validate(img, x, y, win, mean, nodes, leaf, cart3, w, T, K):
+    """second, independent restatement (pure Python / numpy float64) of JoinCascador::Validate for a finished model:
+    cascador.cpp:166-211, cart.cpp:392-404 (1-based heap), data.cpp:18-58 (round, clamp), btcart.cpp:407-424"""
+    import math
+    shape = mean + 0.0
+    score, n = 0.0, 0
+    for t in range(T):
+        lbf = []
+        for k in range(K):
+            c = t * K + k
+            node_idx = 1
+            for _ in range(3):
+                scale, l1, l2, o1x, o1y, o2x, o2y, th = nodes[c][node_idx - 1]
+                assert scale == 0
+                pts = []
+                for s, o in ((shape[2 * l1], o1x), (shape[2 * l1 + 1], o1y), (shape[2 * l2], o2x), (shape[2 * l2 + 1], o2y)):
+                    v = (s + o) * win
+                    r = int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)      # C round(): half away from zero
+                    pts.append(min(max(r, 0), win - 1))
+                val = int(img[y + pts[1], x + pts[0]]) - int(img[y + pts[3], x + pts[2]])
+                node_idx = 2 * node_idx if val <= th else 2 * node_idx + 1
+            idx = node_idx - 8
+            score += leaf[c][idx]
+            score = (score - cart3[c][1]) / cart3[c][2]
+            n += 1
+            if score < cart3[c][0]:
+                return False, score, n, None
+            lbf.append(8 * k + idx)
+        delta = np.zeros_like(shape)
+        for row in lbf:
+            delta = delta + w[t][row]
+        shape = shape + delta
+    return True, score, n, shape
+
+
+def test_second_independent_restatement_agrees(ocpp, ocpp_shipped):
+    """the C restatement against a from-scratch Python one that parses the model file itself: per-window carts
+    evaluated and exit score (bit for bit), and the faces' landmarks"""
+    raw = open(SHIPPED_F32, "rb").read()
+    T, K, L = 5, 540, 27
+    o = 28
+    mean = np.frombuffer(raw, "<f4", 2 * L, o).astype(np.float64); o += 8 * L
+    nodes, leaf, cart3, w = [], [], [], []
+    for t in range(T):
+        for k in range(K):
+            nd = []
+            for i in range(7):
+                ints = np.frombuffer(raw, "<i4", 3, o); fl = np.frombuffer(raw, "<f4", 4, o + 12)
+                th = int(np.frombuffer(raw, "<i4", 1, o + 28)[0])
+                nd.append((int(ints[0]), int(ints[1]), int(ints[2]), float(fl[0]), float(fl[1]), float(fl[2]), float(fl[3]), th))
+                o += 32
+            nodes.append(nd)
+            leaf.append(np.frombuffer(raw, "<f4", 8, o).astype(np.float64)); o += 32
+            cart3.append(np.frombuffer(raw, "<f4", 3, o).astype(np.float64)); o += 12
+        w.append(np.frombuffer(raw, "<f4", 8 * K * 2 * L, o).astype(np.float64).reshape(8 * K, 2 * L)); o += 4 * 8 * K * 2 * L
+    assert o + 4 == len(raw)
+    face = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "face_111x108.npy"))
+    img = np.ascontiguousarray(face[10:60, 20:62])             # 42 x 50 crop: a handful of 20..39 px windows
+    tn, ts = ocpp.trace(ocpp_shipped, img)
+    wins = ocpp.levels(img.shape[1], img.shape[0])
+    i = 0
+    faces = []
+    for win in wins:
+        for y in range(0, img.shape[0] - win + 1, 5):
+            for x in range(0, img.shape[1] - win + 1, 5):
+                ok, score, n, shape = _py_validate(img, x, y, win, mean, nodes, leaf, cart3, w, T, K)
+                assert n == tn[i], (i, n, tn[i])
+                assert np.float64(score).view(np.uint64) == ts[i].view(np.uint64), (i, score, ts[i])
+                if ok:
+                    faces.append((x, y, win, shape))
+                i += 1
+    assert i == len(tn) and i >= 30
+    rects, scores, shapes, _ = ocpp.detect(ocpp_shipped, img, nms=False)
+    assert len(faces) == len(scores)
+    for (x, y, win, shape), r, sh in zip(faces, rects, shapes):
+        assert (x, y, win) == (r[0], r[1], r[2])
+        want = shape.copy(); want[0::2] = x + shape[0::2] * win; want[1::2] = y + shape[1::2] * win
+        np.testing.assert_array_equal(want.view(np.uint64), sh.view(np.uint64))
