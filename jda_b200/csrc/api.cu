@@ -100,6 +100,46 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 constexpr int kMaxChunks = 4;  // host batches are copied and scanned in up to 4 overlapping chunks
 
+// A/B knobs and test hooks, read from the environment ONCE per handle (ctx_init) -- never on the call path.
+// None of them changes results; the test hooks only force rarely taken host paths (queue growth, unchunked copies).
+struct Tuning {
+  int nw = 4;                     // JDA_B200_NW: windows per lane in k2_scan (1, 2, 4)
+  int stragglers = 1;             // JDA_B200_STRAGGLERS
+  int min_tile_windows = 128;     // JDA_B200_MIN_TILE_WINDOWS: a tile with fewer windows per warp pools buffers instead (r1n)
+  int max_span = -1;              // JDA_B200_MAX_SPAN: -1 = by plan (throughput: up to 4 warps' buffers; latency: the whole block's)
+  int latency_tile_windows = 256; // JDA_B200_LATENCY_TILE
+  int tune_pitch = 0;             // JDA_B200_TUNE_PITCH: also try wider pitches and pick by the bank-conflict model (no gain, r1)
+  std::string pitch_extra;        // JDA_B200_PITCH_EXTRA="24:16,30:32": extra tile pitch per window size (A/B)
+  bool even_chunks = false;       // JDA_B200_EVEN_CHUNKS
+  bool no_chunks = false;         // JDA_B200_NO_CHUNKS (test hook)
+  bool tiny_queues = false;       // JDA_B200_TINY_QUEUES (test hook: start with queues that overflow)
+  double level_weight_exp = 1.0;  // JDA_B200_LEVEL_WEIGHT_EXP (r1q: scan -1.7 % against flat weights)
+  std::string sched;              // JDA_B200_SCHED="4,8,16,...": phase ends of k2_scan
+};
+
+Tuning read_tuning() {
+  Tuning t;
+  auto geti = [](const char *name, int &v) { if (const char *e = getenv(name)) v = atoi(e); };
+  int nw = t.nw;
+  geti("JDA_B200_NW", nw);
+  if (nw == 1 || nw == 2 || nw == 4) t.nw = nw;
+  geti("JDA_B200_STRAGGLERS", t.stragglers);
+  t.stragglers = t.stragglers ? 1 : 0;
+  geti("JDA_B200_MIN_TILE_WINDOWS", t.min_tile_windows);
+  t.min_tile_windows = std::max(1, t.min_tile_windows);
+  if (getenv("JDA_B200_MAX_SPAN")) { geti("JDA_B200_MAX_SPAN", t.max_span); t.max_span = std::max(1, t.max_span); }
+  geti("JDA_B200_LATENCY_TILE", t.latency_tile_windows);
+  t.latency_tile_windows = std::max(64, std::min(K2_LIST_CAP, t.latency_tile_windows));
+  geti("JDA_B200_TUNE_PITCH", t.tune_pitch);
+  if (const char *e = getenv("JDA_B200_PITCH_EXTRA")) t.pitch_extra = e;
+  t.even_chunks = getenv("JDA_B200_EVEN_CHUNKS") != nullptr;
+  t.no_chunks = getenv("JDA_B200_NO_CHUNKS") != nullptr;
+  if (const char *e = getenv("JDA_B200_TINY_QUEUES")) t.tiny_queues = atoi(e) != 0;
+  if (const char *e = getenv("JDA_B200_LEVEL_WEIGHT_EXP")) t.level_weight_exp = atof(e);
+  if (const char *e = getenv("JDA_B200_SCHED")) t.sched = e;
+  return t;
+}
+
 struct Context {
   HostModel m;
   std::mutex mu;
@@ -156,24 +196,22 @@ struct Context {
   DevBuf<int> d_trace_n64;
   size_t hit64_cap = 0;
   std::vector<double> h_hits64;
-  int nw = 4;
-  int stragglers = 1;
+  Tuning tune;
+  bool model64_ready = false;
   std::vector<short> sched;
   cudaStream_t stream() const { return user_stream ? user_stream : own_stream; }
 };
 
 constexpr size_t kEagerHits = 64;
-constexpr double kLevelWeightExp = 1.0;  // measured r1q: scan -1.7 % against the flat 1.0 / 1.4 / 2.2 weights (exponent 0)
 constexpr int kLatencyFrames = 4;  // batches this small use the latency tile plan
 constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntWork = kCntSurv + kMaxChunks, kCntHit = kCntWork + kMaxChunks,
               kCntTotal = kCntHit + 1;
 
 // First frame of chunk `ch` when a host batch is copied and scanned in `nchunks` pieces.  The pieces grow
 // (1/8, 2/8, 2/8, 3/8 of the batch): the first scan can only start when the first piece has landed, so it is small.
-int chunk_begin(int n_frames, int ch, int nchunks) {
+int chunk_begin(int n_frames, int ch, int nchunks, bool even = false) {
   if (nchunks != kMaxChunks) return (int)((long long)n_frames * ch / nchunks);
   static const int cum[kMaxChunks + 1] = {0, 1, 3, 5, 8};
-  static const bool even = getenv("JDA_B200_EVEN_CHUNKS") != nullptr;
   if (even) return (int)((long long)n_frames * ch / nchunks);
   return (int)((long long)n_frames * cum[ch] / 8);
 }
@@ -184,11 +222,9 @@ size_t k3s_smem_bytes(int K, int D) {
 }
 size_t k3_smem_bytes(int K) { return (size_t)K3_WARPS * (kMaxDim * 4 + ((K + 15) & ~15)); }
 
-bool ctx_init(Context *c) {
-  if (c->inited) {
-    CU_OK(cudaSetDevice(c->device));
-    return true;
-  }
+void ctx_release_device(Context *c);
+
+bool ctx_init_impl(Context *c) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_err("no CUDA device visible: libjda_b200 has no CPU path");
@@ -251,14 +287,10 @@ bool ctx_init(Context *c) {
   CU_OK(cudaFuncSetAttribute(k3_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   CU_OK(cudaFuncSetAttribute(k3_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   // tuning knobs (not behaviour): windows per lane and the phase schedule of k2_scan
-  if (const char *e = getenv("JDA_B200_NW")) {
-    int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) c->nw = v;
-  }
-  if (const char *e = getenv("JDA_B200_STRAGGLERS")) c->stragglers = atoi(e) ? 1 : 0;
+  c->tune = read_tuning();
   c->sched.clear();
-  if (const char *e = getenv("JDA_B200_SCHED")) {
-    const char *p = e;
+  if (!c->tune.sched.empty()) {
+    const char *p = c->tune.sched.c_str();
     while (*p) {
       int v = (int)strtol(p, (char **)&p, 10);
       if (v > 0 && v < m.K && (c->sched.empty() || v > c->sched.back()) && c->sched.size() < K2_MAX_SCHED - 1)
@@ -271,28 +303,66 @@ bool ctx_init(Context *c) {
       if (v < m.K) c->sched.push_back((short)v);
   }
   c->sched.push_back((short)m.K);
+  return true;
+}
+
+// Device state is all-or-nothing: a failure half way through releases what was created, so a retry starts clean
+// and nothing leaks (`inited` is set only after every step succeeded).
+bool ctx_init(Context *c) {
+  if (c->inited) {
+    CU_OK(cudaSetDevice(c->device));
+    return true;
+  }
+  if (!ctx_init_impl(c)) {
+    const std::string keep = g_err;
+    ctx_release_device(c);
+    g_err = keep;
+    return false;
+  }
   c->inited = true;
   return true;
 }
 
+template <typename T>
+void dev_free(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+template <typename T>
+void host_free(T *&p) {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+}
+
+void release_model64(Context *c) {
+  dev_free(c->d_nodes64); dev_free(c->d_leaf64); dev_free(c->d_cart64); dev_free(c->d_w64); dev_free(c->d_mean64);
+  dev_free(c->d_norms64);
+  c->model64_ready = false;
+}
+
+// frees every device / pinned resource of the handle (safe on a partially initialised one)
+void ctx_release_device(Context *c) {
+  if (c->device >= 0) cudaSetDevice(c->device);
+  dev_free(c->d_nodes); dev_free(c->d_leaf); dev_free(c->d_cart); dev_free(c->d_w); dev_free(c->d_mean);
+  dev_free(c->d_norms); dev_free(c->d_counters);
+  release_model64(c);
+  c->d_tables64.release(); c->d_hits64.release(); c->d_trace_s64.release(); c->d_trace_n64.release();
+  host_free(c->h_counters);
+  host_free(c->h_eager);
+  host_free(c->h_stage);
+  c->d_tables.release(); c->d_dims.release(); c->d_packed.release(); c->d_unpack.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
+  c->d_surv.release(); c->d_shape0.release(); c->d_surv_leaves.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
+  for (auto &e : c->ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+  for (auto &e : c->ev_copy) { if (e) cudaEventDestroy(e); e = nullptr; }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  c->copy_stream = nullptr; c->own_stream = nullptr;
+  c->geo.valid = false; c->geo64.valid = false;
+  cudaGetLastError();
+}
+
 void ctx_free(Context *c) {
-  if (c->inited) {
-    cudaSetDevice(c->device);
-    cudaFree(c->d_nodes); cudaFree(c->d_leaf); cudaFree(c->d_cart); cudaFree(c->d_w); cudaFree(c->d_mean);
-    cudaFree(c->d_norms); cudaFree(c->d_counters);
-    cudaFree(c->d_nodes64); cudaFree(c->d_leaf64); cudaFree(c->d_cart64); cudaFree(c->d_w64); cudaFree(c->d_mean64);
-    cudaFree(c->d_norms64);
-    c->d_tables64.release(); c->d_hits64.release(); c->d_trace_s64.release(); c->d_trace_n64.release();
-    cudaFreeHost(c->h_counters);
-    cudaFreeHost(c->h_eager);
-    cudaFreeHost(c->h_stage);
-    c->d_tables.release(); c->d_dims.release(); c->d_packed.release(); c->d_unpack.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
-    c->d_surv.release(); c->d_shape0.release(); c->d_surv_leaves.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
-    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
-    for (auto &e : c->ev_copy) if (e) cudaEventDestroy(e);
-    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    if (c->own_stream) cudaStreamDestroy(c->own_stream);
-  }
+  ctx_release_device(c);
   delete c;
 }
 
@@ -337,24 +407,18 @@ double estimate_wavefronts(int win, int step, int tw, int th, int pitch) {
   return cnt ? tot / cnt : 1.0;
 }
 
-const char *kDefaultPitchExtra = "";
-int g_min_tile_windows = 128;  // a tile with fewer windows per warp pools buffers instead (win 46 on VGA: -1.8 % scan time, r1n)
-int g_tune_pitch = 0;  // 1: also try wider pitches and pick by the bank-conflict model (measured: no gain, r1)
 
 // Per-level tile shapes.  A level runs from private shared-memory tiles when a tile of at least
 // 64 windows (with its 16-byte-granular pixel box) fits the per-warp scratch; otherwise its windows
 // read pixels from global memory in "virtual" tiles of 32 x 16 windows.  Among the shapes that fit,
 // the one with the lowest modelled cost wins: shared-memory wavefronts per cart (4 table reads + 6
 // pixel reads x conflict factor) x a tail factor that favours tiles with more windows.
-int g_latency_tile_windows = 256;
-int g_max_span = -1;  // -1: by mode (throughput plan: up to 4 warps' buffers; latency plan: the whole block's)
 
 // Extra tile pitch per window size.  The pitch decides how a tile's window rows fold onto the 32 banks, i.e. how
 // often the pixel reads of a compacted packet (windows from several rows) collide; the exact model in
 // tests/design_sims/sim_exact_banks.py ranks the candidates.  JDA_B200_PITCH_EXTRA="24:16,30:32" overrides (A/B).
-int pitch_extra(int win) {
-  static const char *env = getenv("JDA_B200_PITCH_EXTRA");
-  const char *p = env ? env : kDefaultPitchExtra;
+int pitch_extra(const Tuning &tn, int win) {
+  const char *p = tn.pitch_extra.c_str();
   while (*p) {
     char *q;
     const long w = strtol(p, &q, 10);
@@ -368,7 +432,7 @@ int pitch_extra(int win) {
 }
 
 // best shared-memory tile for a budget of `tile_bytes`; returns its window count (0 = none fits)
-int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2_LIST_CAP) {
+int plan_tile(const Tuning &tn, LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2_LIST_CAP) {
   double best_cost = 1e30;
   int best_windows = 0;
   tile_bytes = std::min(tile_bytes, 65536);  // one TMA box (<= 256 x 256)
@@ -377,8 +441,8 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2
     // TMA wants the box to start on a 16-byte boundary in x: tiles whose x origin (tx * tw * step) is not
     // a multiple of 16 start their box at the aligned address below it and carry up to 15 spare bytes
     const int slack = ((tw * L.step) % 16 == 0) ? 0 : 15;
-    const int bw0 = ((((tw - 1) * L.step + L.win + slack) + 15) & ~15) + pitch_extra(L.win);
-    for (int bw = bw0; bw <= std::min(256, bw0 + (g_tune_pitch ? 80 : 0)); bw += 16) {
+    const int bw0 = ((((tw - 1) * L.step + L.win + slack) + 15) & ~15) + pitch_extra(tn, L.win);
+    for (int bw = bw0; bw <= std::min(256, bw0 + (tn.tune_pitch ? 80 : 0)); bw += 16) {
       const int bh_max = std::min(256, tile_bytes / bw);
       if (bh_max < L.win) continue;
       int th = (bh_max - L.win) / L.step + 1;
@@ -387,9 +451,9 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2
       const int bh = (th - 1) * L.step + L.win;
       if ((long long)L.win * bw + L.win >= 65536) continue;  // u16 tile offsets
       const int windows = std::min(tw, L.nx) * th;
-      if (windows < (min_tl < 3 ? std::min(g_min_tile_windows, 6) : g_min_tile_windows)) continue;
+      if (windows < (min_tl < 3 ? std::min(tn.min_tile_windows, 6) : tn.min_tile_windows)) continue;
       // default: most windows per tile, wider tiles on ties; tuned: modelled wavefronts x tail factor
-      const double cost = g_tune_pitch ? (4.0 + 6.0 * estimate_wavefronts(L.win, L.step, tw, th, bw)) * (1.0 + 40.0 / windows)
+      const double cost = tn.tune_pitch ? (4.0 + 6.0 * estimate_wavefronts(L.win, L.step, tw, th, bw)) * (1.0 + 40.0 / windows)
                                        : -(double)windows;
       if (cost < best_cost) {
         best_cost = cost;
@@ -405,21 +469,17 @@ int plan_tile(LevelInfo &L, int tile_bytes, int min_tl = 3, int max_windows = K2
 // (with its 16-byte-granular pixel box) fits a warp's 8 KB buffer -- or, for coarser levels, the
 // buffers of 2 or 4 neighbouring warps (only every 2nd / 4th warp then works on that level).  Levels
 // that fit neither read pixels from global memory in "virtual" tiles of 32 x 16 windows.
-void plan_level(LevelInfo &L, bool latency) {
-  if (const char *e = getenv("JDA_B200_MIN_TILE_WINDOWS")) g_min_tile_windows = std::max(1, atoi(e));
-  if (const char *e = getenv("JDA_B200_TUNE_PITCH")) g_tune_pitch = atoi(e);
-  if (const char *e = getenv("JDA_B200_MAX_SPAN")) g_max_span = std::max(1, atoi(e));
-  if (const char *e = getenv("JDA_B200_LATENCY_TILE")) g_latency_tile_windows = std::max(64, std::min(K2_LIST_CAP, atoi(e)));
+void plan_level(const Tuning &tn, LevelInfo &L, bool latency) {
   // Two plans.  Throughput (many frames in flight): coarse levels pool at most 4 warps' buffers, what is
   // left reads global memory in 512-window virtual tiles -- measured fastest on 128+ frame batches.
   // Latency (a handful of frames): the coarsest levels pool the whole block's buffers and go straight to
   // cart-parallel straggler mode, global-memory tiles are small: a single VGA frame's scan drops from
   // 0.58 ms to 0.29 ms because no warp is left with a 0.5 ms dependent chain.
-  const int max_span = g_max_span > 0 ? g_max_span : (latency ? K2_WARPS : 4);
+  const int max_span = tn.max_span > 0 ? tn.max_span : (latency ? K2_WARPS : 4);
   L.use_smem = 0;
   L.span = 1;
   // latency plan: 256-window tiles on the fine levels -- twice the tiles, shorter dependent chains per warp
-  if (plan_tile(L, K2_TILE_BYTES, 3, latency ? g_latency_tile_windows : K2_LIST_CAP) > 0) {
+  if (plan_tile(tn, L, K2_TILE_BYTES, 3, latency ? tn.latency_tile_windows : K2_LIST_CAP) > 0) {
     L.use_smem = 1;  // fits a single warp's buffer: every warp works
   } else {
     // pool buffers: more bytes per tile (more windows) against fewer independent groups.  With every
@@ -432,7 +492,7 @@ void plan_level(LevelInfo &L, bool latency) {
     for (int span : spans) {
       if (span > max_span || K2_WARPS % span) continue;
       LevelInfo t = L;
-      const int windows = plan_tile(t, span * K2_TILE_BYTES, latency ? 1 : 3);
+      const int windows = plan_tile(tn, t, span * K2_TILE_BYTES, latency ? 1 : 3);
       const double score = windows * std::sqrt((double)K2_WARPS / span);
       if (windows > 0 && score > best) { best = score; pick = t; pick.use_smem = 1; pick.span = span; }
     }
@@ -469,7 +529,7 @@ bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int ma
     L.nx = (w - L.win) / L.step + 1;
     L.ny = (h - L.win) / L.step + 1;
     if (L.nx > 8191 || L.ny > 8191) { set_err("frame too large for 13-bit window indices"); return false; }
-    plan_level(L, latency);
+    plan_level(c->tune, L, latency);
     L.table_off = i * g.table_bytes;
     L.win_base = base;
     base += (long long)L.nx * L.ny;
@@ -543,7 +603,7 @@ bool copy_mixed_chunk(Run &R, int ch) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;
   if (ch >= R.nchunks || ch < R.chunks_copied) return true;
-  const int f0 = chunk_begin(b.n_frames, ch, R.nchunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks);
+  const int f0 = chunk_begin(b.n_frames, ch, R.nchunks, c->tune.even_chunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks, c->tune.even_chunks);
   const UnpackFrame *tab = c->h_unpack.data();
   int run0 = f0;
   for (int f = f0; f <= f1; f++) {
@@ -585,7 +645,7 @@ bool stage_frames(Run &R, const unsigned char *frames) {
   R.pitch = (b.width + 15) & ~15;
   R.fstride = (size_t)R.pitch * b.height;
   if (!c->d_frames.ensure(R.fstride * b.n_frames + 256)) return false;
-  if (b.n_frames >= 128 && !m.any_scaled && R.use_scan && !R.tracing && !getenv("JDA_B200_NO_CHUNKS")) {
+  if (b.n_frames >= 128 && !m.any_scaled && R.use_scan && !R.tracing && !c->tune.no_chunks) {
     R.nchunks = kMaxChunks;
     R.host_chunks = true;
   }
@@ -635,7 +695,7 @@ bool stage_frames(Run &R, const unsigned char *frames) {
     }
   }
   for (int ch = 0; ch < R.nchunks && !staged; ch++) {
-    const int f0 = chunk_begin(b.n_frames, ch, R.nchunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks);
+    const int f0 = chunk_begin(b.n_frames, ch, R.nchunks, c->tune.even_chunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks, c->tune.even_chunks);
     if (b.frame_stride == (size_t)b.pitch * b.height) {
       CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f0 * R.fstride, R.pitch, frames + f0 * b.frame_stride, b.pitch, b.width,
                               (size_t)b.height * (f1 - f0), cudaMemcpyHostToDevice, c->copy_stream));
@@ -716,7 +776,7 @@ bool launch_scan(Run &R) {
       const LevelInfo &L = g.lv[g.n_levels - 1 - i];
       // cost per window grows with the window size (coarse windows survive deeper and their tiles hold fewer windows
       // per warp): measured per level in profiles/r1m_level_probe.txt, ~ (win / 24)^1.6, global-memory levels x1.6
-      static const double e = getenv("JDA_B200_LEVEL_WEIGHT_EXP") ? atof(getenv("JDA_B200_LEVEL_WEIGHT_EXP")) : kLevelWeightExp;
+      const double e = c->tune.level_weight_exp;
       w[i] = (double)L.nx * L.ny * (e > 0 ? std::pow(L.win / 24.0, e) * (L.use_smem ? 1.0 : 1.6)
                                           : (L.use_smem ? (L.span == 1 ? 1.0 : 1.4) : 2.2));
       tot += w[i];
@@ -725,7 +785,7 @@ bool launch_scan(Run &R) {
     for (int i = 0; i < g.n_levels; i++) { acc += w[i]; P.level_cum[i] = (float)(acc / tot); }
   }
   P.use_tma = tma_ok ? 1 : 0;
-  P.stragglers = c->stragglers;
+  P.stragglers = c->tune.stragglers;
   if (R.tracing) {
     P.trace_n = c->d_trace_n.p; P.trace_s = c->d_trace_s.p;
     P.trace_leaf = (R.trace->leaf && R.trace->w1 > R.trace->w0) ? c->d_trace_leaf.p : nullptr;
@@ -734,7 +794,7 @@ bool launch_scan(Run &R) {
   const size_t smem = k2_smem_bytes(g.table_bytes);
   const int grid = c->sm_count;
   for (int ch = 0; ch < R.nchunks; ch++) {
-    const int f0 = chunk_begin(b.n_frames, ch, R.nchunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks);
+    const int f0 = chunk_begin(b.n_frames, ch, R.nchunks, c->tune.even_chunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks, c->tune.even_chunks);
     if (f1 <= f0) continue;
     P.frames = R.d_frames + (size_t)f0 * R.fstride;
     P.n_frames = f1 - f0;
@@ -756,15 +816,16 @@ bool launch_scan(Run &R) {
     }
     if (R.mixed && !copy_mixed_chunk(R, ch)) return false;  // no-op unless an earlier chunk was empty
     if (R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[ch], 0));
-    if (R.tracing) {
-      if (c->nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
-      else if (c->nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
-      else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
-    } else if (c->nw == 1) {
-      k2_scan<1, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
-    } else if (R.mixed) {  // per-frame window grids (always 4 windows per lane: the tuning knob is for A/B runs)
+    const int nw = c->tune.nw;
+    if (R.mixed) {  // per-frame window grids: always the MIXED instantiation (4 windows per lane whatever the A/B knob says)
       k2_scan<4, false, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
-    } else if (c->nw == 4) {
+    } else if (R.tracing) {
+      if (nw == 1) k2_scan<1, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+      else if (nw == 4) k2_scan<4, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+      else k2_scan<2, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+    } else if (nw == 1) {
+      k2_scan<1, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
+    } else if (nw == 4) {
       k2_scan<4, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
     } else {
       k2_scan<2, false><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
@@ -932,8 +993,8 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   if (timing) CU_OK(cudaEventRecord(c->ev[1], s));
   if (!make_planes(R) || !prepare_trace(R)) return false;
 
-  if (const char *e = getenv("JDA_B200_TINY_QUEUES")) {  // test hook: start with queues that overflow, exercise grow-and-retry
-    if (atoi(e) && c->surv_cap == 0) { c->surv_cap = 8; c->hit_cap = 2; }
+  if (c->tune.tiny_queues) {  // test hook (read in ctx_init): start with queues that overflow, exercise grow-and-retry
+    if (c->surv_cap == 0) { c->surv_cap = 8; c->hit_cap = 2; }
   } else {
     if (c->surv_cap == 0) c->surv_cap = 1 << 16;
     if (c->hit_cap == 0) c->hit_cap = 1 << 14;
@@ -1006,9 +1067,7 @@ bool ensure_model64_host(Context *c) {
   return true;
 }
 
-bool ensure_model64(Context *c) {
-  if (c->d_nodes64) return true;
-  if (!ensure_model64_host(c)) return false;
+bool ensure_model64_impl(Context *c) {
   const HostModelD &m = c->md;
   CU_OK(cudaMalloc(&c->d_nodes64, m.nodes.size() * sizeof(NodeRecD)));
   CU_OK(cudaMalloc(&c->d_leaf64, m.leaf.size() * 8));
@@ -1023,6 +1082,21 @@ bool ensure_model64(Context *c) {
   CU_OK(cudaMemcpy(c->d_mean64, m.mean_shape.data(), m.mean_shape.size() * 8, cudaMemcpyHostToDevice));
   CU_OK(cudaFuncSetAttribute(k4_cascade_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(K4_WARPS * (kMaxDim * 8 + ((m.K + 15) & ~15)))));
+  return true;
+}
+
+// all-or-nothing like ctx_init: a failed upload frees its partial allocations, the next call starts over
+bool ensure_model64(Context *c) {
+  if (c->model64_ready) return true;
+  if (!ensure_model64_host(c)) return false;
+  if (!ensure_model64_impl(c)) {
+    const std::string keep = g_err;
+    release_model64(c);
+    cudaGetLastError();
+    g_err = keep;
+    return false;
+  }
+  c->model64_ready = true;
   return true;
 }
 
@@ -1049,7 +1123,7 @@ bool ensure_geometry64(Context *c, int w, int h, int minimum_size, int step, dou
     L.nx = (w - L.win) / step + 1;
     L.ny = (h - L.win) / step + 1;
     if (L.nx > 8191 || L.ny > 8191) { set_err("frame too large for 13-bit window indices"); return false; }
-    plan_level(L, latency);
+    plan_level(c->tune, L, latency);
     L.table_off = i * g.table_bytes;
     L.win_base = base;
     base += (long long)L.nx * L.ny;
@@ -1668,6 +1742,7 @@ long long jdaB200CountWindows(int width, int height, float scale, int min_size, 
 int jdaB200DescribePlan(int width, int height, float scale, int min_size, int max_size, char *buf, int cap) {
   const bool latency = cap < 0;  // negative cap: describe the latency plan (batches of <= 4 frames)
   if (cap < 0) cap = -cap;
+  const Tuning tn = read_tuning();
   int wins[kMaxLevels + 1];
   int n = (width < 24 || height < 24) ? 0 : enumerate_levels(width, height, scale, min_size, max_size, wins, kMaxLevels + 1);
   n = std::min(n, kMaxLevels);
@@ -1678,7 +1753,7 @@ int jdaB200DescribePlan(int width, int height, float scale, int min_size, int ma
     memset(&L, 0, sizeof L);
     L.win = wins[i]; L.step = level_step(L.win);
     L.nx = (width - L.win) / L.step + 1; L.ny = (height - L.win) / L.step + 1;
-    plan_level(L, latency);
+    plan_level(tn, L, latency);
     if (buf && o < cap)
       o += snprintf(buf + o, cap - o, "%d %d %d %d %d %d %d %d %d %d %d\n", L.win, L.step, L.nx, L.ny, 1 << L.tw_log2,
                     L.th, L.box_w, L.box_h, L.use_smem, (1 << L.tw_log2) * L.th, L.span);

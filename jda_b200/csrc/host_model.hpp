@@ -24,7 +24,7 @@ namespace jda {
 constexpr int kDepth = 4;       // only depth-4 carts are runnable by the kernels
 constexpr int kNodes = 7;       // internal nodes per cart
 constexpr int kLeaves = 8;      // leaves per cart
-constexpr int kMaxLevels = 20;  // pyramid levels per geometry
+constexpr int kMaxLevels = 64;  // pyramid levels per geometry (the survivor key has 6 bits for the level)
 constexpr int kMaxDim = 128;    // 2 * landmark_n upper bound
 constexpr int kMaxNorm = 32;    // stage-0 carts with non-trivial (mean, std) the scan kernel can hold
 constexpr int kCartBytes = 104;  // stage-0 table record of one cart (layout below, at build_stage0_table)
