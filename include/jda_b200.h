@@ -91,6 +91,11 @@ typedef struct {
   float th;
   int t_limit; /* 0 = all stages; 1..T = only the first t_limit stages (Validate's current_stage_idx) */
   int flags;
+  int k_limit; /* 0 = stages are run whole.  > 0: a cascade that stops INSIDE a stage, as JoinCascador::Validate does
+                * while that stage is being trained (src/jda/cascador.cpp:178-209, caller btcart.cpp:146-152): t_limit
+                * then counts the FULL stages (0 .. T-1, 0 allowed) and carts [0, k_limit) of stage t_limit follow
+                * (k_limit = current_cart_idx + 1), with no regression after them.  Mining passes this together with
+                * JDA_B200_RAW_HITS | JDA_B200_NO_FINAL_TH. */
 } jdaB200Batch;
 
 /* work counters + device timings of the last batch call on this handle */
@@ -201,7 +206,16 @@ JDA_API void jdaB200ResultsRelease(jdaResult *results, int n);
 JDA_API int jdaB200SetDevice(void *cascador, int device);
 JDA_API int jdaB200SetStream(void *cascador, void *cuda_stream);
 
-/* model dimensions: out[0..3] = T, K, landmark_n, tree_depth */
+/* jdaCascadorSerializeTo with options.  The reference's writer stores the header's stage
+ * field as T + 1 (c/jda.c:662-665), which the C++ loader refuses (cascador.cpp:138 wants T), and only knows the
+ * float32 flavour.  flags = 0 writes exactly what jdaCascadorSerializeTo writes.  Returns 0, negative on failure. */
+enum {
+  JDA_B200_SAVE_STAGE_T = 1, /* header stage field = T                                                    */
+  JDA_B200_SAVE_DOUBLE = 2   /* double flavour (README.md:84-111); with STAGE_T: loadable by the C++ tree */
+};
+JDA_API int jdaB200SerializeTo(void *cascador, const char *model, int flags);
+
+/* model dimensions: out[0..3] = T, K, landmark_n, tree_depth (2..6 accepted; the reference fixes 4, c/jda.c:28) */
 JDA_API void jdaB200ModelDims(void *cascador, int *out4);
 
 /* last error text of the calling thread ("" if none) */
@@ -235,6 +249,11 @@ JDA_API long long jdaB200Trace(void *cascador, const unsigned char *frame, int w
                                float scale, int min_size, int max_size, int t_limit, int flags,
                                int *carts_evaluated, float *exit_score, unsigned char *leaves,
                                long long leaf_w0, long long leaf_w1);
+/* the same with jdaB200Batch's k_limit (a cascade that stops inside stage t_limit) */
+JDA_API long long jdaB200TraceK(void *cascador, const unsigned char *frame, int width, int height,
+                                float scale, int min_size, int max_size, int t_limit, int k_limit, int flags,
+                                int *carts_evaluated, float *exit_score, unsigned char *leaves,
+                                long long leaf_w0, long long leaf_w1);
 
 /* Device bilinear down-sample (replaces jdaImageResize, c/jda.c:203-230); host in, host out. */
 JDA_API int jdaB200Resize(void *cascador, const unsigned char *src, int sw, int sh,

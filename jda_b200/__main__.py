@@ -3,6 +3,8 @@ are GUI/OpenCV demos and are not rebuilt).
 
   python -m jda_b200 info    MODEL [--float] [--size WxH] [--max-size N]
   python -m jda_b200 convert MODEL_DOUBLE OUT_FLOAT32          (jdaCascadorSerializeTo, c/jda.c:644-716)
+  python -m jda_b200 convert MODEL OUT [--float] --cpp-loadable  (double flavour, header stage field T: what the
+                                                                  C++ loader accepts, cascador.cpp:126-164)
   python -m jda_b200 detect  MODEL IMAGE... [--float] [--fddb-out FILE] [--scale S --min-size N --max-size N --th T]
   python -m jda_b200 detect  MODEL IMAGE... --cpp [--fddb-min 20 --fddb-step 5 --fddb-scale 1.2 --overlap 0.3 --no-nms]
 
@@ -93,6 +95,10 @@ def main(argv=None):
     p.add_argument("--size", default="640x480"); p.add_argument("--max-size", type=int, default=-1)
     p = sub.add_parser("convert")
     p.add_argument("model"); p.add_argument("out")
+    p.add_argument("--float", action="store_true", help="the input is a float32-flavour file")
+    p.add_argument("--cpp-loadable", action="store_true",
+                   help="write the double flavour with the header's stage field = T (cascador.cpp:138), not the C "
+                        "serialiser's T + 1 (c/jda.c:662-665)")
     p = sub.add_parser("detect")
     p.add_argument("model"); p.add_argument("images", nargs="+"); p.add_argument("--float", action="store_true")
     p.add_argument("--fddb-out"); p.add_argument("--scale", type=float, default=1.25)
@@ -112,9 +118,13 @@ def main(argv=None):
     a = ap.parse_args(argv)
 
     if a.cmd == "convert":
-        c = api.Cascador(a.model, double=True)
-        c.save_f32(a.out)
-        print("wrote %s (%d bytes, float32 flavour, T=%d K=%d L=%d)" % (a.out, os.path.getsize(a.out), c.T, c.K, c.L))
+        c = api.Cascador(a.model, double=not a.float)
+        if a.cpp_loadable:
+            c.save(a.out, api.SAVE_STAGE_T | api.SAVE_DOUBLE)
+        else:
+            c.save_f32(a.out)
+        print("wrote %s (%d bytes, %s flavour, T=%d K=%d L=%d depth=%d)" %
+              (a.out, os.path.getsize(a.out), "double" if a.cpp_loadable else "float32", c.T, c.K, c.L, c.depth))
         return 0
     c = api.Cascador(a.model, double=not a.float)
     if a.cmd == "info":

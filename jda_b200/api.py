@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get("JDA_B200_LIB", "libjda_b200.so"))
 
 DEVICE_INPUT, RAW_HITS, NO_FINAL_TH, NO_TMA, NO_STAGE0_SCAN = 1, 2, 4, 8, 16
+SAVE_STAGE_T, SAVE_DOUBLE = 1, 2
 
 
 class _Result(C.Structure):
@@ -30,7 +31,8 @@ class _Result(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("n_frames", C.c_int), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_int),
                 ("frame_stride", C.c_size_t), ("scale", C.c_float), ("min_size", C.c_int),
-                ("max_size", C.c_int), ("th", C.c_float), ("t_limit", C.c_int), ("flags", C.c_int)]
+                ("max_size", C.c_int), ("th", C.c_float), ("t_limit", C.c_int), ("flags", C.c_int),
+                ("k_limit", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -140,6 +142,11 @@ def lib():
     L.jdaB200Trace.restype = C.c_longlong
     L.jdaB200Trace.argtypes = [vp, ub, ci, ci, cf, ci, ci, ci, ci, C.POINTER(ci), C.POINTER(cf), ub,
                                C.c_longlong, C.c_longlong]
+    L.jdaB200TraceK.restype = C.c_longlong
+    L.jdaB200TraceK.argtypes = [vp, ub, ci, ci, cf, ci, ci, ci, ci, ci, C.POINTER(ci), C.POINTER(cf), ub,
+                                C.c_longlong, C.c_longlong]
+    L.jdaB200SerializeTo.restype = ci
+    L.jdaB200SerializeTo.argtypes = [vp, cp, ci]
     L.jdaB200Resize.restype = ci
     L.jdaB200Resize.argtypes = [vp, ub, ci, ci, ub, ci, ci]
     _lib = L
@@ -153,7 +160,7 @@ EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSeri
            "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan", "jdaB200ResultsRelease",
            "jdaB200DetectMixed", "jdaB200JoinCascadorDetect", "jdaB200ResultF64Release",
            "jdaB200JoinCascadorTrace", "jdaB200JoinCascadorLevels", "jdaB200JoinCascadorFilterMargins",
-           "jdaB200DetectBatchFlat", "jdaB200FlatResultRelease"]
+           "jdaB200DetectBatchFlat", "jdaB200FlatResultRelease", "jdaB200TraceK", "jdaB200SerializeTo"]
 
 
 def last_error():
@@ -249,6 +256,12 @@ class Cascador:
     def save_f32(self, path):
         lib().jdaCascadorSerializeTo(self._h, os.fsencode(path))
 
+    def save(self, path, flags=0):
+        """jdaB200SerializeTo: flags 0 = jdaCascadorSerializeTo's bytes; SAVE_STAGE_T | SAVE_DOUBLE = a file the
+        reference's C++ loader accepts (cascador.cpp:126-164)."""
+        if lib().jdaB200SerializeTo(self._h, os.fsencode(path), flags) != 0:
+            raise RuntimeError("jdaB200SerializeTo failed")
+
     def set_stream(self, cuda_stream_ptr):
         lib().jdaB200SetStream(self._h, C.c_void_p(cuda_stream_ptr))
 
@@ -261,7 +274,7 @@ class Cascador:
         return _unpack(res)
 
     def detect_batch(self, frames, scale=1.25, min_size=24, max_size=-1, th=0.0, t_limit=0, flags=0,
-                     device_ptr=None, shape=None, pitch=None, frame_stride=None, unpack=True, flat=False):
+                     device_ptr=None, shape=None, pitch=None, frame_stride=None, unpack=True, flat=False, k_limit=0):
         """frames: [n,h,w] u8 numpy array (host), or device_ptr + shape=(n,h,w) for frames resident
         in HBM (any allocator: torch .data_ptr(), cudaMalloc ...).  Returns a list of
         (boxes, scores, shapes) per frame, or just the detection count when unpack=False."""
@@ -279,7 +292,7 @@ class Cascador:
             pitch = w if pitch is None else pitch
             frame_stride = pitch * h if frame_stride is None else frame_stride
             flags |= DEVICE_INPUT
-        b = Batch(n, w, h, pitch, frame_stride, scale, min_size, max_size, th, t_limit, flags)
+        b = Batch(n, w, h, pitch, frame_stride, scale, min_size, max_size, th, t_limit, flags, k_limit)
         if flat:
             # jdaB200DetectBatchFlat: (counts[n], boxes[total,3], scores[total], shapes[total,2L]), frame order
             fr = FlatResult()
@@ -437,7 +450,7 @@ class Cascador:
         self.last_stats = stats
         return out
 
-    def trace(self, img, scale=1.25, min_size=24, max_size=-1, t_limit=0, flags=0, leaf_range=None):
+    def trace(self, img, scale=1.25, min_size=24, max_size=-1, t_limit=0, flags=0, leaf_range=None, k_limit=0):
         """per-window (carts evaluated, exit score) in scan order + optional leaf indices."""
         a = np.ascontiguousarray(img, np.uint8)
         h, w = a.shape
@@ -451,8 +464,8 @@ class Cascador:
         else:
             w0 = w1 = 0
             lv, lp = None, None
-        n = lib().jdaB200Trace(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, scale, min_size,
-                               max_size, t_limit, flags, tn.ctypes.data_as(C.POINTER(C.c_int)),
+        n = lib().jdaB200TraceK(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, scale, min_size,
+                               max_size, t_limit, k_limit, flags, tn.ctypes.data_as(C.POINTER(C.c_int)),
                                ts.ctypes.data_as(C.POINTER(C.c_float)), lp, w0, w1)
         if n < 0:
             raise RuntimeError("jdaB200Trace failed: " + last_error())

@@ -286,6 +286,8 @@ bool ctx_init_impl(Context *c) {
   const size_t s3 = k3_smem_bytes(c->m.K);
   CU_OK(cudaFuncSetAttribute(k3_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   CU_OK(cudaFuncSetAttribute(k3_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
+  CU_OK(cudaFuncSetAttribute(k3_cascade<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
+  CU_OK(cudaFuncSetAttribute(k3_cascade<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   // tuning knobs (not behaviour): windows per lane and the phase schedule of k2_scan
   c->tune = read_tuning();
   c->sched.clear();
@@ -589,7 +591,8 @@ struct Run {
   int nchunks;         // scan launches (the host copy is split the same way)
   int chunks_copied;   // mixed-size batches: chunks whose host -> device copies have been issued
   bool host_chunks;
-  int D, rec_words, t_run, leaf_stride, leaf_pad;
+  int D, rec_words, t_run, k_extra, leaf_stride, leaf_pad;
+  int scan_K;          // carts the scan walks: K, or k_extra when the truncated cascade ends inside stage 0
   long long total_windows;
   float r;             // 1.f / sqrtf(2.f) as the reference computes it (c/jda.c:341)
   int hw, hh, qw, qh;
@@ -750,19 +753,20 @@ bool launch_scan(Run &R) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;
   const Geometry &g = *R.geo;
-  const HostModel &m = c->m;
   jdaB200Stats &st = c->last;
   ScanParams P;
   memset(&P, 0, sizeof P);
   for (int i = 0; i < g.n_levels; i++) P.lv[i] = g.lv[i];
   P.frame_stride = R.fstride; P.pitch = R.pitch; P.W = b.width; P.H = b.height;
-  P.n_levels = g.n_levels; P.K = m.K; P.table_bytes = g.table_bytes;
+  P.n_levels = g.n_levels; P.K = R.scan_K; P.table_bytes = g.table_bytes;
   P.tables = R.tables; P.norms = R.norms;
   P.windows_per_frame = g.windows_per_frame;
-  P.n_sched = (int)c->sched.size();
-  for (int i = 0; i < P.n_sched; i++) P.sched[i] = c->sched[i];
+  P.n_sched = 0;
+  for (size_t i = 0; i < c->sched.size() && c->sched[i] < R.scan_K; i++) P.sched[P.n_sched++] = c->sched[i];
+  P.sched[P.n_sched++] = (short)R.scan_K;  // the last phase ends at the last cart the scan walks
   P.surv = c->d_surv.p; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)c->surv_cap;
-  P.surv_leaves = c->d_surv_leaves.p; P.leaf_pad = R.leaf_pad;
+  P.surv_leaves = R.t_run > 0 ? c->d_surv_leaves.p : nullptr;  // the leaves feed the stage-0 regression only
+  P.leaf_pad = R.leaf_pad;
   P.frame_dims = R.mixed ? c->d_dims.p : nullptr;
   // TMA needs 16-byte aligned base and strides
   const bool tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)R.d_frames % 16 == 0) &&
@@ -863,7 +867,8 @@ bool launch_cascade(Run &R) {
   Q.frames = R.d_frames; Q.frame_stride = R.fstride; Q.pitch = R.pitch; Q.W = b.width; Q.H = b.height;
   Q.hq = m.any_scaled ? c->d_hq.p : nullptr; Q.hq_stride = R.hq_stride; Q.hw = R.hw; Q.hh = R.hh; Q.qw = R.qw; Q.qh = R.qh;
   Q.nodes = c->d_nodes; Q.leaf = c->d_leaf; Q.cart = c->d_cart; Q.w = c->d_w; Q.mean_shape = c->d_mean;
-  Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.t_run = R.t_run; Q.r = R.r;
+  Q.depth = m.depth; Q.nn = m.nn; Q.nl = m.nl;
+  Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.t_run = R.t_run; Q.k_extra = R.k_extra; Q.r = R.r;
   Q.n_levels = g.n_levels;
   for (int i = 0; i < g.n_levels; i++) {
     Q.lv_win[i] = g.lv[i].win; Q.lv_step[i] = g.lv[i].step; Q.lv_nx[i] = g.lv[i].nx; Q.lv_ny[i] = g.lv[i].ny;
@@ -871,7 +876,10 @@ bool launch_cascade(Run &R) {
   }
   Q.windows_per_frame = g.windows_per_frame;
   Q.dense = R.use_scan ? 0 : 1; Q.dense_total = R.total_windows;
-  Q.t_start = R.staged0 ? 1 : 0;
+  // queue entries resume after stage 0 when its regression is already applied (k3_stage0) or does not exist (the
+  // truncated cascade ended inside stage 0: the scan walked all of its k_extra carts)
+  Q.t_start = (R.staged0 || (R.use_scan && R.t_run == 0)) ? 1 : 0;
+  Q.n_eval0 = R.scan_K;
   Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
   Q.init_shape = R.staged0 ? c->d_shape0.p : nullptr;
   Q.work_counter = c->d_counters + kCntWork;
@@ -884,8 +892,13 @@ bool launch_cascade(Run &R) {
   }
   const int grid = c->sm_count * 8;
   const size_t smem = k3_smem_bytes(m.K);
-  if (R.tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);
-  else k3_cascade<false><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);
+  if (m.depth == kDepth) {
+    if (R.tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);
+    else k3_cascade<false><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);
+  } else {  // tree_depth from the header (2..6): node / leaf counts are run-time values
+    if (R.tracing) k3_cascade<true, false><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);
+    else k3_cascade<false, false><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);
+  }
   CU_OK(cudaGetLastError());
   st.cascade_launches++;
   return true;
@@ -975,6 +988,12 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   R.D = m.D();
   R.rec_words = kHitHeader + R.D;
   R.t_run = (b.t_limit > 0 && b.t_limit < m.T) ? b.t_limit : m.T;
+  R.k_extra = 0;
+  if (b.k_limit > 0 && b.t_limit >= 0 && b.t_limit < m.T) {  // Validate's unfinished stage (cascador.cpp:199-209)
+    R.t_run = b.t_limit;
+    R.k_extra = std::min(b.k_limit, m.K);
+  }
+  R.scan_K = R.t_run == 0 ? R.k_extra : m.K;
   R.leaf_stride = m.T * m.K;
   R.leaf_pad = (m.K + 15) & ~15;
   R.total_windows = st.windows;
@@ -985,7 +1004,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   }
   // a handful of frames: the cohort-staged k3_stage0 is a ~0.1 ms serial pipeline for a few survivors, so the
   // cascade kernel redoes stage 0 itself (same bits); batches take the staged path
-  R.staged0 = R.use_scan && !R.latency_plan;
+  R.staged0 = R.use_scan && !R.latency_plan && R.t_run > 0;
   cudaStream_t s = R.s;
 
   if (timing) CU_OK(cudaEventRecord(c->ev[0], s));
@@ -1173,6 +1192,7 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
   R.s = c->stream();
   R.D = m.D();
   R.leaf_pad = (m.K + 15) & ~15;
+  R.scan_K = m.K;  // (R.t_run stays 0: the prefilter's survivors are re-evaluated from cart 0, no leaf records needed)
   R.total_windows = st.windows;
   R.use_scan = c->filter64_ok && !(prm.flags & JDA_B200_NO_STAGE0_SCAN) && !tracing;
   cudaStream_t s = R.s;
@@ -1551,6 +1571,12 @@ void jdaCascadorSerializeTo(void *cascador, const char *model) {
   save_model_f32(static_cast<Context *>(cascador)->m, model);
 }
 
+int jdaB200SerializeTo(void *cascador, const char *model, int flags) {
+  if (!cascador || !model) return -2;
+  return save_model(static_cast<Context *>(cascador)->m, model, (flags & JDA_B200_SAVE_STAGE_T) != 0,
+                    (flags & JDA_B200_SAVE_DOUBLE) != 0) ? 0 : -1;
+}
+
 void jdaCascadorRelease(void *cascador) {
   if (cascador) ctx_free(static_cast<Context *>(cascador));
 }
@@ -1716,7 +1742,7 @@ int jdaB200SetStream(void *cascador, void *cuda_stream) {
 void jdaB200ModelDims(void *cascador, int *out4) {
   Context *c = static_cast<Context *>(cascador);
   if (!c || !out4) return;
-  out4[0] = c->m.T; out4[1] = c->m.K; out4[2] = c->m.L; out4[3] = kDepth;
+  out4[0] = c->m.T; out4[1] = c->m.K; out4[2] = c->m.L; out4[3] = c->m.depth;
 }
 
 const char *jdaB200LastError(void) { return g_err.c_str(); }
@@ -1768,6 +1794,13 @@ void jdaB200Nms(int n, const int *bboxes, const float *scores, unsigned char *ke
 long long jdaB200Trace(void *cascador, const unsigned char *frame, int width, int height, float scale,
                        int min_size, int max_size, int t_limit, int flags, int *carts_evaluated,
                        float *exit_score, unsigned char *leaves, long long leaf_w0, long long leaf_w1) {
+  return jdaB200TraceK(cascador, frame, width, height, scale, min_size, max_size, t_limit, 0, flags, carts_evaluated,
+                       exit_score, leaves, leaf_w0, leaf_w1);
+}
+
+long long jdaB200TraceK(void *cascador, const unsigned char *frame, int width, int height, float scale,
+                        int min_size, int max_size, int t_limit, int k_limit, int flags, int *carts_evaluated,
+                        float *exit_score, unsigned char *leaves, long long leaf_w0, long long leaf_w1) {
   Context *c = static_cast<Context *>(cascador);
   if (!c || !frame) return -2;
   std::lock_guard<std::mutex> lock(c->mu);
@@ -1775,7 +1808,7 @@ long long jdaB200Trace(void *cascador, const unsigned char *frame, int width, in
   memset(&b, 0, sizeof b);
   b.n_frames = 1; b.width = width; b.height = height; b.pitch = width;
   b.frame_stride = (size_t)width * height;
-  b.scale = scale; b.min_size = min_size; b.max_size = max_size; b.th = 0.f; b.t_limit = t_limit;
+  b.scale = scale; b.min_size = min_size; b.max_size = max_size; b.th = 0.f; b.t_limit = t_limit; b.k_limit = k_limit;
   b.flags = (flags & ~JDA_B200_DEVICE_INPUT) | JDA_B200_NO_FINAL_TH;
   TraceOut t;
   t.n = carts_evaluated; t.s = exit_score; t.leaf = leaves; t.w0 = leaf_w0; t.w1 = leaf_w1;

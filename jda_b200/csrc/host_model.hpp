@@ -21,9 +21,10 @@
 
 namespace jda {
 
-constexpr int kDepth = 4;       // only depth-4 carts are runnable by the kernels
-constexpr int kNodes = 7;       // internal nodes per cart
-constexpr int kLeaves = 8;      // leaves per cart
+constexpr int kDepth = 4;       // the reference's depth (c/jda.c:28); the scan kernel and its tables are built for it
+constexpr int kNodes = 7;       // internal nodes per depth-4 cart
+constexpr int kLeaves = 8;      // leaves per depth-4 cart
+constexpr int kMinDepth = 2, kMaxDepth = 6;  // depths the generic cascade kernel runs (header field tree_depth)
 constexpr int kMaxLevels = 64;  // pyramid levels per geometry (the survivor key has 6 bits for the level)
 constexpr int kMaxDim = 128;    // 2 * landmark_n upper bound
 constexpr int kMaxNorm = 32;    // stage-0 carts with non-trivial (mean, std) the scan kernel can hold
@@ -42,11 +43,13 @@ static_assert(sizeof(NodeRec) == 32, "NodeRec must be 32 bytes");
 struct HostModel {
   int hdr[7] = {0, 0, 0, 0, 0, 0, 0};
   int T = 0, K = 0, L = 0;
+  int depth = kDepth;             // tree_depth from the header (README.md:84-111); nn / nl follow from it
+  int nn = kNodes, nl = kLeaves;  // internal nodes 2^(depth-1) - 1 and leaves 2^(depth-1) per cart
   std::vector<float> mean_shape;  // [2L]
-  std::vector<NodeRec> nodes;     // [T*K*7]
-  std::vector<float> leaf;        // [T*K*8]
+  std::vector<NodeRec> nodes;     // [T*K*nn]
+  std::vector<float> leaf;        // [T*K*nl]
   std::vector<float> cart;        // [T*K*4] = th, mean, std, 0
-  std::vector<float> w;           // [T][K*8][2L]
+  std::vector<float> w;           // [T][K*nl][2L]
   bool any_scaled = false;        // some node samples the h/q planes
   bool stage0_lut_ok = false;     // stage 0 can run from per-level integer look-up tables
   int D() const { return 2 * L; }
@@ -88,7 +91,11 @@ inline bool load_model(const char *path, bool dbl, HostModel &m, std::string &er
   if (!r.ok || m.T <= 0 || m.T > 32 || m.K <= 0 || m.K > 4096 || m.L <= 0 || 2 * m.L > kMaxDim) {
     err = "bad model header"; fclose(f); return false;
   }
-  if (depth != kDepth) { err = "tree_depth != 4 is not supported"; fclose(f); return false; }
+  // c/jda.c:24-32 fixes tree_depth = 4 at compile time; here it comes from the header like T / K / L.  Depth 4 runs
+  // the stage-0 scan kernel; other depths run every stage through the generic cascade kernel.
+  if (depth < kMinDepth || depth > kMaxDepth) { err = "tree_depth outside 2..6"; fclose(f); return false; }
+  m.depth = depth; m.nl = 1 << (depth - 1); m.nn = m.nl - 1;
+  const int kNodes = m.nn, kLeaves = m.nl;  // (shadow the depth-4 constants inside this function)
   const int D = m.D();
   const size_t C = (size_t)m.T * m.K;
   m.mean_shape.resize(D);
@@ -135,18 +142,26 @@ inline bool load_model(const char *path, bool dbl, HostModel &m, std::string &er
   for (int k = 0; k < m.K; k++)
     if (m.cart[k * 4 + 1] != 0.f || m.cart[k * 4 + 2] != 1.f) norm0++;
   // the scan kernel keeps one level's table (K x kCartBytes) in shared memory next to its tile buffers
-  m.stage0_lut_ok = !s0_scaled && norm0 <= kMaxNorm && m.K * kCartBytes <= kMaxStage0TableBytes;
+  m.stage0_lut_ok = depth == kDepth && !s0_scaled && norm0 <= kMaxNorm && m.K * kCartBytes <= kMaxStage0TableBytes;
   return true;
 }
 
-// float32 flavour, byte layout of c/jda.c:644-716 (stage field T+1, cart -1)
-inline bool save_model_f32(const HostModel &m, const char *path) {
+// Model file writer.  Default = the float32 flavour with the byte layout of c/jda.c:644-716, including its header
+// quirk: stage field T + 1, cart -1 (c/jda.c:662-665), which the C++ loader rejects (cascador.cpp:138 wants T).
+//   stage_T : write T in the stage field instead
+//   dbl     : double flavour (README.md:84-111; f32 -> f64 widening is exact), what JoinCascador::SerializeFrom reads
+inline bool save_model(const HostModel &m, const char *path, bool stage_T, bool dbl) {
   FILE *f = fopen(path, "wb");
   if (!f) return false;
-  int h[7] = {0, m.T, m.K, m.L, kDepth, m.T + 1, -1};
+  const int kNodes = m.nn, kLeaves = m.nl;
+  int h[7] = {0, m.T, m.K, m.L, m.depth, stage_T ? m.T : m.T + 1, -1};
   fwrite(h, 4, 7, f);
+  auto reals = [&](const float *p, size_t n) {
+    if (!dbl) { fwrite(p, 4, n, f); return; }
+    for (size_t i = 0; i < n; i++) { const double d = (double)p[i]; fwrite(&d, 8, 1, f); }
+  };
   const int D = m.D();
-  fwrite(m.mean_shape.data(), 4, D, f);
+  reals(m.mean_shape.data(), D);
   for (int t = 0; t < m.T; t++) {
     for (int k = 0; k < m.K; k++) {
       size_t c = (size_t)t * m.K + k;
@@ -154,19 +169,20 @@ inline bool save_model_f32(const HostModel &m, const char *path) {
         const NodeRec &n = m.nodes[c * kNodes + i];
         int a = n.lm1 >> 1, b = n.lm2 >> 1;
         fwrite(&n.scale, 4, 1, f); fwrite(&a, 4, 1, f); fwrite(&b, 4, 1, f);
-        fwrite(&n.o1x, 4, 1, f); fwrite(&n.o1y, 4, 1, f); fwrite(&n.o2x, 4, 1, f); fwrite(&n.o2y, 4, 1, f);
+        reals(&n.o1x, 4);
         fwrite(&n.th, 4, 1, f);
       }
-      fwrite(&m.leaf[c * kLeaves], 4, kLeaves, f);
-      fwrite(&m.cart[c * 4], 4, 3, f);
+      reals(&m.leaf[c * kLeaves], kLeaves);
+      reals(&m.cart[c * 4], 3);
     }
-    fwrite(m.w.data() + (size_t)t * m.K * kLeaves * D, 4, (size_t)m.K * kLeaves * D, f);
+    reals(m.w.data() + (size_t)t * m.K * kLeaves * D, (size_t)m.K * kLeaves * D);
   }
   int z = 0;
   fwrite(&z, 4, 1, f);
   fclose(f);
   return true;
 }
+inline bool save_model_f32(const HostModel &m, const char *path) { return save_model(m, path, false, false); }
 
 // ------------------------------------------------------------------------------- geometry
 

@@ -105,6 +105,10 @@ struct CascadeParams {
   const float *w;
   const float *mean_shape;
   int T, K, L, t_run;
+  int k_extra;         // > 0: after the t_run full stages, carts [0, k_extra) of stage t_run, no regression after them
+                       // (Validate's unfinished stage, src/jda/cascador.cpp:199-209)
+  int n_eval0;         // carts already evaluated for a queue entry when the kernel resumes it (trace)
+  int depth, nn, nl;   // tree depth (c/jda.c:28 fixes 4), internal nodes and leaves per cart: read by k3_cascade<.., false>
   float r;             // 1.f / sqrtf(2.f), computed on the host like c/jda.c:341
   int n_levels;
   int lv_win[kMaxLevels], lv_step[kMaxLevels], lv_nx[kMaxLevels], lv_ny[kMaxLevels];
@@ -561,7 +565,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
       const int src = __ffs(rest) - 1;
       const unsigned sl = __shfl_sync(0xffffffffu, slot, src);
       const PixBase<SMEM> pb = window_base<SMEM>(c, __shfl_sync(0xffffffffu, w, src), true);
-      if (sl >= P.surv_cap) continue;
+      if (sl >= P.surv_cap || !P.surv_leaves) continue;  // no leaf store: nothing regresses from this stage (truncated cascade)
       uint8_t *out = P.surv_leaves + (size_t)sl * P.leaf_pad;
       for (int k0 = 0; k0 < P.K; k0 += 32) {
         const int k = min(k0 + lane, P.K - 1);
@@ -738,11 +742,14 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
 constexpr int K3_WARPS = 4;
 constexpr int K3_G = 4;  // chunks of 32 carts walked together per survivor
 
-template <bool TRACE>
+// D4 = true: depth-4 carts (7 nodes, 8 leaves) as compile-time constants -- the shipped model and the only depth the
+// reference's C path can load (c/jda.c:24-32).  D4 = false: depth 2..6 from the model header.
+template <bool TRACE, bool D4 = true>
 __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constant__ CascadeParams P) {
   extern __shared__ __align__(16) uint8_t smem3[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = 2 * P.L;
+  const int NN = D4 ? kNodes : P.nn, NL = D4 ? kLeaves : P.nl, DL = D4 ? kDepth - 1 : P.depth - 1;
   const int per_warp = kMaxDim * 4 + ((P.K + 15) & ~15);
   float *shape = reinterpret_cast<float *>(smem3 + (size_t)warp * per_warp);
   uint8_t *leafs = reinterpret_cast<uint8_t *>(shape + kMaxDim);
@@ -790,16 +797,19 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
 
     __syncwarp();
     const bool resumed = !P.dense && P.t_start > 0;
-    for (int i = lane; i < D; i += 32) shape[i] = resumed ? P.init_shape[(size_t)e * D + i] : P.mean_shape[i];
+    for (int i = lane; i < D; i += 32)
+      shape[i] = (resumed && P.init_shape) ? P.init_shape[(size_t)e * D + i] : P.mean_shape[i];
     __syncwarp();
 
     float score = resumed ? score0 : 0.f;
-    int n_eval = resumed ? P.t_start * P.K : 0;
+    int n_eval = resumed ? P.n_eval0 : 0;
     bool rejected = false;
-    for (int t = resumed ? P.t_start : 0; t < P.t_run && !rejected; t++) {
+    const int t_end = P.t_run + (P.k_extra > 0 ? 1 : 0);
+    for (int t = resumed ? P.t_start : 0; t < t_end && !rejected; t++) {
+      const int Kt = t < P.t_run ? P.K : P.k_extra;  // the unfinished stage of a truncated cascade stops after k_extra carts
       // K3_G chunks of 32 carts are walked together (independent load chains: the tree walk is a string of
       // dependent L2 accesses), then their scores are replayed chunk by chunk with early exit
-      for (int kc = 0; kc < P.K && !rejected; kc += 32 * K3_G) {
+      for (int kc = 0; kc < Kt && !rejected; kc += 32 * K3_G) {
         float ls[K3_G];
         float4 cp[K3_G];
         int idx[K3_G];
@@ -808,14 +818,14 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
 #pragma unroll
         for (int g = 0; g < K3_G; g++) {
           const int k = kc + 32 * g + lane;
-          ok[g] = k < P.K;
-          nd[g] = P.nodes + ((size_t)t * P.K + (ok[g] ? k : 0)) * kNodes;
+          ok[g] = k < Kt;
+          nd[g] = P.nodes + ((size_t)t * P.K + (ok[g] ? k : 0)) * NN;
           idx[g] = 0;
           ls[g] = 0.f;
           cp[g] = make_float4(0.f, 0.f, 1.f, 0.f);
         }
 #pragma unroll
-        for (int lvl = 0; lvl < kDepth - 1; lvl++) {
+        for (int lvl = 0; lvl < DL; lvl++) {
           int4 a[K3_G];
           float4 o[K3_G];
 #pragma unroll
@@ -857,16 +867,16 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
           if (ok[g]) {
             const int k = kc + 32 * g + lane;
             const size_t c = (size_t)t * P.K + k;
-            const int lf = idx[g] - kNodes;
+            const int lf = idx[g] - NN;
             leafs[k] = (uint8_t)lf;
-            ls[g] = __ldg(P.leaf + c * kLeaves + lf);
+            ls[g] = __ldg(P.leaf + c * NL + lf);
             cp[g] = __ldg(P.cart + c);
           }
         }
         // replay the score in cart order, one chunk of 32 at a time
 #pragma unroll
         for (int g = 0; g < K3_G; g++) {
-          const int cnt = min(32, P.K - (kc + 32 * g));
+          const int cnt = min(32, Kt - (kc + 32 * g));
           if (cnt <= 0 || rejected) continue;
           const unsigned normed = __ballot_sync(0xffffffffu, cp[g].y != 0.f || cp[g].z != 1.f);  // carts with a real (mean, std)
           int stop = -1;
@@ -887,10 +897,10 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
           if (stop >= 0) rejected = true;
         }
       }
-      if (rejected) break;
+      if (rejected || t >= P.t_run) break;  // no regression after the carts of an unfinished stage (cascador.cpp:199-209)
       __syncwarp();
       // global regression, c/jda.c:403-411
-      const float *wt = P.w + (size_t)t * P.K * kLeaves * D;
+      const float *wt = P.w + (size_t)t * P.K * NL * D;
       for (int i0 = 0; i0 < D; i0 += 64) {
         // two coordinates per lane per sweep over the K rows (independent chains, each k ascending).  The 16
         // row loads of a batch are issued together before their adds: the gather is a string of L2 reads.
@@ -901,7 +911,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constan
 #pragma unroll
           for (int u = 0; u < 16; u++) {
             const int k = min(k0 + u, P.K - 1);
-            const float *row = wt + (size_t)(k * kLeaves + leafs[k]) * D + i0 + lane;
+            const float *row = wt + (size_t)(k * NL + leafs[k]) * D + i0 + lane;
             v0[u] = on0 ? __ldg(row) : 0.f;
             v1[u] = on1 ? __ldg(row + 32) : 0.f;
           }

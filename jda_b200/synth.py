@@ -104,7 +104,8 @@ def fddb_shape(seed):
 # ------------------------------------------------------------------ models
 
 def write_model(path, seed=0, T=5, K=540, L=27, depth=4, double=True, scales=(0,),
-                mode="reject", norm_every=270, w_amp=2e-4, coord_max=None):
+                mode="reject", norm_every=270, w_amp=2e-4, coord_max=None, scales_by_stage=None,
+                header_stage=None):
     """Random model in the reference's file layout.
 
     mode: 'passall' -> every cart threshold -1e30 (all windows run T*K carts + T regressions)
@@ -112,6 +113,10 @@ def write_model(path, seed=0, T=5, K=540, L=27, depth=4, double=True, scales=(0,
     scales: allowed node.scale values; with 1/2 present pass coord_max (~0.45) so sampled
             coordinates stay inside the region where the reference's h/q indexing is defined.
     norm_every: carts k with (k+1) % norm_every == 0 get a non-trivial (mean, std).
+    scales_by_stage: {stage: allowed scales} overriding `scales` for those stages, e.g. {0: (0,)} keeps
+            stage 0 on the o plane (the LUT scan serves it) while later stages sample the h / q planes.
+    header_stage: value of the header's current_stage_idx field (default T, what the C++ trainer writes
+            for a finished model; the C serialiser writes T + 1, c/jda.c:662-665).
     """
     rng = np.random.default_rng(seed)
     nl = 1 << (depth - 1)
@@ -121,11 +126,13 @@ def write_model(path, seed=0, T=5, K=540, L=27, depth=4, double=True, scales=(0,
     mean = rng.uniform(0.25, 0.75, D)
     if coord_max is not None:
         mean = rng.uniform(0.12, coord_max - 0.1, D)
-    chunks = [struct.pack("<7i", 0, T, K, L, depth, T, -1), mean.astype(real).tobytes()]
+    chunks = [struct.pack("<7i", 0, T, K, L, depth, T if header_stage is None else header_stage, -1),
+              mean.astype(real).tobytes()]
     for t in range(T):
+        st_scales = (scales_by_stage or {}).get(t, scales)
         for k in range(K):
             for i in range(nn):
-                sc = int(rng.choice(scales))
+                sc = int(rng.choice(st_scales))
                 l1, l2 = int(rng.integers(0, L)), int(rng.integers(0, L))
                 off = rng.uniform(-0.12, 0.12, 4)
                 if coord_max is not None:

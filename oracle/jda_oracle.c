@@ -55,6 +55,8 @@ typedef struct {
   float *leaf;         /* [(t*K+k)*nl + j] */
   float *cth, *cmean, *cstd;
   float *w;            /* [t][K*nl][2L] */
+  int k_extra;         /* scan(): after the T full stages, carts [0, k_extra) of stage T without regression
+                          (Validate's unfinished stage, src/jda/cascador.cpp:199-209); 0 in a loaded model */
 } Model;
 
 /* ---------------------------------------------------------------- model IO */
@@ -224,8 +226,12 @@ static int eval_window(const Model *m, const Plane pl[3], int x, int y, int win,
   int evaluated = 0;
   int *lbf = (int *)malloc(m->K * sizeof(int));
   int pass = 1;
-  for (int t = 0; t < m->T && pass; t++) {
-    for (int k = 0; k < m->K; k++) {
+  const int t_end = m->T + (m->k_extra > 0 ? 1 : 0);
+  for (int t = 0; t < t_end && pass; t++) {
+    /* stage T of a truncated cascade stops after k_extra carts and has no regression
+       (src/jda/cascador.cpp:199-209: carts [0, current_cart_idx] of the stage being trained) */
+    const int Kt = t < m->T ? m->K : m->k_extra;
+    for (int k = 0; k < Kt; k++) {
       size_t c = (size_t)t * m->K + k;
       int idx = 0;
       for (int lv = 0; lv < m->depth - 1; lv++) {
@@ -261,7 +267,7 @@ static int eval_window(const Model *m, const Plane pl[3], int x, int y, int win,
       if (score < m->cth[c]) { pass = 0; break; }
       lbf[k] = k * m->nl + leaf;
     }
-    if (!pass) break;
+    if (!pass || t >= m->T) break;
     if (st) st->stage_survivors[t]++;
     const float *wt = m->w + (size_t)t * m->K * m->nl * D;
     for (int k = 0; k < m->K; k++) {
@@ -295,16 +301,24 @@ static void hits_push(Hits *h, int D, int x, int y, int win, float score, const 
  * Scan of c/jda.c:318-439 with instrumentation.
  *   t_limit  : stages to run (m->T for detection; fewer mirrors Validate's
  *              current_stage_idx loop for mining, src/jda/cascador.cpp:178-197)
+ *   k_limit  : > 0: t_limit counts FULL stages (0 allowed) and carts [0, k_limit) of stage t_limit
+ *              follow without regression (Validate's current_cart_idx + 1, cascador.cpp:199-209)
  *   use_th   : apply the final threshold (c/jda.c:414)
  *   trace_n  : optional [windows] carts evaluated per window, scan order
  *   trace_s  : optional [windows] score at exit per window
  *   trace_leaf, leaf_w0, leaf_w1 : optional leaf indices of windows [w0,w1), [T*K] each
  */
 static void scan(const Model *m0, const uint8_t *img, int w, int h, float scale, int min_size,
-                 int max_size, float th, int t_limit, int use_th, Hits *hits, Stats *st,
+                 int max_size, float th, int t_limit, int k_limit, int use_th, Hits *hits, Stats *st,
                  int *trace_n, float *trace_s, uint8_t *trace_leaf, long long leaf_w0, long long leaf_w1) {
   Model mm = *m0;
-  if (t_limit > 0 && t_limit < mm.T) mm.T = t_limit;
+  mm.k_extra = 0;
+  if (k_limit > 0 && t_limit >= 0 && t_limit < mm.T) {
+    mm.T = t_limit;
+    mm.k_extra = k_limit < mm.K ? k_limit : mm.K;
+  } else if (t_limit > 0 && t_limit < mm.T) {
+    mm.T = t_limit;
+  }
   const Model *m = &mm;
   const float r = 1.f / sqrtf(2.f);
   int hw = (int)(w * r), hh = (int)(h * r), qw = w / 2, qh = h / 2;
@@ -381,18 +395,23 @@ typedef struct {
 void jdo_result_free(jdoResult r) { free(r.bboxes); free(r.shapes); free(r.scores); }
 
 /* pre-NMS hits in scan order, shapes still window-normalised (c/jda.c:416-437) */
-jdoResult jdo_detect_raw(void *m_, const uint8_t *img, int w, int h, float scale, int min_size,
-                         int max_size, float th, int t_limit, int use_th, long long *stats_out) {
+jdoResult jdo_detect_raw_k(void *m_, const uint8_t *img, int w, int h, float scale, int min_size,
+                           int max_size, float th, int t_limit, int k_limit, int use_th, long long *stats_out) {
   Model *m = (Model *)m_;
   Hits hits = {0, 0, NULL, NULL, NULL};
   Stats st; memset(&st, 0, sizeof st);
-  scan(m, img, w, h, scale, min_size, max_size, th, t_limit, use_th, &hits, &st, NULL, NULL, NULL, 0, 0);
+  scan(m, img, w, h, scale, min_size, max_size, th, t_limit, k_limit, use_th, &hits, &st, NULL, NULL, NULL, 0, 0);
   if (stats_out) {
     stats_out[0] = st.windows; stats_out[1] = st.carts; stats_out[2] = st.ub_reads;
     for (int t = 0; t < 16; t++) stats_out[3 + t] = st.stage_survivors[t];
   }
   jdoResult r = {hits.n, m->L, hits.box, hits.shape, hits.score};
   return r;
+}
+
+jdoResult jdo_detect_raw(void *m_, const uint8_t *img, int w, int h, float scale, int min_size,
+                         int max_size, float th, int t_limit, int use_th, long long *stats_out) {
+  return jdo_detect_raw_k(m_, img, w, h, scale, min_size, max_size, th, t_limit, 0, use_th, stats_out);
 }
 
 /* full jdaDetect, c/jda.c:443-480 */
@@ -430,13 +449,19 @@ jdoResult jdo_detect(void *m_, const uint8_t *img, int w, int h, float scale, fl
 
 /* per-window trace: carts evaluated + exit score for every window (scan order),
  * leaf indices for windows [leaf_w0, leaf_w1).  Returns the window count. */
+long long jdo_trace_k(void *m_, const uint8_t *img, int w, int h, float scale, int min_size, int max_size,
+                      int t_limit, int k_limit, int *trace_n, float *trace_s, uint8_t *trace_leaf,
+                      long long leaf_w0, long long leaf_w1) {
+  Stats st; memset(&st, 0, sizeof st);
+  scan((Model *)m_, img, w, h, scale, min_size, max_size, 0.f, t_limit, k_limit, 0, NULL, &st,
+       trace_n, trace_s, trace_leaf, leaf_w0, leaf_w1);
+  return st.windows;
+}
+
 long long jdo_trace(void *m_, const uint8_t *img, int w, int h, float scale, int min_size, int max_size,
                     int t_limit, int *trace_n, float *trace_s, uint8_t *trace_leaf,
                     long long leaf_w0, long long leaf_w1) {
-  Stats st; memset(&st, 0, sizeof st);
-  scan((Model *)m_, img, w, h, scale, min_size, max_size, 0.f, t_limit, 0, NULL, &st,
-       trace_n, trace_s, trace_leaf, leaf_w0, leaf_w1);
-  return st.windows;
+  return jdo_trace_k(m_, img, w, h, scale, min_size, max_size, t_limit, 0, trace_n, trace_s, trace_leaf, leaf_w0, leaf_w1);
 }
 
 /* number of candidate windows enumerated by c/jda.c:332-339 */

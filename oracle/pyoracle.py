@@ -119,6 +119,15 @@ class Oracle:
         L.jdo_detect_raw.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int,
                                      C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                      C.POINTER(C.c_longlong)]
+        L.jdo_detect_raw_k.restype = _Result
+        L.jdo_detect_raw_k.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int,
+                                       C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_longlong)]
+        L.jdo_trace_k.restype = C.c_longlong
+        L.jdo_trace_k.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_float,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_float), C.POINTER(C.c_ubyte),
+                                  C.c_longlong, C.c_longlong]
         L.jdo_result_free.argtypes = [_Result]
         L.jdo_result_free.restype = None
         L.jdo_trace.restype = C.c_longlong
@@ -172,18 +181,20 @@ class Oracle:
         return _unpack(res, self.lib.jdo_result_free)
 
     def detect_raw(self, h, img, scale=1.25, min_size=24, max_size=-1, th=0.0,
-                   t_limit=0, use_th=True):
-        """pre-NMS hits (scan order, normalised shapes) + stats dict."""
+                   t_limit=0, use_th=True, k_limit=0):
+        """pre-NMS hits (scan order, normalised shapes) + stats dict.
+        k_limit > 0: t_limit full stages (0 allowed), then carts [0, k_limit) of stage t_limit, no regression
+        after them (Validate's unfinished stage, src/jda/cascador.cpp:199-209)."""
         a, p, w, hh = _img(img)
         st = (C.c_longlong * self.N_STATS)()
-        res = self.lib.jdo_detect_raw(h, p, w, hh, scale, min_size, max_size, th,
-                                      t_limit, 1 if use_th else 0, st)
+        res = self.lib.jdo_detect_raw_k(h, p, w, hh, scale, min_size, max_size, th,
+                                        t_limit, k_limit, 1 if use_th else 0, st)
         boxes, scores, shapes = _unpack(res, self.lib.jdo_result_free)
         stats = {"windows": st[0], "carts": st[1], "ub_reads": st[2],
                  "stage_survivors": list(st[3:3 + 16])}
         return boxes, scores, shapes, stats
 
-    def trace(self, h, img, scale=1.25, min_size=24, max_size=-1, t_limit=0, leaf_range=None):
+    def trace(self, h, img, scale=1.25, min_size=24, max_size=-1, t_limit=0, leaf_range=None, k_limit=0):
         """per-window (carts evaluated, exit score) in scan order; optional leaves."""
         a, p, w, hh = _img(img)
         nwin = self.count_windows(w, hh, scale, min_size, max_size)
@@ -197,7 +208,7 @@ class Oracle:
         else:
             w0 = w1 = 0
             lv, lp = None, None
-        n = self.lib.jdo_trace(h, p, w, hh, scale, min_size, max_size, t_limit,
+        n = self.lib.jdo_trace_k(h, p, w, hh, scale, min_size, max_size, t_limit, k_limit,
                                tn.ctypes.data_as(C.POINTER(C.c_int)),
                                ts.ctypes.data_as(C.POINTER(C.c_float)), lp, w0, w1)
         assert n == nwin, (n, nwin)

@@ -170,6 +170,9 @@ SYN = [
     dict(seed=3, mode="reject", scales=(0, 1, 2), coord_max=0.45),
     dict(seed=4, mode="passall", scales=(0, 1, 2), coord_max=0.45),
     dict(seed=5, mode="reject", scales=(0,), norm_every=7),      # > 32 normalised carts: generic path
+    # stage 0 all scale 0 (LUT scan), later stages sample h / q: k2_scan -> k3_stage0 -> k3_cascade reading the planes
+    dict(seed=6, mode="reject", scales=(0, 1, 2), coord_max=0.45, scales_by_stage={0: (0,)}),
+    dict(seed=7, mode="passall", scales=(0, 1, 2), coord_max=0.45, scales_by_stage={0: (0,)}),
 ]
 
 
@@ -191,6 +194,51 @@ def test_synthetic_models(oracle, tmp_path, cfg):
         np.testing.assert_array_equal(_bits(ts), _bits(os_))
         np.testing.assert_array_equal(lv, olv)
     c.close(); oracle.release(ho)
+
+
+@pytest.mark.parametrize("n_frames", [9, 130])
+def test_scan_plus_planes_batches(oracle, tmp_path, n_frames):
+    """Stage 0 from the LUT scan, stages >= 1 sampling the h / q planes, in batch mode (cohort-staged stage 0; 130
+    frames: the size at which a scale-0 model would be copied in chunks -- a model with planes must not be).
+    c/jda.c:340-354, 385-394."""
+    path = synth.write_model(str(tmp_path / "syn.model"), seed=6, mode="reject", scales=(0, 1, 2), coord_max=0.45,
+                             scales_by_stage={0: (0,)})
+    c = api.Cascador(path, double=True)
+    ho = oracle.load(path, True)
+    frames = synth.make_frames("facemix", n_frames, 112, 90, seed0=300)
+    res = c.detect_batch(frames, th=-1e30, flags=api.RAW_HITS)
+    st = c.last_stats
+    assert st["scan_launches"] >= 1 and st["resize_launches"] == 1, st
+    hits = 0
+    for f in range(n_frames):
+        ob, osc, osh, ost = oracle.detect_raw(ho, frames[f], th=-1e30)
+        assert ost["ub_reads"] == 0
+        _same(res[f], (ob, osc, osh))
+        hits += len(osc)
+    assert hits > 0
+    # mixed sizes with such a model go shape group by shape group (the canvas path needs a plane-free model)
+    sizes = [(112, 90), (90, 112), (112, 90), (64, 48), (90, 112)]
+    imgs = [synth.facemix_frame(400 + i, w, h) for i, (w, h) in enumerate(sizes)]
+    got = c.detect_mixed(imgs, th=-1e30)
+    for g, img in zip(got, imgs):
+        _same(g, oracle.detect(ho, img, th=-1e30))
+    c.close(); oracle.release(ho)
+
+
+def test_more_than_twenty_pyramid_levels(casc, oracle, oracle_shipped):
+    """1080p at scale 1.2 visits 22 window sizes, 4K at the reference's own 1.25 visits 21 (c/jda.c:331-332):
+    round 1 refused both (kMaxLevels = 20)."""
+    assert len(api.levels(1920, 1080, 1.2, 24, -1)) == 22 and len(api.levels(3840, 2160, 1.25, 24, -1)) == 21
+    img = synth.facemix_frame(77, 1920, 1080)
+    _same(casc.detect(img, scale=1.2), oracle.detect(oracle_shipped, img, scale=1.2))
+    # 4K: flat background (cheap for the CPU oracle) with faces pasted at several sizes
+    big = np.full((2160, 3840), 100, np.uint8)
+    small = synth.face_canvas()
+    big[200:200 + 480, 300:300 + 640] = small
+    big[1200:1200 + 960, 2000:2000 + 1280] = np.kron(small, np.ones((2, 2), np.uint8))
+    got = casc.detect(big)
+    _same(got, oracle.detect(oracle_shipped, big))
+    assert len(got[1]) >= 2
 
 
 DIMS = [dict(T=2, K=33, L=5), dict(T=3, K=96, L=40), dict(T=1, K=540, L=27), dict(T=6, K=64, L=16),
@@ -224,6 +272,30 @@ def test_model_dimensions_from_the_header(oracle, tmp_path, dims, mode):
     out = tmp_path / "rt.model"
     c.save_f32(str(out)); oracle.save_f32(ho, str(tmp_path / "rt_o.model"))
     assert out.read_bytes() == (tmp_path / "rt_o.model").read_bytes()
+    c.close(); oracle.release(ho)
+
+
+@pytest.mark.parametrize("depth", [2, 3, 5, 6])
+def test_tree_depth_from_the_header(oracle, tmp_path, depth):
+    """tree_depth 2..6 (c/jda.c:24-32 compiles in 4): every stage through the generic cascade
+    kernel with run-time node / leaf counts.  Oracle = the restatement (the reference binary only loads depth 4)."""
+    path = synth.write_model(str(tmp_path / "d.model"), seed=50 + depth, T=3, K=70, L=11, depth=depth, norm_every=9)
+    c = api.Cascador(path, double=True)
+    ho = oracle.load(path, True)
+    assert c.depth == depth
+    frames = [synth.blur_frame(9, 96, 80), synth.facemix_frame(3, 200, 150)]
+    for img in frames:
+        for kw in (dict(th=-1e30), dict(scale=1.3, min_size=30, max_size=60, th=0.0)):
+            _same(c.detect(img, **kw), oracle.detect(ho, img, **kw))
+    batch = synth.make_frames("facemix", 7, 120, 90, seed0=5)
+    for g, f in zip(c.detect_batch(batch, th=-1e30, flags=api.RAW_HITS, t_limit=1, k_limit=33), batch):
+        ob, osc, osh, _ = oracle.detect_raw(ho, f, th=-1e30, t_limit=1, k_limit=33)
+        _same(g, (ob, osc, osh))
+    tn, ts, lv = c.trace(frames[0], leaf_range=(0, 400))
+    on, os_, olv = oracle.trace(ho, frames[0], leaf_range=(0, 400))
+    np.testing.assert_array_equal(tn, on)
+    np.testing.assert_array_equal(_bits(ts), _bits(os_))
+    np.testing.assert_array_equal(lv, olv)
     c.close(); oracle.release(ho)
 
 
@@ -400,6 +472,32 @@ def test_mining_mode_truncated_cascade(casc, oracle, oracle_shipped, t_limit):
     ob, osc, osh, st = oracle.detect_raw(oracle_shipped, img, t_limit=t_limit, use_th=False)
     assert len(osc) == st["stage_survivors"][t_limit - 1] > 0
     _same(got, (ob, osc, osh))
+
+
+@pytest.mark.parametrize("tk", [(0, 18), (0, 540), (2, 101), (1, 1), (4, 270)], ids=lambda tk: "t%d_k%d" % tk)
+@pytest.mark.parametrize("n_frames", [1, 6])
+def test_mining_mode_cart_granular(casc, oracle, oracle_shipped, tk, n_frames):
+    """Validate() while a stage is being trained (src/jda/cascador.cpp:178-209, caller btcart.cpp:146-152):
+    t full stages, then carts [0, k) of stage t, no regression after them.  1 frame: latency plan (k3_cascade
+    redoes stage 0); 6 frames: throughput plan (k2_scan -> k3_stage0 -> k3_cascade)."""
+    t, k = tk
+    frames = np.stack([synth.face_canvas()] + [synth.facemix_frame(90 + i) for i in range(n_frames - 1)])
+    got = casc.detect_batch(frames, t_limit=t, k_limit=k, flags=api.RAW_HITS | api.NO_FINAL_TH)
+    total = 0
+    for f in range(n_frames):
+        ob, osc, osh, st = oracle.detect_raw(oracle_shipped, frames[f], t_limit=t, k_limit=k, use_th=False)
+        _same(got[f], (ob, osc, osh))
+        total += len(osc)
+    assert total > 0
+    if n_frames == 1:  # per-window trace: carts evaluated stop at t*K + k, exit score, leaves of the partial stage
+        nwin = api.count_windows(640, 480)
+        rng = (nwin - 2500, nwin)
+        tn, ts, lv = casc.trace(frames[0], t_limit=t, k_limit=k, leaf_range=rng)
+        on, os_, olv = oracle.trace(oracle_shipped, frames[0], t_limit=t, k_limit=k, leaf_range=rng)
+        assert on.max() == t * 540 + k
+        np.testing.assert_array_equal(tn, on)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+        np.testing.assert_array_equal(lv, olv)
 
 
 def test_concurrent_callers_and_changing_arguments(casc, oracle, oracle_shipped):

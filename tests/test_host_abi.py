@@ -63,12 +63,53 @@ def test_bad_models_are_rejected(tmp_path):
     p.write_bytes(open(SHIPPED_F32, "rb").read()[:100000])
     with pytest.raises(RuntimeError):
         api.Cascador(str(p), double=False)
-    q = tmp_path / "depth5.model"
+    q = tmp_path / "depth5.model"          # depth 5 is a legal header now, but this file holds depth-4 carts: short read
     b = bytearray(open(SHIPPED_F32, "rb").read())
     b[16:20] = (5).to_bytes(4, "little")
     q.write_bytes(bytes(b))
     with pytest.raises(RuntimeError):
         api.Cascador(str(q), double=False)
+    b[16:20] = (7).to_bytes(4, "little")      # outside 2..6
+    q.write_bytes(bytes(b))
+    with pytest.raises(RuntimeError):
+        api.Cascador(str(q), double=False)
+
+
+@pytest.mark.parametrize("depth", [2, 3, 5, 6])
+def test_tree_depth_comes_from_the_header(oracle, tmp_path, depth):
+    """c/jda.c:24-32 fixes JDA_TREE_DEPTH = 4 at compile time; here the loader takes it from the
+    header (README.md:84-111) and the serialiser writes it back.  Oracle = the restatement, which does the same."""
+    path = synth.write_model(str(tmp_path / "d.model"), seed=40 + depth, T=2, K=50, L=9, depth=depth)
+    c = api.Cascador(path, double=True)
+    h = oracle.load(path, True)
+    assert (c.T, c.K, c.L, c.depth) == (2, 50, 9, depth) == oracle.dims(h)
+    a, b = tmp_path / "a", tmp_path / "b"
+    c.save_f32(str(a)); oracle.save_f32(h, str(b))
+    assert a.read_bytes() == b.read_bytes()
+    c.close(); oracle.release(h)
+
+
+def test_serialiser_flags_stage_field_and_double_flavour(tmp_path):
+    """c/jda.c:662-665 writes the header's stage field as T + 1, which cascador.cpp:138 refuses; jdaB200SerializeTo
+    can write T and the double flavour the C++ loader reads."""
+    import struct
+    c = api.Cascador(SHIPPED_F32, double=False)
+    plain, fixed, wide = tmp_path / "p", tmp_path / "f", tmp_path / "w"
+    c.save(str(plain), 0)
+    assert plain.read_bytes() == open(SHIPPED_F32, "rb").read()                  # flags 0 = jdaCascadorSerializeTo
+    c.save(str(fixed), api.SAVE_STAGE_T)
+    fb, pb = fixed.read_bytes(), plain.read_bytes()
+    assert struct.unpack("<7i", pb[:28]) == (0, 5, 540, 27, 4, 6, -1)
+    assert struct.unpack("<7i", fb[:28]) == (0, 5, 540, 27, 4, 5, -1) and fb[28:] == pb[28:]
+    c.save(str(wide), api.SAVE_STAGE_T | api.SAVE_DOUBLE)
+    assert wide.stat().st_size == 10476464                                     # the shipped double model's size
+    ref_wide = synth.widen_f32_model(SHIPPED_F32, str(tmp_path / "rw"))
+    assert wide.read_bytes() == open(ref_wide, "rb").read()
+    c2 = api.Cascador(str(wide), double=True)                                  # and back: exact round trip
+    back = tmp_path / "b"
+    c2.save_f32(str(back))
+    assert back.read_bytes() == pb
+    c.close(); c2.close()
 
 
 @pytest.mark.parametrize("w,h,scale,mn,mx", [(640, 480, 1.25, 24, -1), (640, 480, 1.25, 24, 192),

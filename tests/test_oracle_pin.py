@@ -114,6 +114,9 @@ SYN = [
     dict(seed=2, mode="reject", scales=(0,)),
     dict(seed=3, mode="reject", scales=(0, 1, 2), coord_max=0.45),
     dict(seed=4, mode="passall", scales=(0, 1, 2), coord_max=0.45, double=False),
+    # stage 0 on the o plane only, h / q nodes from stage 1 on: the model shape that takes the LUT scan AND the planes
+    dict(seed=6, mode="reject", scales=(0, 1, 2), coord_max=0.45, scales_by_stage={0: (0,)}),
+    dict(seed=7, mode="passall", scales=(0, 1, 2), coord_max=0.45, scales_by_stage={0: (0,)}),
 ]
 
 
@@ -161,3 +164,33 @@ def test_nms_passall_many_hits(oracle, reflib, tmp_path):
     assert len(raw[1]) == oracle.count_windows(128, 100) and len(want[1]) < len(raw[1])
     _same(got, want)
     oracle.release(ho); reflib.release(hr)
+
+
+def test_oracle_cart_granular_truncation_properties(oracle, oracle_shipped):
+    """k_limit (Validate's unfinished stage, src/jda/cascador.cpp:199-209) has no reference binary behind it on the
+    float path, so it is pinned through properties against the reference-pinned whole-stage cascade: stopping after
+    ALL K carts of stage t passes exactly the windows that t + 1 whole stages pass, with the same scores, and their
+    shapes are the shapes after t whole stages (no regression follows an unfinished stage); carts evaluated never
+    exceed t*K + k and windows that die earlier die at the same cart with the same score."""
+    from jda_b200 import synth
+    img = synth.face_canvas()
+    K = 540
+    for t in (0, 1, 3):
+        pb, ps, psh, _ = oracle.detect_raw(oracle_shipped, img, t_limit=t, k_limit=K, use_th=False)
+        fb, fs, fsh, _ = oracle.detect_raw(oracle_shipped, img, t_limit=t + 1, use_th=False)
+        np.testing.assert_array_equal(pb, fb)
+        np.testing.assert_array_equal(ps.view(np.uint32), fs.view(np.uint32))
+        assert len(ps) > 0 and not np.array_equal(psh, fsh)
+        if t > 0:
+            tb, _, tsh, _ = oracle.detect_raw(oracle_shipped, img, t_limit=t, use_th=False)
+            keys = {tuple(b): i for i, b in enumerate(tb.tolist())}
+            idx = [keys[tuple(b)] for b in pb.tolist()]
+            np.testing.assert_array_equal(psh.view(np.uint32), tsh[idx].view(np.uint32))
+    full_n, full_s, _ = oracle.trace(oracle_shipped, img)
+    for t, k in ((0, 18), (2, 101)):
+        n, s, _ = oracle.trace(oracle_shipped, img, t_limit=t, k_limit=k)
+        cap = t * K + k
+        np.testing.assert_array_equal(n, np.minimum(full_n, cap))
+        early = full_n < cap
+        np.testing.assert_array_equal(s[early].view(np.uint32), full_s[early].view(np.uint32))
+        assert (n == cap).sum() > 0
