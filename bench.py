@@ -14,6 +14,14 @@ value : whole-job windows/s with the frames already resident in HBM (device poin
 e2e   : same metric through the reference-facing call with HOST frames (pinned): H2D of every frame
         and D2H of the hit records happen inside the timed region.
 Prints ONE JSON line on rank 0.
+
+    --workload cfg4   BASELINE.json configs[3]: 2845 FDDB-shaped frames of mixed sizes, sharded over the ranks in
+                      contiguous blocks (STRONG scaling: the job is fixed), jdaB200DetectMixed per rank + one NCCL
+                      all-gather of the detection records; every rank checks that it holds the same job-wide table.
+    --workload cfg5   BASELINE.json configs[4]: hard-negative mining scan over 100,000 VGA backgrounds (sigma in
+                      {0,1,2,4,6} by seed mod 5), truncated cascade (--mine-t / --mine-k = Validate's
+                      current_stage_idx / current_cart_idx + 1), every survivor emitted and all-gathered (strong scaling).
+The default workload (vga) is the headline the driver runs; cfg4 / cfg5 print the same JSON contract.
 """
 import argparse
 import json
@@ -32,6 +40,9 @@ W, H = 640, 480
 ARGS = dict(scale=1.25, min_size=24, max_size=192, th=0.0)
 WINDOWS_PER_FRAME = 169236
 METRIC = "candidate windows/sec, VGA 3-octave pyramid (scale 1.25, min 24, max 192), full cascade"
+METRIC_BY_WORKLOAD = {"vga": METRIC,
+                      "cfg4": "candidate windows/sec, 2845 FDDB-shaped frames (longest side 450), full pyramid, full cascade",
+                      "cfg5": "candidate windows/sec, mining scan over 100k VGA backgrounds (3-octave pyramid, truncated cascade, every survivor emitted)"}
 
 
 def frame_pool(n_distinct, dist, seed0):
@@ -131,12 +142,79 @@ def cpu_reference_run(frames, threads, use_ref=True):
     return dt, kind
 
 
+def cpu_frames_run(frames, threads, kw):
+    """the reference's jdaDetect over a list of frames of any sizes on `threads` host threads; returns seconds, kind"""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    if os.path.exists(pyoracle.REF_SO):
+        lib, kind = pyoracle.RefLib(), "reference"
+    else:
+        lib, kind = pyoracle.Oracle(), "port"
+    h = lib.load(MODEL, double=False)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda f: lib.detect(h, f, kw["scale"], 0.1, kw["min_size"], kw["max_size"], kw["th"]), frames))
+    dt = time.perf_counter() - t0
+    lib.release(h)
+    return dt, kind
+
+
+CFG4_FRAMES, CFG4_DISTINCT = 2845, 48
+CFG4_ARGS = dict(scale=1.25, min_size=24, max_size=-1, th=0.0)
+CFG5_FRAMES, CFG5_DISTINCT = 100000, 40
+
+
+def cfg4_pool():
+    from jda_b200 import synth
+    return [synth.facemix_frame(11000 + i, *synth.fddb_shape(i)) for i in range(CFG4_DISTINCT)]
+
+
+def cfg4_windows(api_or_oracle_count, frames):
+    return sum(api_or_oracle_count(f.shape[1], f.shape[0], 1.25, 24, -1) for f in frames)
+
+
+def cfg5_pool():
+    from jda_b200 import synth
+    return np.stack([synth.mining_background(21000 + i) for i in range(CFG5_DISTINCT)])
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     n = max(8, min(2 * cores, 256))  # two frames per host thread so every core stays busy for the whole step
+    if a.workload in ("cfg4", "cfg5"):
+        # the reference's jdaDetect on a bounded sample of the same frames; it has no truncated-cascade entry point
+        # in its C API (Validate lives in the C++ tree), so the mining scan is timed as full detects of the backgrounds
+        # -- on face-free frames nearly every window dies inside stage 0 either way
+        from oracle import pyoracle
+        if a.workload == "cfg4":
+            pool = cfg4_pool()
+            frames = [pool[i % len(pool)] for i in range(n)]
+            kw, name = CFG4_ARGS, "fddb_2845_mixed_sizes"
+            wins = cfg4_windows(pyoracle.Oracle().count_windows, frames)
+        else:
+            pool = cfg5_pool()
+            frames = [pool[i % len(pool)] for i in range(n)]
+            kw, name = ARGS, "mining_100k_backgrounds"
+            wins = n * WINDOWS_PER_FRAME
+        for _ in range(a.warmup):
+            cpu_frames_run(frames[:max(2, n // 4)], cores, kw)
+        tot, kind = 0.0, "port"
+        for _ in range(a.steps):
+            dt, kind = cpu_frames_run(frames, cores, kw)
+            tot += dt
+        val = a.steps * wins / tot
+        print(json.dumps({"impl": "reference", "metric": METRIC_BY_WORKLOAD[a.workload], "value": val, "unit": "windows/s",
+                          "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8",
+                          "data": "synthetic", "config": {"workload": name, "frames_per_step": n, **kw},
+                          "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": kind,
+                                           "sample": "%d frames of the workload per step, %d threads over jdaDetect" % (n, cores)},
+                          "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     pool = frame_pool(min(n, 96), a.dist, 0)
     pool = pool[np.arange(n) % len(pool)]
     for _ in range(a.warmup):
@@ -167,6 +245,9 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--dist", default="mix", choices=["mix", "noise", "blur6", "facemix"])
     ap.add_argument("--distinct", type=int, default=96, help="distinct synthetic frames tiled into a batch")
+    ap.add_argument("--workload", default="vga", choices=["vga", "cfg4", "cfg5"])
+    ap.add_argument("--mine-t", type=int, default=1, help="cfg5: full stages of the truncated cascade (current_stage_idx)")
+    ap.add_argument("--mine-k", type=int, default=0, help="cfg5: carts of the unfinished stage (current_cart_idx + 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     a = ap.parse_args()
@@ -192,10 +273,11 @@ def main():
     c.set_stream(stream.cuda_stream)
 
     B = a.batch
-    pool = frame_pool(a.distinct, a.dist, 100000 * rank)
-    host = [torch.from_numpy(tile_batch(pool, B, s)).pin_memory() for s in (0, 37)]
-    dev = [h.cuda(non_blocking=False) for h in host]
-    torch.cuda.synchronize()
+    if a.workload == "vga":
+        pool = frame_pool(a.distinct, a.dist, 100000 * rank)
+        host = [torch.from_numpy(tile_batch(pool, B, s)).pin_memory() for s in (0, 37)]
+        dev = [h.cuda(non_blocking=False) for h in host]
+        torch.cuda.synchronize()
 
     from jda_b200 import shard
 
@@ -243,11 +325,11 @@ def main():
         gather_records(res)
         return c.last_stats
 
-    def timed(step_fn, steps, warmup, sample_clocks=False):
+    def timed(step_fn, steps, warmup, sample_clocks=False, warm_fn=None):
         # the sampler starts before the warm-up: nvidia-smi needs ~0.5 s before its first line
         sampler = ClockSampler(local) if sample_clocks else None
         for i in range(warmup):
-            step_fn(i)
+            (warm_fn or step_fn)(i)
         exchange_wait()
         torch.cuda.synchronize()
         if dist_on:
@@ -279,6 +361,205 @@ def main():
         clocks = sampler.stop(t0, t1) if sampler else None
         return ms, acc, clocks
 
+    def table_check(table, n_local):
+        """every rank must hold the same job-wide table: compare a checksum and the record count across ranks"""
+        chk = int(np.ascontiguousarray(table, np.float32).view(np.uint32).astype(np.uint64).sum()) & ((1 << 62) - 1)
+        mine = torch.tensor([chk, len(table), n_local], dtype=torch.int64, device="cuda")
+        if dist_on:
+            allv = torch.empty(world * 3, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(allv, mine)
+            allv = allv.cpu().numpy().reshape(world, 3)
+        else:
+            allv = mine.cpu().numpy().reshape(1, 3)
+        fid = table[:, 0]
+        return {"ranks_agree": bool((allv[:, 0] == allv[0, 0]).all() and (allv[:, 1] == allv[0, 1]).all()),
+                "records": int(len(table)), "records_equal_sum_of_ranks": bool(int(allv[:, 2].sum()) == len(table)),
+                "frame_order": bool((np.diff(fid) >= 0).all()) if len(fid) > 1 else True}
+
+    def finish_line(out, metric_windows_per_step, cpu_fn):
+        """clocks / cpu_baseline / print, shared by the cfg4 and cfg5 workloads"""
+        if rank == 0:
+            if not a.no_cpu_baseline and world == 1:
+                out["cpu_baseline"] = cpu_fn()
+            print(json.dumps(out), flush=True)
+        c.close()
+        if dist_on:
+            exchange["pool"].shutdown()
+            dist.destroy_process_group()
+
+    # ------------------------------------------------------------------ config 4: 2845 FDDB-shaped frames, sharded
+    if a.workload == "cfg4":
+        poolm = cfg4_pool()
+        lo, hi = shard.shard_range(CFG4_FRAMES, rank, world)
+        sizes = [poolm[i % CFG4_DISTINCT].size for i in range(lo, hi)]
+        pin = torch.empty(max(sum(sizes), 1), dtype=torch.uint8).pin_memory().numpy()
+        fr, o = [], 0
+        for i in range(lo, hi):
+            f = poolm[i % CFG4_DISTINCT]
+            v = pin[o:o + f.size].reshape(f.shape)
+            v[:] = f
+            fr.append(v)
+            o += f.size
+        per_distinct = [api.count_windows(f.shape[1], f.shape[0], 1.25, 24, -1) for f in poolm]
+        job_windows = sum(per_distinct[i % CFG4_DISTINCT] for i in range(CFG4_FRAMES))
+        gsync = shard.RecordGather(5 + 2 * c.L, device="cuda") if dist_on else None
+        last = {}
+
+        def step4(i):
+            res = c.detect_many(fr, **CFG4_ARGS) if fr else []
+            st = dict(c.last_stats) if fr else {k: 0 for k in ("ms_scan", "ms_cascade", "ms_h2d", "ms_d2h", "ms_host", "raw_hits", "stage0_survivors", "detections", "scan_launches", "cascade_launches", "resize_launches")}
+            rec = shard.pack_records(res, frame0=lo, landmark_n=c.L)
+            if dist_on:
+                gsync.start(rec)
+                last["table"] = gsync.finish()
+            else:
+                last["table"] = rec
+            last["n_local"] = len(rec)
+            return st
+
+        ms, acc, clocks = timed(step4, a.steps, a.warmup, sample_clocks=True)
+        value = a.steps * job_windows / (ms * 1e-3)
+        check = table_check(last["table"], last["n_local"])
+        h2d = sum(sizes)
+        if dist_on:
+            t = torch.tensor([h2d], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            h2d = int(t.item())
+        out = {"metric": METRIC_BY_WORKLOAD["cfg4"], "value": value, "unit": "windows/s", "n_gpus": world, "steps": a.steps,
+               "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+               "config": {"workload": "fddb_2845_mixed_sizes", "frames": CFG4_FRAMES, "distinct_frames": CFG4_DISTINCT,
+                          "windows_per_step": job_windows, **CFG4_ARGS, "l2": "inputs larger than L2 (425 MB of frames per step)",
+                          "parallelism": "contiguous frame blocks over %d rank(s), jdaB200DetectMixed per rank, one NCCL "
+                                         "all-gather of detection records per step (inside the timed region)" % world,
+                          "note": "host frames (pinned) in: every step copies its frames host->device, so value IS the "
+                                  "end-to-end figure; e2e repeats it"},
+               "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": int(check["records"]) * (6 + 2 * c.L) * 4},
+               "gpu_launches": acc["launches"], "clocks": clocks,
+               "kernel_ms_per_step_rank0": {"k2_scan": acc["ms_scan"] / a.steps, "k3_cascade": acc["ms_cascade"] / a.steps,
+                                            "h2d": acc["ms_h2d"] / a.steps, "host_nms": acc["ms_host"] / a.steps},
+               "gather_check": check}
+
+        def cpu4():
+            cores = os.cpu_count() or 1
+            n = max(8, min(2 * cores, 256))
+            sample = [poolm[i % CFG4_DISTINCT] for i in range(n)]
+            dt, kind = cpu_frames_run(sample, cores, CFG4_ARGS)
+            wins = sum(per_distinct[i % CFG4_DISTINCT] for i in range(n))
+            return {"value": wins / dt, "unit": "windows/s", "cores": cores, "kind": kind,
+                    "sample": "%d of the 2845 frames, %d threads over jdaDetect (%.1f s)" % (n, cores, dt)}
+        return finish_line(out, job_windows, cpu4)
+
+    # ------------------------------------------------------------------ config 5: mining scan over 100k backgrounds
+    if a.workload == "cfg5":
+        pool5 = cfg5_pool()
+        lo, hi = shard.shard_range(CFG5_FRAMES, rank, world)
+        # two resident batches of B frames alternate (each larger than L2); frame g of the job is pool5[g % 40]
+        host5 = [torch.from_numpy(tile_batch(pool5, B, s)).pin_memory() for s in (0, 17)]
+        dev5 = [h.cuda(non_blocking=False) for h in host5]
+        torch.cuda.synchronize()
+        mine_kw = dict(scale=1.25, min_size=24, max_size=192, th=0.0, t_limit=a.mine_t, k_limit=a.mine_k,
+                       flags=api.RAW_HITS | api.NO_FINAL_TH)
+        keys = ("ms_scan", "ms_cascade", "ms_h2d", "ms_d2h", "ms_host", "raw_hits", "stage0_survivors", "detections",
+                "scan_launches", "cascade_launches", "resize_launches")
+        last = {"table": None, "n_local": 0}
+
+        def run5(n_frames, from_host):
+            tot = {k: 0 for k in keys}
+            f = 0
+            bi = 0
+            while f < n_frames:
+                nb = min(B, n_frames - f)
+                if from_host:
+                    res = c.detect_batch(host5[bi & 1].numpy()[:nb], flat=True, **mine_kw)
+                else:
+                    res = c.detect_batch(None, device_ptr=dev5[bi & 1].data_ptr(), shape=(nb, H, W), flat=True, **mine_kw)
+                for k in keys:
+                    tot[k] += c.last_stats[k]
+                if dist_on:
+                    if exchange["fut"] is not None:
+                        last["table"] = exchange["fut"].result()
+                    last["n_local"] = len(res[2])
+                    exchange["fut"] = exchange["pool"].submit(_exchange5, res, lo + f)
+                else:
+                    last["table"] = shard.pack_records_flat(*res, frame0=lo + f)
+                    last["n_local"] = len(res[2])
+                f += nb
+                bi += 1
+            return tot
+
+        def _exchange5(res, frame0):
+            table = gather.finish()
+            gather.start(shard.pack_records_flat(*res, frame0=frame0))
+            return table
+
+        def exchange_wait5():
+            if exchange["fut"] is not None:
+                exchange["fut"].result()
+                exchange["fut"] = None
+            if gather is not None:
+                t = gather.finish()
+                if t is not None:
+                    last["table"] = t
+        exchange_wait_vga = exchange_wait
+
+        def step5(i):
+            st = run5(hi - lo, False)
+            exchange_wait5()
+            return st
+
+        def warm5(i):
+            st = run5(min(2 * B, hi - lo), False)
+            exchange_wait5()
+            return st
+
+        ms, acc, clocks = timed(step5, a.steps, a.warmup, sample_clocks=True, warm_fn=warm5)
+        value = a.steps * CFG5_FRAMES * WINDOWS_PER_FRAME / (ms * 1e-3)
+        check = table_check(last["table"], last["n_local"])     # the table of the job's LAST batch on every rank
+        # e2e: the same loop from pinned host batches over a bounded slice of the share (1/8, at least 4 batches)
+        n_e = min(hi - lo, max(4 * B, (hi - lo) // 8))
+
+        def step5e(i):
+            st = run5(n_e, True)
+            exchange_wait5()
+            return st
+        ms_e, acc_e, _ = timed(step5e, 1, 1, warm_fn=lambda i: (run5(min(B, hi - lo), True), exchange_wait5())[0])
+        ne_all = n_e
+        if dist_on:
+            t = torch.tensor([n_e], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            ne_all = int(t.item())
+        e2e_value = ne_all * WINDOWS_PER_FRAME / (ms_e * 1e-3)
+        out = {"metric": METRIC_BY_WORKLOAD["cfg5"], "value": value, "unit": "windows/s", "n_gpus": world, "steps": a.steps,
+               "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+               "config": {"workload": "mining_100k_backgrounds", "frames": CFG5_FRAMES, "distinct_frames": CFG5_DISTINCT,
+                          "sigmas": [0, 1, 2, 4, 6], "frame": [W, H], "windows_per_frame": WINDOWS_PER_FRAME,
+                          "batch": B, "full_stages": a.mine_t, "carts_of_unfinished_stage": a.mine_k,
+                          "l2": "inputs larger than L2 (157 MB batches, two alternate)",
+                          "warmup_step": "two batches per rank (a timed step is the rank's whole share)",
+                          "parallelism": "contiguous frame blocks over %d rank(s); per batch one NCCL all-gather of the "
+                                         "survivor records (frame, x, y, size, score, 54 shape floats), launched under "
+                                         "the next batch's scan" % world},
+               "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": ne_all * W * H,
+                       "d2h_bytes_per_step": int(acc_e["raw_hits"]) * (6 + 2 * c.L) * 4 * world,
+                       "frames": ne_all, "note": "pinned host batches in, over 1/8 of the job"},
+               "gpu_launches": acc["launches"], "clocks": clocks,
+               "kernel_ms_per_step_rank0": {"k2_scan": acc["ms_scan"] / a.steps, "k3_cascade": acc["ms_cascade"] / a.steps,
+                                            "d2h": acc["ms_d2h"] / a.steps, "host": acc["ms_host"] / a.steps},
+               "survivors_per_step_rank0": acc["raw_hits"] / a.steps, "gather_check_last_batch": check}
+
+        def cpu5():
+            cores = os.cpu_count() or 1
+            n = max(8, min(2 * cores, 256))
+            sample = [pool5[i % CFG5_DISTINCT] for i in range(n)]
+            dt, kind = cpu_frames_run(sample, cores, ARGS)
+            return {"value": n * WINDOWS_PER_FRAME / dt, "unit": "windows/s", "cores": cores, "kind": kind,
+                    "sample": "%d of the backgrounds through full jdaDetect (the C API has no truncated cascade), "
+                              "%d threads (%.1f s)" % (n, cores, dt)}
+        return finish_line(out, 0, cpu5)
+
     ms, acc, clocks = timed(step_resident, a.steps, a.warmup, sample_clocks=True)
     total_windows = a.steps * B * WINDOWS_PER_FRAME * world
     value = total_windows / (ms * 1e-3)
@@ -286,6 +567,16 @@ def main():
     e2e_steps = max(3, a.steps // 2)
     ms_e, acc_e, _ = timed(step_e2e, e2e_steps, 2)
     e2e_value = e2e_steps * B * WINDOWS_PER_FRAME * world / (ms_e * 1e-3)
+    # the same call from plain pageable memory (what a caller that never heard of cudaHostAlloc passes)
+    pageable = [np.array(h.numpy(), copy=True) for h in host]
+
+    def step_e2e_pageable(i):
+        res = c.detect_batch(pageable[i & 1], flat=True, **ARGS)
+        gather_records(res)
+        return c.last_stats
+    ms_p, _, _ = timed(step_e2e_pageable, 3, 1)
+    e2e_pageable = 3 * B * WINDOWS_PER_FRAME * world / (ms_p * 1e-3)
+    del pageable
     rec_bytes = (6 + 2 * c.L) * 4
     d2h = int(acc_e["raw_hits"] / e2e_steps) * rec_bytes + 22 * 4
 
@@ -298,7 +589,8 @@ def main():
                       "model": "shipped T=5 K=540 L=27 (tests/golden/jda_shipped_f32.model)",
                       "parallelism": "frames sharded, %d rank(s), NCCL all-gather of detections" % world},
            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": B * W * H * world,
-                   "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps},
+                   "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
+                   "host_memory": "pinned", "pageable_host_memory_value": e2e_pageable},
            "gpu_launches": acc["launches"], "clocks": clocks,
            "kernel_ms_per_step": {"k2_scan": acc["ms_scan"] / a.steps, "k3_cascade": acc["ms_cascade"] / a.steps,
                                   "d2h": acc["ms_d2h"] / a.steps, "host_nms": acc["ms_host"] / a.steps},
@@ -317,32 +609,47 @@ def main():
         bytes_pw = 118.0 * carts_pw + 216.0      # per window inside k2 (stage 0); survivors' stages are k3's
         k2_s = acc["ms_scan"] / a.steps * 1e-3
         achieved = B * WINDOWS_PER_FRAME * bytes_pw / k2_s / 1e9
+        # counters of the dominant kernel come from the committed ncu capture (profiles/k2_capture.json, written by
+        # tools/ncu_digest.py on the GPU box) and are tied to the tree by the hash of csrc/: a capture taken on other
+        # kernel sources is reported as stale instead of being quoted as if it were this tree's
+        from jda_b200 import buildinfo
+        cap, sha = None, buildinfo.source_sha()
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "k2_capture.json")))
+        except Exception:
+            pass
+        fresh = bool(cap) and cap.get("source_sha") == sha
+        if cap and not fresh:
+            print("bench.py: profiles/k2_capture.json was taken on csrc %s, this tree is %s -- re-run tools/gpu_round.sh"
+                  % (cap.get("source_sha"), sha), file=sys.stderr)
+        traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["frames"] * B if cap else None
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak,
-                           # dram__bytes_read+write of k2_scan from the committed ncu capture
-                           # (profiles/r1s_metrics_k2_k3.txt: 84.4 MB read + 24.5 MB written for a 256-frame
-                           # launch: the frames, the tables, the survivors' leaf records; 110 + 28 MB in the r1p
-                           # capture -- how much of the batch is still in L2 varies), scaled to B frames
-                           "traffic": (84.4e6 + 24.5e6) / 256 * B, "kernel": "k2_scan",
+                           "traffic": traffic, "kernel": "k2_scan",
+                           # physical DRAM bytes per launch (ncu) over this run's launch time, against the same peak
+                           "dram_frac": (traffic / k2_s / 1e9 / peak) if traffic else None,
+                           "capture": {"source_sha": cap.get("source_sha") if cap else None, "tree_sha": sha,
+                                       "matches_tree": fresh, "frames": cap.get("frames") if cap else None,
+                                       "file": "profiles/k2_capture.json"},
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                           "note": "logical (algorithmic touched) bytes: 118 B x carts/window + 216 B; data is "
-                                   "served from shared memory/L2 so frac may exceed 1; compulsory DRAM is "
-                                   "~1.8 B/window (see DESIGN.md)",
+                           "note": "frac: logical (algorithmic touched) bytes, 118 B x carts/window + 216 B, served from "
+                                   "shared memory -- may exceed 1; dram_frac: the bytes that really cross HBM "
+                                   "(frames + tables + survivor records, ~2 B/window); see DESIGN.md",
                            "carts_per_window": carts_pw, "algorithmic_bytes_per_window": bytes_pw,
                            "k2_windows_per_s": B * WINDOWS_PER_FRAME / k2_s}
         # The unit that actually binds k2_scan is the shared-memory data pipe: 1 wavefront / clk / SM (measured:
-        # tools/probes/lds_probe.cu -> profiles/r1g_lds_probe.txt).  Wavefronts per window come from the committed ncu
-        # capture of this workload (profiles/r1s_metrics_k2_k3.txt: 2.412e9 shared wavefronts for 256 frames, of
-        # which 0.951e9 are bank-conflict replays); the rate is this run's.
-        wf_per_window = 2.411590994e9 / (256 * WINDOWS_PER_FRAME)
-        sm_hz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
-        wf_rate = wf_per_window * B * WINDOWS_PER_FRAME / k2_s
-        out["roofline_onchip"] = {"bound": "shared-memory data pipe (LSU wavefronts)", "kernel": "k2_scan",
-                                  "achieved": wf_rate / 1e12, "peak": 148 * sm_hz / 1e12, "unit": "Twavefronts/s",
-                                  "frac": wf_rate / (148 * sm_hz),
-                                  "wavefronts_per_window": wf_per_window, "bank_conflict_share": 0.950957148 / 2.411590994,
-                                  "peak_source": "1 wavefront/clk/SM measured by tools/probes/lds_probe.cu x 148 SMs x SM clock",
-                                  "note": "wavefronts/window from the committed ncu capture of the same workload, rate from this run"}
+        # tools/probes/lds_probe.cu -> profiles/r1g_lds_probe.txt).  Wavefronts per window from the capture above,
+        # the rate from this run.
+        if cap:
+            wf_per_window = cap["smem_wavefronts"] / (cap["frames"] * WINDOWS_PER_FRAME)
+            sm_hz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+            wf_rate = wf_per_window * B * WINDOWS_PER_FRAME / k2_s
+            out["roofline_onchip"] = {"bound": "shared-memory data pipe (LSU wavefronts)", "kernel": "k2_scan",
+                                      "achieved": wf_rate / 1e12, "peak": 148 * sm_hz / 1e12, "unit": "Twavefronts/s",
+                                      "frac": wf_rate / (148 * sm_hz), "wavefronts_per_window": wf_per_window,
+                                      "bank_conflict_share": cap["smem_bank_conflicts"] / cap["smem_wavefronts"],
+                                      "capture_matches_tree": fresh,
+                                      "peak_source": "1 wavefront/clk/SM measured by tools/probes/lds_probe.cu x 148 SMs x SM clock"}
         if not a.no_cpu_baseline and world == 1:  # the reported CPU baseline is an N=1 item
             cores = os.cpu_count() or 1
             n = max(8, min(2 * cores, 256))

@@ -95,6 +95,10 @@ class RecordGather:
         self.pending = None
         self.exchanges = 0
         self._host = {}
+        self._back = {}
+        # CUDA: the exchange lives on its own stream (upload -> all-gather -> read-back into pinned memory -> event),
+        # so neither start() nor finish() issues a blocking copy: finish() waits on the event only
+        self._side = torch.cuda.Stream(self.dev) if self.dev.type == "cuda" else None
 
     def _launch(self, rec, cap, async_op):
         torch = self.torch
@@ -108,11 +112,24 @@ class RecordGather:
         host[0, 0] = float(rec.shape[0])     # exact up to 2^24 records per rank
         if n:
             host[1:n + 1] = torch.from_numpy(np.ascontiguousarray(rec[:n], np.float32))
-        send = host.to(self.dev, non_blocking=True)
-        recv = torch.empty((self.world * (cap + 1), self.width), dtype=torch.float32, device=self.dev)
-        work = self.dist.all_gather_into_tensor(recv, send, group=self.group, async_op=async_op)
         self.exchanges += 1
-        return dict(rec=rec, cap=cap, host=host, send=send, recv=recv, work=work)
+        if self._side is None:               # CPU tensors (gloo)
+            recv = torch.empty((self.world * (cap + 1), self.width), dtype=torch.float32)
+            work = self.dist.all_gather_into_tensor(recv, host.clone(), group=self.group, async_op=async_op)
+            return dict(rec=rec, cap=cap, recv=recv, work=work, event=None, back=None)
+        back = self._back.get(cap)
+        if back is None:
+            back = torch.empty((self.world * (cap + 1), self.width), dtype=torch.float32).pin_memory()
+            self._back[cap] = back
+        with torch.cuda.stream(self._side):
+            send = host.to(self.dev, non_blocking=True)
+            recv = torch.empty((self.world * (cap + 1), self.width), dtype=torch.float32, device=self.dev)
+            work = self.dist.all_gather_into_tensor(recv, send, group=self.group, async_op=True)
+            work.wait()                      # stream-level: the side stream waits for NCCL, the host does not
+            back.copy_(recv, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(self._side)
+        return dict(rec=rec, cap=cap, recv=recv, send=send, work=None, event=event, back=back)
 
     def start(self, rec):
         assert self.pending is None, "finish() the previous exchange first"
@@ -125,7 +142,11 @@ class RecordGather:
         while True:
             if p["work"] is not None:
                 p["work"].wait()
-            allr = p["recv"].cpu().numpy().reshape(self.world, p["cap"] + 1, self.width)
+            if p["event"] is not None:
+                p["event"].synchronize()
+                allr = p["back"].numpy().reshape(self.world, p["cap"] + 1, self.width).copy()
+            else:
+                allr = p["recv"].numpy().reshape(self.world, p["cap"] + 1, self.width)
             counts = allr[:, 0, 0].astype(np.int64)
             if counts.max() <= p["cap"]:
                 self.cap = max(self.cap, 1 << int(np.ceil(np.log2(max(int(counts.max()) * 2, 1)))))

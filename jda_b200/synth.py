@@ -81,6 +81,14 @@ def facemix_frame(seed, w=640, h=480):
     return f
 
 
+MINING_SIGMAS = (0.0, 1.0, 2.0, 4.0, 6.0)
+
+
+def mining_background(seed, w=640, h=480):
+    """a face-free background, noise blurred with sigma in {0, 1, 2, 4, 6} by seed mod 5."""
+    return blur_frame(seed, w, h, sigma=MINING_SIGMAS[seed % 5])
+
+
 DISTRIBUTIONS = {"noise": noise_frame, "blur6": blur_frame, "facemix": facemix_frame}
 
 

@@ -26,7 +26,8 @@ grep -c k2_scan $O/${tag}_launches.csv
 # full capture: one launch of each kernel at 256 resident frames
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2_scan|k3_' -s 6 -c 3 -f -o /tmp/${tag}_full \
   python bench.py --batch 256 --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $O/${tag}_ncu_full.log 2>&1
-python tools/ncu_digest.py /tmp/${tag}_full.ncu-rep $O/${tag}_full >> $O/${tag}_ncu_full.log 2>&1
+python tools/ncu_digest.py /tmp/${tag}_full.ncu-rep $O/${tag}_full 256 >> $O/${tag}_ncu_full.log 2>&1
+cp $O/${tag}_full_k2_capture.json $O/k2_capture.json 2>/dev/null   # -> profiles/k2_capture.json (bench.py reads it)
 ls -la /tmp/${tag}_full.ncu-rep >> $O/${tag}_ncu_full.log 2>&1
 fi
 if [ "${AB:-0}" = "1" ]; then

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Digest an .ncu-rep into two small text files (key counters per kernel; per-source-line hot spots)
-so that only kilobytes travel back from the GPU box.   usage: ncu_digest.py rep.ncu-rep out_prefix"""
-import csv, subprocess, sys, io
+so that only kilobytes travel back from the GPU box.   usage: ncu_digest.py rep.ncu-rep out_prefix [frames]
+Also writes <out_prefix>_k2_capture.json: the k2_scan counters bench.py's roofline block quotes (DRAM bytes, shared
+wavefronts, bank-conflict replays, duration) tagged with the hash of csrc/ they were measured on; copy it to
+profiles/k2_capture.json so that bench.py can tell whether the capture belongs to the tree it runs."""
+import csv, json, os, subprocess, sys, io
 
 KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__registers_per_thread',
         'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'smsp__inst_executed.sum',
@@ -31,6 +34,29 @@ def main():
             for i, h in enumerate(hdr):
                 if h in KEEP or (h.startswith(STALLS) and h.endswith('_per_issue_active.ratio')):
                     f.write('%-92s %s %s\n' % (h, r[i], units[i]))
+    # machine-readable capture of the dominant kernel for bench.py
+    def num(r, name):
+        v = r[hdr.index(name)].replace(',', '')
+        u = units[hdr.index(name)]
+        mult = {'Mbyte': 1e6, 'Kbyte': 1e3, 'Gbyte': 1e9, 'byte': 1.0, 'ms': 1e-3, 'us': 1e-6, 'ns': 1e-9, 's': 1.0,
+                'msecond': 1e-3, 'usecond': 1e-6, 'nsecond': 1e-9, 'second': 1.0}.get(u, 1.0)
+        return float(v) * mult
+    k2 = [r for r in rows[2:] if 'k2_scan' in r[kn]]
+    if k2:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from jda_b200 import buildinfo
+        r = k2[0]
+        cap = {'kernel': r[kn], 'source_sha': buildinfo.source_sha(), 'frames': int(sys.argv[3]) if len(sys.argv) > 3 else 256,
+               'time_s': num(r, 'gpu__time_duration.sum'),
+               'dram_bytes_read': num(r, 'dram__bytes_read.sum'), 'dram_bytes_write': num(r, 'dram__bytes_write.sum'),
+               'smem_wavefronts': num(r, 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'),
+               'smem_bank_conflicts': num(r, 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum'),
+               'warp_instructions': num(r, 'smsp__inst_executed.sum'),
+               'lsu_data_pipe_pct': num(r, 'l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed'),
+               'issue_active_pct': num(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'),
+               'how': 'ncu --set full --clock-control none, one k2_scan launch of `bench.py --batch <frames>` (tools/gpu_round.sh)'}
+        with open(out + '_k2_capture.json', 'w') as f:
+            json.dump(cap, f, indent=1)
     rows = list(csv.reader(io.StringIO(run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass']))))
     secs, cur = [], None
     for r in rows:
