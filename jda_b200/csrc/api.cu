@@ -115,6 +115,8 @@ struct Tuning {
   bool tiny_queues = false;       // JDA_B200_TINY_QUEUES (test hook: start with queues that overflow)
   double level_weight_exp = 1.0;  // JDA_B200_LEVEL_WEIGHT_EXP (r1q: scan -1.7 % against flat weights)
   std::string sched;              // JDA_B200_SCHED="4,8,16,...": phase ends of k2_scan
+  int force_plan = 0;             // JDA_B200_FORCE_PLAN=latency|throughput (test hook: the per-window trace is a one-frame
+                                  // call and would otherwise only ever see the latency tile plan)
 };
 
 Tuning read_tuning() {
@@ -137,6 +139,7 @@ Tuning read_tuning() {
   if (const char *e = getenv("JDA_B200_TINY_QUEUES")) t.tiny_queues = atoi(e) != 0;
   if (const char *e = getenv("JDA_B200_LEVEL_WEIGHT_EXP")) t.level_weight_exp = atof(e);
   if (const char *e = getenv("JDA_B200_SCHED")) t.sched = e;
+  if (const char *e = getenv("JDA_B200_FORCE_PLAN")) t.force_plan = e[0] == 'l' ? 1 : e[0] == 't' ? 2 : 0;
   return t;
 }
 
@@ -972,6 +975,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   memset(&R, 0, sizeof R);
   R.c = c; R.b = &b; R.mixed = mixed; R.trace = trace; R.timing = timing; R.tracing = trace != nullptr;
   R.latency_plan = b.n_frames <= kLatencyFrames;
+  if (c->tune.force_plan) R.latency_plan = c->tune.force_plan == 1;
   if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, R.latency_plan)) return false;
   const Geometry &g = c->geo;
   R.geo = &c->geo; R.tables = c->d_tables.p; R.norms = c->d_norms;
@@ -1182,6 +1186,7 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
   memset(&R, 0, sizeof R);
   R.c = c; R.b = &b; R.timing = timing;
   R.latency_plan = n_frames <= kLatencyFrames;
+  if (c->tune.force_plan) R.latency_plan = c->tune.force_plan == 1;
   if (!ensure_geometry64(c, width, height, prm.minimum_size, prm.step, prm.scale, R.latency_plan)) return false;
   const Geometry &g = c->geo64;
   R.geo = &g; R.tables = c->d_tables64.p; R.norms = c->d_norms64;

@@ -78,10 +78,20 @@ def wavefronts(addr):
     return cnt.max(axis=1)
 
 
-def simulate(img, deaths, win, step, tw, th_rows, pitch, xy, n1, n2, nx, ny, nw=4, order="row", max_tiles=None, rng=None):
-    """returns dict depth -> [sum wavefronts, loads] and per-phase totals"""
-    o1 = xy[..., 1] * pitch + xy[..., 0]     # tile-format offsets with this pitch
-    o2 = xy[..., 3] * pitch + xy[..., 2]
+def simulate(img, deaths, win, step, tw, th_rows, pitch, xy, n1, n2, nx, ny, nw=4, order="row", max_tiles=None, rng=None,
+             planes=False):
+    """returns dict depth -> [sum wavefronts, loads] and per-phase totals.
+    planes=True: the de-interleaved tile layout (round 2): pixel (x, y) of the tile lives in plane (y % step, x % step) at
+    (y // step, x // step), so a window's base is wy * bx + wx and neighbouring windows are ONE byte apart; `pitch` is bx."""
+    if planes:
+        halo = (win - 1) // step
+        by = th_rows + halo
+        psz = pitch * by
+        o1 = ((xy[..., 1] % step) * step + xy[..., 0] % step) * psz + (xy[..., 1] // step) * pitch + xy[..., 0] // step
+        o2 = ((xy[..., 3] % step) * step + xy[..., 2] % step) * psz + (xy[..., 3] // step) * pitch + xy[..., 2] // step
+    else:
+        o1 = xy[..., 1] * pitch + xy[..., 0]     # tile-format offsets with this pitch
+        o2 = xy[..., 3] * pitch + xy[..., 2]
     tot = np.zeros((3, 2))
     per_phase = np.zeros((len(SCHED), 2))
     d2 = np.minimum(deaths, K).reshape(ny, nx)
@@ -93,11 +103,15 @@ def simulate(img, deaths, win, step, tw, th_rows, pitch, xy, n1, n2, nx, ny, nw=
         wy, wx = np.mgrid[0:hh, 0:tw]
         valid = (wx < ww).reshape(-1)
         gidx = ((y0 + wy) * nx + np.minimum(x0 + wx, nx - 1)).reshape(-1)   # index into the level arrays
-        tbase = (wy * step * pitch + wx * step).reshape(-1)
+        tbase = (wy * pitch + wx).reshape(-1) if planes else (wy * step * pitch + wx * step).reshape(-1)
         dd = np.where(valid, d2.reshape(-1)[gidx], 0)
         # lane 'window 0' stand-in for masked / dead lanes: the tile origin
         g0, b0 = gidx[0], 0
         alive = np.nonzero(valid)[0] if False else np.arange(hh * tw)        # phase 0 enumerates densely
+        if order.startswith("block"):   # block-major enumeration: blocks of bw x bh windows, row-major inside a block
+            bw_, bh_ = (int(v) for v in order[5:].split("x"))
+            key = ((wy // bh_) * ((tw + bw_ - 1) // bw_) + wx // bw_) * (bw_ * bh_) + (wy % bh_) * bw_ + wx % bw_
+            alive = np.argsort(key.reshape(-1)[:hh * tw], kind="stable")
         cart = 0
         for ph, cend in enumerate(SCHED):
             n = len(alive)
@@ -105,8 +119,7 @@ def simulate(img, deaths, win, step, tw, th_rows, pitch, xy, n1, n2, nx, ny, nw=
                 break
             if ph > 0 and n <= 15:
                 break                                   # straggler mode from here (not modelled)
-            if order == "row":
-                lst = alive
+            lst = alive
             npk = (n + 31) // 32
             W_ = np.full(npk * 32, -1, np.int64)
             W_[:n] = lst
@@ -168,9 +181,17 @@ def main():
     cands = [(p["tw"], p["th"], p["box_w"])]
     for a in sys.argv[3:]:
         cands.append(tuple(int(v) for v in a.split(",")))
-    for tw, thr, pitch in cands:
-        tot, per = simulate(img, deaths, win, step, tw, thr, pitch, xy, n1, n2, nx, ny, max_tiles=40)
-        s = "tw %2d th %2d pitch %3d: " % (tw, thr, pitch)
+    halo = (win - 1) // step
+    for tw, thr, pitch in cands + [(c[0], c[1], -((c[0] + halo + 15) // 16 * 16)) for c in cands[:1]] + \
+            [(32, 16, -((32 + halo + 15) // 16 * 16)), (16, 32, -((16 + halo + 15) // 16 * 16)), (64, 8, -((64 + halo + 15) // 16 * 16))]:
+        planes = pitch < 0
+        pitch = abs(pitch)
+        if planes and step * step * pitch * (thr + halo) > 8192:
+            print("(planes tw %d th %d bx %d: %d bytes, does not fit 8 KB)" % (tw, thr, pitch, step * step * pitch * (thr + halo)))
+            continue
+        tot, per = simulate(img, deaths, win, step, tw, thr, pitch, xy, n1, n2, nx, ny, max_tiles=40, planes=planes,
+                            order=os.environ.get("SIM_ORDER", "row"))
+        s = "%s tw %2d th %2d pitch %3d: " % ("PLANES" if planes else "raw   ", tw, thr, pitch)
         s += "  ".join("%s %.2f" % (nm, tot[i, 0] / tot[i, 1]) for i, nm in enumerate(("root", "L1", "L2")))
         s += "  all %.3f wavefronts / LDS.U8" % (tot[:, 0].sum() / tot[:, 1].sum())
         print(s)

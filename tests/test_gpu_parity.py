@@ -81,6 +81,29 @@ def test_trace_matches_oracle(casc, oracle, oracle_shipped, frame, flags):
         np.testing.assert_array_equal(lv, olv)
 
 
+@pytest.mark.parametrize("flags", [0, api.NO_TMA], ids=["tma", "plain_loads"])
+@pytest.mark.parametrize("frame", ["noise", "faces", "odd_size", "narrow", "wide"])
+def test_trace_throughput_plan(oracle, oracle_shipped, frame, flags):
+    """The batch (throughput) tile plan on one frame: pooled tiles, 512-window lists, global-memory levels -- every
+    window's reject cart, exit score and leaves.  JDA_B200_FORCE_PLAN is a test hook: a one-frame call (the trace entry
+    point) would otherwise only ever take the latency plan."""
+    os.environ["JDA_B200_FORCE_PLAN"] = "throughput"
+    try:
+        c = api.Cascador(SHIPPED_F32, double=False)
+    finally:
+        del os.environ["JDA_B200_FORCE_PLAN"]
+    img = TRACE_FRAMES[frame]()
+    nwin = api.count_windows(img.shape[1], img.shape[0])
+    for rng in [(max(nwin - 9000, 0), nwin), (nwin // 2, nwin // 2 + 2000), (0, 2000)]:
+        tn, ts, lv = c.trace(img, flags=flags, leaf_range=rng)
+        on, os_, olv = oracle.trace(oracle_shipped, img, leaf_range=rng)
+        np.testing.assert_array_equal(tn, on)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+        np.testing.assert_array_equal(lv, olv)
+    _same(c.detect(img, th=-1.0), oracle.detect(oracle_shipped, img, th=-1.0))
+    c.close()
+
+
 def test_trace_generic_kernel_only(casc, oracle, oracle_shipped):
     """stage-0 scan switched off: every window through k3_cascade."""
     img = synth.face_canvas()[:240, :320].copy()
