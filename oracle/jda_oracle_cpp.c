@@ -4,15 +4,18 @@
  *
  * TEST INFRASTRUCTURE ONLY.  Nothing under jda_b200/ may include, link or execute this file.
  *
- * PARITY UNPINNED.  The C++ detector cannot be compiled in this image: it needs OpenCV C++
- * headers (libjda.cmake:3, find_package(OpenCV REQUIRED)) and its Config singleton parses
- * ../config.json with 3rdparty/jsmnpp, so there is no reference binary to run this file
- * against and the reference ships no golden vectors.  What is restated
- * touches no OpenCV arithmetic: with every node at scale == 0 and
- * face.similarity_transform = false (both true for the shipped model and config) method 1
- * only indexes cv::Mat pixels and does double arithmetic.  Models with scale != 0 nodes would
- * sample cv::resize'd planes (cascador.cpp:330-331), whose bit-level behaviour differs between
- * OpenCV versions: this file refuses them.
+ * PINNED (round 2).  The reference's own src/jda/cascador.cpp and cart.cpp (whole files) plus the
+ * detect-path functions of data.cpp / btcart.cpp / common.cpp are compiled from where they lie
+ * against oracle/cvshim/ (a small stand-in for the OpenCV core headers: the image has no OpenCV C++)
+ * into oracle/_ref_cpp/libjda_ref_cpp.so (oracle/Makefile: ref_cpp), and tests/test_oracle_cpp.py
+ * compares this file with that binary bit for bit: JoinCascador::Detect (faces, scores, landmarks,
+ * patch / cart statistics, with and without NMS), Validate on every window (carts evaluated, exit
+ * score), the shipped model, full-precision synthetic models and training snapshots.
+ * Scope of the pin = scope of this file: fddb.method = 1, every node at scale == 0,
+ * face.similarity_transform = false (both true for the shipped model and config), shift_size = 0
+ * (src/test.cpp:17,75).  Models with scale != 0 nodes sample cv::resize'd planes
+ * (cascador.cpp:330-331) -- OpenCV's arithmetic, third party, not under /root/reference: this file
+ * refuses them, and the stand-in's resize is not OpenCV's.
  *
  * What it restates (reference file:line, /root/reference):
  *   model layout (double flavour)          src/jda/cascador.cpp:126-164, src/jda/cart.cpp:406-428

@@ -6,6 +6,10 @@ arm may import this module (see oracle/jda_oracle.c header).
   Oracle  -- our restatement, oracle/libjda_oracle.so (instrumented)
   RefLib  -- the reference's own c/jda.c, oracle/_ref/libjda_ref.so, reached
              through the reference's C API (c/jda.h:18-68) and nothing else
+  OracleCpp -- our restatement of the double-precision C++ detector, oracle/libjda_oracle_cpp.so
+  RefCpp  -- the reference's own C++ detector (src/jda/cascador.cpp, cart.cpp + the detect-path functions of
+             data.cpp / btcart.cpp / common.cpp) built against oracle/cvshim/ into oracle/_ref_cpp/, reached
+             through oracle/ref_cpp_driver.cpp
 """
 import ctypes as C
 import os
@@ -215,12 +219,83 @@ class Oracle:
         return tn[:nwin], ts[:nwin], lv
 
 
+REF_CPP_SO = os.path.join(HERE, "_ref_cpp", "libjda_ref_cpp.so")
+REF_CPP_RUN = os.path.join(HERE, "_ref_cpp", "run")      # its parent holds config.json (Config reads "../config.json")
+
+
+class RefCpp:
+    """The reference's own JoinCascador (double precision, fddb.method = 1) behind oracle/ref_cpp_driver.cpp.
+    Models must be double-flavour files (JoinCascador::SerializeFrom reads doubles)."""
+
+    def __init__(self, path=REF_CPP_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        os.makedirs(REF_CPP_RUN, exist_ok=True)
+        L = self.lib = C.CDLL(path)
+        L.jref_open.restype = C.c_void_p
+        L.jref_open.argtypes = [C.c_char_p, C.c_char_p]
+        L.jref_close.argtypes = [C.c_void_p]
+        L.jref_close.restype = None
+        L.jref_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.jref_dims.restype = None
+        L.jref_detect.restype = C.c_int
+        L.jref_detect.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                  C.c_double, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_int)),
+                                  C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double)),
+                                  C.POINTER(C.c_double)]
+        L.jref_release.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.jref_release.restype = None
+        L.jref_trace.restype = C.c_longlong
+        L.jref_trace.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_longlong]
+
+    def load(self, path):
+        return self.lib.jref_open(os.fsencode(path), os.fsencode(REF_CPP_RUN))
+
+    def release(self, h):
+        self.lib.jref_close(h)
+
+    def dims(self, h):
+        d = (C.c_int * 6)()
+        self.lib.jref_dims(h, d)
+        return dict(zip(("T", "K", "L", "depth", "stage", "cart"), d))
+
+    def detect(self, h, img, minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True):
+        """JoinCascador::Detect: (rects[n,4], scores[n] f64, shapes[n,2L] f64, stats dict)"""
+        a, p, w, hh = _img(img)
+        r, s, sh = C.POINTER(C.c_int)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+        st = (C.c_double * 4)()
+        n = self.lib.jref_detect(h, p, w, hh, minimum_size, step, scale, overlap, 1 if nms else 0, 0,
+                                 C.byref(r), C.byref(s), C.byref(sh), st)
+        D = 2 * self.dims(h)["L"]
+        if n > 0:
+            out = (np.ctypeslib.as_array(r, shape=(n, 4)).copy(), np.ctypeslib.as_array(s, shape=(n,)).copy(),
+                   np.ctypeslib.as_array(sh, shape=(n, D)).copy())
+        else:
+            out = (np.zeros((0, 4), np.int32), np.zeros((0,), np.float64), np.zeros((0, D), np.float64))
+        self.lib.jref_release(r, s, sh)
+        stats = {"patch_n": int(st[0]), "face_patch_n": int(st[1]), "nonface_patch_n": int(st[2]),
+                 "cart_gothrough_n": int(st[3])}
+        return out + (stats,)
+
+    def trace(self, h, img, minimum_size=20, step=5, scale=1.2):
+        """Validate on every window in detectMultiScale1's order: (carts evaluated, exit score)"""
+        a, p, w, hh = _img(img)
+        n = self.lib.jref_trace(h, p, w, hh, minimum_size, step, scale, 0, None, None, 0)
+        tn = np.zeros(max(n, 1), np.int32)
+        ts = np.zeros(max(n, 1), np.float64)
+        m = self.lib.jref_trace(h, p, w, hh, minimum_size, step, scale, 0, tn.ctypes.data_as(C.POINTER(C.c_int)),
+                                ts.ctypes.data_as(C.POINTER(C.c_double)), n)
+        assert m == n
+        return tn[:n], ts[:n]
+
+
 ORACLE_CPP_SO = os.path.join(HERE, "libjda_oracle_cpp.so")
 
 
 class OracleCpp:
     """Restatement of the reference's double-precision C++ detector (JoinCascador::Detect, fddb.method = 1),
-    oracle/jda_oracle_cpp.c.  PARITY UNPINNED: the C++ detector cannot be built in this image."""
+    oracle/jda_oracle_cpp.c.  Pinned bit for bit against RefCpp (tests/test_oracle_cpp.py)."""
 
     # model/config.json "fddb": minimum_size 20, step 5, scale 1.2, overlap 0.3, nms true
     DEFAULTS = dict(minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True)

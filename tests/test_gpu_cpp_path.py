@@ -2,8 +2,9 @@
 fddb.method = 1) against its CPU restatement oracle/jda_oracle_cpp.c, through the C ABI.
 
 Bar: bit-exact.  Rects are integers; scores and landmarks are the same double operations in the same order, so
-they are compared as raw 64-bit patterns.  The oracle itself is PARITY UNPINNED (see its header): these tests show
-the kernels compute what the restatement computes, not that the restatement is the reference.
+they are compared as raw 64-bit patterns.  The oracle is pinned bit for bit to the reference's own C++ detector built
+into oracle/_ref_cpp/ (tests/test_oracle_cpp.py); test_against_the_reference_cpp_binary compares the CUDA path with
+that binary directly.
 """
 import numpy as np
 import pytest
@@ -54,6 +55,28 @@ def test_known_answer_config_json_settings(casc, ocpp, ocpp_shipped):
     st = casc.last_stats
     assert st["windows"] == 140215 and st["scan_launches"] == 1 and st["raw_hits"] == 365
     assert st["stage0_survivors"] >= 365                      # the prefilter passes a superset of the true survivors
+
+
+def test_against_the_reference_cpp_binary(casc, tmp_path):
+    """the CUDA path vs the reference's own JoinCascador::Detect (src/jda/cascador.cpp compiled into oracle/_ref_cpp),
+    no restatement in between"""
+    import os
+    from oracle import pyoracle
+    if not os.path.exists(pyoracle.REF_CPP_SO):
+        pytest.skip("oracle/_ref_cpp/libjda_ref_cpp.so not built")
+    ref = pyoracle.RefCpp()
+    hr = ref.load(synth.widen_f32_model(SHIPPED_F32, str(tmp_path / "wide.model")))
+    assert hr
+    for img, kw in ((synth.face_canvas(), dict()), (synth.facemix_frame(3, 320, 240), dict(nms=False)),
+                    (synth.facemix_frame(7, *synth.fddb_shape(7)), dict(minimum_size=30, step=7, scale=1.3, overlap=0.5))):
+        want = ref.detect(hr, img, **kw)
+        _same(casc.detect_cpp(img, **kw), want)
+        assert casc.last_stats["windows"] == want[3]["patch_n"] and casc.last_stats["raw_hits"] == want[3]["face_patch_n"]
+    tn, ts = casc.trace_cpp(synth.noise_frame(2, 90, 70))
+    rn, rs = ref.trace(hr, synth.noise_frame(2, 90, 70))
+    np.testing.assert_array_equal(tn, rn)
+    np.testing.assert_array_equal(_bits(ts), _bits(rs))
+    ref.release(hr)
 
 
 @pytest.mark.parametrize("frame", ["faces", "noise", "blur", "facemix", "odd"])

@@ -1,11 +1,15 @@
 """The restatement of the reference's double-precision C++ detector (oracle/jda_oracle_cpp.c: JoinCascador::Detect,
 fddb.method = 1) and the host logic of its CUDA counterpart.  No GPU needed.
 
-PARITY UNPINNED: the C++ detector cannot be built in this image (OpenCV C++ headers, jsmnpp config), the reference
-ships no golden vectors for it.  What is checked here: the restatement against independent restatements of its
-pieces (multimap NMS, window ladder) and of the whole of Validate (a from-scratch Python restatement that parses the
-model file itself: per-window cart counts, exit scores and landmarks agree bit for bit), its known answers as
-regression pins, and the error bound that lets the float32 scan kernel prefilter stage 0 of the double path.
+PINNED (round 2): the reference's own src/jda/cascador.cpp and cart.cpp (whole) + the detect-path functions of
+data.cpp / btcart.cpp / common.cpp are compiled from where they lie against a ~200-line stand-in for the OpenCV core
+headers (oracle/cvshim/, oracle/Makefile target ref_cpp) and the restatement is compared with that binary bit for bit:
+JoinCascador::Detect (faces, scores, landmarks, patch and cart statistics), the raw list without NMS, and Validate on
+every window (carts evaluated, exit score) -- shipped model, full-precision synthetic models, training snapshots whose
+header stops inside a stage.  Also kept: the independent restatements of its pieces (multimap NMS, window ladder, a
+from-scratch Python Validate) and the error bound that lets the float32 scan kernel prefilter stage 0 of the double path.
+Scope of the pin: fddb.method = 1, models without scale != 0 nodes, face.similarity_transform = false, shift_size = 0
+(src/test.cpp:17,75) -- what runs through cv::resize is OpenCV's arithmetic, which the stand-in does not reproduce.
 """
 import numpy as np
 import pytest
@@ -26,6 +30,100 @@ def ocpp_shipped(ocpp):
     assert h
     yield h
     ocpp.release(h)
+
+
+@pytest.fixture(scope="module")
+def refcpp():
+    """the reference's own C++ detector (oracle/_ref_cpp); skip when it was never built"""
+    import os
+    from oracle import pyoracle
+    if not os.path.exists(pyoracle.REF_CPP_SO):
+        pytest.skip("oracle/_ref_cpp/libjda_ref_cpp.so not built (needs /root/reference)")
+    return pyoracle.RefCpp()
+
+
+@pytest.fixture(scope="module")
+def wide_shipped(tmp_path_factory):
+    """the shipped model as a double-flavour file (JoinCascador::SerializeFrom reads doubles; f32 -> f64 is exact)"""
+    return synth.widen_f32_model(SHIPPED_F32, str(tmp_path_factory.mktemp("wide") / "wide.model"))
+
+
+def _same64(a, b):
+    np.testing.assert_array_equal(np.ascontiguousarray(a, np.float64).view(np.uint64),
+                                  np.ascontiguousarray(b, np.float64).view(np.uint64))
+
+
+PIN_FRAMES = {"faces": lambda: synth.face_canvas(), "facemix": lambda: synth.facemix_frame(3, 320, 240),
+              "noise": lambda: synth.noise_frame(5, 160, 120), "fddb_shape": lambda: synth.facemix_frame(7, *synth.fddb_shape(7))}
+
+
+@pytest.mark.parametrize("frame", list(PIN_FRAMES))
+def test_restatement_pinned_to_reference_detect(ocpp, ocpp_shipped, refcpp, wide_shipped, frame):
+    """JoinCascador::Detect of the reference binary vs the restatement: faces, scores and landmarks as raw 64-bit
+    patterns, with and without NMS, for config.json's fddb settings and two others; patch / cart statistics"""
+    hr = refcpp.load(wide_shipped)
+    assert hr and refcpp.dims(hr) == dict(T=5, K=540, L=27, depth=4, stage=5, cart=-1)
+    img = PIN_FRAMES[frame]()
+    for kw in (dict(), dict(minimum_size=30, step=7, scale=1.3, overlap=0.5), dict(minimum_size=24, step=3, scale=1.25, nms=False)):
+        if kw.get("step") == 3 and img.shape[1] > 400:
+            continue                                   # (keeps the CPU suite short)
+        rr, rs, rsh, st = refcpp.detect(hr, img, **kw)
+        orr, os_, osh, carts = ocpp.detect(ocpp_shipped, img, **kw)
+        np.testing.assert_array_equal(rr, orr)
+        _same64(rs, os_)
+        _same64(rsh, osh)
+        # DetectionStatisic (cascador.hpp:14-25): patches, and carts walked by the windows that were rejected
+        raw = ocpp.detect(ocpp_shipped, img, **dict(kw, nms=False))
+        mn, stp, sc = kw.get("minimum_size", 20), kw.get("step", 5), kw.get("scale", 1.2)
+        assert st["patch_n"] == ocpp.count_windows(img.shape[1], img.shape[0], mn, stp, sc)
+        assert st["face_patch_n"] == len(raw[1])
+        assert st["cart_gothrough_n"] == carts - 2700 * len(raw[1])
+    if frame == "faces":
+        assert rr.shape[0] >= 1
+    refcpp.release(hr)
+
+
+def test_restatement_pinned_to_reference_validate_trace(ocpp, ocpp_shipped, refcpp, wide_shipped):
+    """Validate per window (cascador.cpp:166-211) through the reference binary: carts evaluated and exit score"""
+    hr = refcpp.load(wide_shipped)
+    for img in (synth.face_canvas()[20:260, 40:300].copy(), synth.noise_frame(2, 90, 70)):
+        rn, rs = refcpp.trace(hr, img)
+        on, os_ = ocpp.trace(ocpp_shipped, img)
+        np.testing.assert_array_equal(rn, on)
+        _same64(rs, os_)
+        assert len(rn) > 500
+    refcpp.release(hr)
+
+
+def test_restatement_pinned_to_reference_synthetic_models(ocpp, refcpp, tmp_path):
+    """full-precision double models (values that do not survive a float round trip): pass-all, rejecting with many
+    normalised carts, and training snapshots whose header stops inside a stage (cascador.cpp:199-209)"""
+    img = synth.facemix_frame(11, 120, 100)
+    for name, kw, hdr in (("pass", dict(seed=1, mode="passall"), None), ("rej", dict(seed=2, mode="reject", norm_every=7), None),
+                          ("snap", dict(seed=4, mode="reject"), (2, 17)), ("snap0", dict(seed=5, mode="reject"), (0, 300)),
+                          ("small", dict(seed=6, mode="reject", T=3, K=64, L=9, norm_every=5), None)):
+        p = synth.write_model(str(tmp_path / (name + ".model")), **kw)
+        if hdr:
+            b = bytearray(open(p, "rb").read())
+            b[20:24] = hdr[0].to_bytes(4, "little"); b[24:28] = hdr[1].to_bytes(4, "little", signed=True)
+            open(p, "wb").write(bytes(b))
+        hr, ho = refcpp.load(p), ocpp.load(p, True)
+        assert hr and ho
+        if hdr:
+            assert (refcpp.dims(hr)["stage"], refcpp.dims(hr)["cart"]) == hdr
+        rn, rs = refcpp.trace(hr, img)
+        on, os_ = ocpp.trace(ho, img)
+        np.testing.assert_array_equal(rn, on)
+        _same64(rs, os_)
+        for nms in (True, False):
+            rr, rsc, rsh, _ = refcpp.detect(hr, img, nms=nms)
+            orr, osc, osh, _ = ocpp.detect(ho, img, nms=nms)
+            np.testing.assert_array_equal(rr, orr)
+            _same64(rsc, osc)
+            _same64(rsh, osh)
+        if name == "pass":
+            assert len(rsc) == ocpp.count_windows(120, 100)
+        refcpp.release(hr); ocpp.release(ho)
 
 
 def test_header_and_scope(ocpp, ocpp_shipped, tmp_path):
