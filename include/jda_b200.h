@@ -134,6 +134,17 @@ JDA_API int jdaB200DetectBatchFlat(void *cascador, const unsigned char *frames, 
                                    jdaB200FlatResult *result, jdaB200Stats *stats /* may be NULL */);
 JDA_API void jdaB200FlatResultRelease(jdaB200FlatResult *result);
 
+/* The same in two halves, so that two batches can be in flight on one handle (SURVEY.md 8(b) "additive exports"):
+ * jdaB200Submit copies the batch in and launches its kernels without waiting for them and returns a ticket (>= 0);
+ * jdaB200Collect waits for that ticket, runs NMS / relocation and fills `result` exactly as jdaB200DetectBatchFlat
+ * would.  Submit batch i + 1 before collecting batch i: its host -> device copy then runs beside the scan of batch i,
+ * and the host post-processing of batch i beside the scan of batch i + 1.  At most two tickets are outstanding
+ * (a third jdaB200Submit returns -3); tickets are collected in the order they were issued; `frames` (host or device)
+ * must stay valid and unchanged until its ticket is collected; the synchronous entry points refuse to run while a
+ * ticket is outstanding.  Negative return values are failures (jdaB200LastError). */
+JDA_API int jdaB200Submit(void *cascador, const unsigned char *frames, const jdaB200Batch *batch);
+JDA_API int jdaB200Collect(void *cascador, int ticket, jdaB200FlatResult *result, jdaB200Stats *stats /* may be NULL */);
+
 /* Frames of different sizes in one call (reference: test.cpp:73-235 feeds FDDB images of all shapes one by one to
  * the detector; here they share one launch).  Host memory only.  pitch = 0 means pitch == width. */
 typedef struct {

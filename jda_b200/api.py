@@ -103,6 +103,10 @@ def lib():
     L.jdaB200DetectBatch.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(_Result), C.POINTER(Stats)]
     L.jdaB200DetectBatchFlat.restype = ci
     L.jdaB200DetectBatchFlat.argtypes = [vp, vp, C.POINTER(Batch), C.POINTER(FlatResult), C.POINTER(Stats)]
+    L.jdaB200Submit.restype = ci
+    L.jdaB200Submit.argtypes = [vp, vp, C.POINTER(Batch)]
+    L.jdaB200Collect.restype = ci
+    L.jdaB200Collect.argtypes = [vp, ci, C.POINTER(FlatResult), C.POINTER(Stats)]
     L.jdaB200FlatResultRelease.restype = None
     L.jdaB200FlatResultRelease.argtypes = [C.POINTER(FlatResult)]
     L.jdaB200DetectMixed.restype = ci
@@ -160,7 +164,7 @@ EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSeri
            "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan", "jdaB200ResultsRelease",
            "jdaB200DetectMixed", "jdaB200JoinCascadorDetect", "jdaB200ResultF64Release",
            "jdaB200JoinCascadorTrace", "jdaB200JoinCascadorLevels", "jdaB200JoinCascadorFilterMargins",
-           "jdaB200DetectBatchFlat", "jdaB200FlatResultRelease", "jdaB200TraceK", "jdaB200SerializeTo"]
+           "jdaB200DetectBatchFlat", "jdaB200FlatResultRelease", "jdaB200TraceK", "jdaB200SerializeTo", "jdaB200Submit", "jdaB200Collect"]
 
 
 def last_error():
@@ -318,6 +322,52 @@ class Cascador:
         if rc != 0:
             raise RuntimeError("jdaB200DetectBatch failed: " + last_error())
         return self._unpack_results(res, n, unpack)
+
+    def submit(self, frames, scale=1.25, min_size=24, max_size=-1, th=0.0, t_limit=0, flags=0,
+               device_ptr=None, shape=None, pitch=None, frame_stride=None, k_limit=0):
+        """jdaB200Submit: copy the batch in and launch its kernels; returns a ticket for collect().  `frames` (a
+        C-contiguous [n,h,w] u8 array, or device_ptr + shape) must stay alive and unchanged until then."""
+        if device_ptr is None:
+            a = frames
+            assert a.dtype == np.uint8 and a.ndim == 3 and a.flags["C_CONTIGUOUS"]
+            n, h, w = a.shape
+            ptr = a.ctypes.data
+            pitch = w if pitch is None else pitch
+            frame_stride = pitch * h if frame_stride is None else frame_stride
+        else:
+            n, h, w = shape
+            ptr = int(device_ptr)
+            pitch = w if pitch is None else pitch
+            frame_stride = pitch * h if frame_stride is None else frame_stride
+            flags |= DEVICE_INPUT
+        b = Batch(n, w, h, pitch, frame_stride, scale, min_size, max_size, th, t_limit, flags, k_limit)
+        t = lib().jdaB200Submit(self._h, C.c_void_p(ptr), C.byref(b))
+        if t < 0:
+            raise RuntimeError("jdaB200Submit failed: " + last_error())
+        self._pending = getattr(self, "_pending", {})
+        self._pending[t] = (frames, n)
+        return t
+
+    def collect(self, ticket):
+        """jdaB200Collect: (counts[n], boxes[total,3], scores[total], shapes[total,2L]) like detect_batch(flat=True)"""
+        L = lib()
+        fr = FlatResult()
+        st = Stats()
+        rc = L.jdaB200Collect(self._h, ticket, C.byref(fr), C.byref(st))
+        _, n = self._pending.pop(ticket, (None, 0))
+        self.last_stats = st.as_dict()
+        if rc != 0:
+            raise RuntimeError("jdaB200Collect failed: " + last_error())
+        tot, D = fr.total, 2 * fr.landmark_n
+        counts = np.ctypeslib.as_array(fr.counts, shape=(max(n, 1),))[:n].copy()
+        if tot:
+            out = (counts, np.ctypeslib.as_array(fr.bboxes, shape=(tot, 3)).copy(),
+                   np.ctypeslib.as_array(fr.scores, shape=(tot,)).copy(),
+                   np.ctypeslib.as_array(fr.shapes, shape=(tot, D)).copy())
+        else:
+            out = (counts, np.zeros((0, 3), np.int32), np.zeros((0,), np.float32), np.zeros((0, D), np.float32))
+        L.jdaB200FlatResultRelease(C.byref(fr))
+        return out
 
     def _unpack_results(self, res, n, unpack=True):
         L = lib()

@@ -143,13 +143,48 @@ Tuning read_tuning() {
   return t;
 }
 
+constexpr int kSlots = 2;
+constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntWork = kCntSurv + kMaxChunks, kCntHit = kCntWork + kMaxChunks,
+              kCntTotal = kCntHit + 1;
+
+struct Run;
+
+// Device / pinned scratch of one batch in flight.
+struct Scratch {
+  DevBuf<uint8_t> d_frames, d_hq;
+  DevBuf<int2> d_dims;             // mixed-size batches: (width, height) per frame
+  DevBuf<uint8_t> d_packed;        // mixed-size batches: frames as they lie in host memory, back to back
+  DevBuf<UnpackFrame> d_unpack;
+  std::vector<UnpackFrame> h_unpack;
+  DevBuf<uint4> d_surv;
+  DevBuf<float> d_shape0;
+  DevBuf<uint8_t> d_surv_leaves;
+  DevBuf<float> d_hits;
+  unsigned *d_counters = nullptr;  // [kMaxChunks][kMaxLevels] tile counters, surv_count, work, hit_count
+  unsigned *h_counters = nullptr;  // pinned mirror
+  std::vector<float> h_hits;
+  float *h_eager = nullptr;        // pinned: the first kEagerHits hit records
+  uint8_t *h_stage = nullptr;      // pinned staging for small pageable inputs
+  size_t h_stage_cap = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_copy[kMaxChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_done = nullptr;   // counters + first hit records of the batch are in pinned memory
+  jdaB200Stats last;               // work counters + timings of the batch that used this set last
+  bool ready = false;              // events and pinned buffers exist
+  // a submitted batch waiting for jdaB200Collect
+  bool busy = false;
+  int ticket = -1;
+  jdaB200Batch batch;
+  const unsigned char *frames = nullptr;
+  Run *run = nullptr;
+};
+
 struct Context {
   HostModel m;
   std::mutex mu;
   int device = -1;
   bool inited = false;
   cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_stream = nullptr;
-  cudaEvent_t ev_copy[kMaxChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int sm_count = 148;
   EncodeTiledFn encode = nullptr;
   // device model
@@ -162,27 +197,16 @@ struct Context {
   Geometry geo;
   DevBuf<uint8_t> d_tables;
   Stage0Norm *d_norms = nullptr;
-  // scratch
-  DevBuf<uint8_t> d_frames, d_hq, d_trace_leaf;
-  DevBuf<int2> d_dims;             // mixed-size batches: (width, height) per frame
-  DevBuf<uint8_t> d_packed;        // mixed-size batches: frames as they lie in host memory, back to back
-  DevBuf<UnpackFrame> d_unpack;
-  std::vector<UnpackFrame> h_unpack;
-  DevBuf<uint4> d_surv;
-  DevBuf<float> d_shape0;
-  DevBuf<uint8_t> d_surv_leaves;
-  DevBuf<float> d_hits;
+  // scratch: two sets, so that a submitted batch (jdaB200Submit) can be copied in and scanned while the results of
+  // the one before are still being collected; the synchronous entry points use set 0.  `sc` = the set in use.
+  Scratch slot[kSlots];
+  Scratch *sc = &slot[0];
+  DevBuf<uint8_t> d_trace_leaf;    // (tracing is synchronous: one copy)
   DevBuf<int> d_trace_n;
   DevBuf<float> d_trace_s;
-  unsigned *d_counters = nullptr;  // [kMaxLevels] tile counters, [kMaxLevels] surv_count, [+1] hit_count
-  unsigned *h_counters = nullptr;  // pinned mirror
-  std::vector<float> h_hits;
-  float *h_eager = nullptr;        // pinned: the first kEagerHits hit records
-  uint8_t *h_stage = nullptr;      // pinned staging for small pageable inputs
-  size_t h_stage_cap = 0;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t surv_cap = 0, hit_cap = 0;
-  jdaB200Stats last;
+  size_t surv_cap = 0, hit_cap = 0;  // queue capacities (shared: a set's buffers are grown to them before use)
+  cudaStream_t d2h_stream = nullptr; // read-back of hit records beyond the first few: must not queue behind the next batch
+  int next_ticket = 0;
   // double-precision detector (JoinCascador::Detect, method 1): model kept as doubles, its own geometry and tables
   std::string path;
   bool path_dbl = false;
@@ -207,9 +231,6 @@ struct Context {
 
 constexpr size_t kEagerHits = 64;
 constexpr int kLatencyFrames = 4;  // batches this small use the latency tile plan
-constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntWork = kCntSurv + kMaxChunks, kCntHit = kCntWork + kMaxChunks,
-              kCntTotal = kCntHit + 1;
-
 // First frame of chunk `ch` when a host batch is copied and scanned in `nchunks` pieces.  The pieces grow
 // (1/8, 2/8, 2/8, 3/8 of the batch): the first scan can only start when the first piece has landed, so it is small.
 int chunk_begin(int n_frames, int ch, int nchunks, bool even = false) {
@@ -226,6 +247,47 @@ size_t k3s_smem_bytes(int K, int D) {
 size_t k3_smem_bytes(int K) { return (size_t)K3_WARPS * (kMaxDim * 4 + ((K + 15) & ~15)); }
 
 void ctx_release_device(Context *c);
+
+template <typename T>
+void dev_free(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+template <typename T>
+void host_free(T *&p) {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+}
+
+// events, counters and pinned staging of one scratch set (set 0 with the handle, set 1 at the first jdaB200Submit)
+bool slot_init(Scratch &sc) {
+  if (sc.ready) return true;
+  for (auto &e : sc.ev) CU_OK(cudaEventCreate(&e));
+  for (auto &e : sc.ev_copy) CU_OK(cudaEventCreate(&e));
+  CU_OK(cudaEventCreateWithFlags(&sc.ev_done, cudaEventDisableTiming));
+  CU_OK(cudaMalloc(&sc.d_counters, kCntTotal * sizeof(unsigned)));
+  CU_OK(cudaMallocHost(&sc.h_counters, kCntTotal * sizeof(unsigned)));
+  CU_OK(cudaMallocHost(&sc.h_eager, kEagerHits * (kHitHeader + kMaxDim) * sizeof(float)));
+  sc.h_stage_cap = (size_t)8 << 20;
+  CU_OK(cudaMallocHost(&sc.h_stage, sc.h_stage_cap));
+  sc.ready = true;
+  return true;
+}
+
+void run_delete(Run *r);
+void slot_free(Scratch &sc) {
+  run_delete(sc.run);
+  sc.run = nullptr;
+  dev_free(sc.d_counters);
+  host_free(sc.h_counters); host_free(sc.h_eager); host_free(sc.h_stage);
+  sc.d_dims.release(); sc.d_packed.release(); sc.d_unpack.release(); sc.d_frames.release(); sc.d_hq.release();
+  sc.d_surv.release(); sc.d_shape0.release(); sc.d_surv_leaves.release(); sc.d_hits.release();
+  for (auto &e : sc.ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+  for (auto &e : sc.ev_copy) { if (e) cudaEventDestroy(e); e = nullptr; }
+  if (sc.ev_done) cudaEventDestroy(sc.ev_done);
+  sc.ev_done = nullptr;
+  sc.ready = false; sc.busy = false;
+}
 
 bool ctx_init_impl(Context *c) {
   int ndev = 0;
@@ -247,9 +309,10 @@ bool ctx_init_impl(Context *c) {
   }
   c->sm_count = prop.multiProcessorCount;
   CU_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-  for (auto &e : c->ev) CU_OK(cudaEventCreate(&e));
   CU_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  for (auto &e : c->ev_copy) CU_OK(cudaEventCreate(&e));
+  CU_OK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  c->sc = &c->slot[0];
+  if (!slot_init(c->slot[0])) return false;
   const HostModel &m = c->m;
   CU_OK(cudaMalloc(&c->d_nodes, m.nodes.size() * sizeof(NodeRec)));
   CU_OK(cudaMalloc(&c->d_leaf, m.leaf.size() * 4));
@@ -262,11 +325,6 @@ bool ctx_init_impl(Context *c) {
   CU_OK(cudaMemcpy(c->d_cart, m.cart.data(), m.cart.size() * 4, cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(c->d_w, m.w.data(), m.w.size() * 4, cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(c->d_mean, m.mean_shape.data(), m.mean_shape.size() * 4, cudaMemcpyHostToDevice));
-  CU_OK(cudaMalloc(&c->d_counters, kCntTotal * sizeof(unsigned)));
-  CU_OK(cudaMallocHost(&c->h_counters, kCntTotal * sizeof(unsigned)));
-  CU_OK(cudaMallocHost(&c->h_eager, kEagerHits * (kHitHeader + kMaxDim) * sizeof(float)));
-  c->h_stage_cap = (size_t)8 << 20;
-  CU_OK(cudaMallocHost(&c->h_stage, c->h_stage_cap));
   {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -328,17 +386,6 @@ bool ctx_init(Context *c) {
   return true;
 }
 
-template <typename T>
-void dev_free(T *&p) {
-  if (p) cudaFree(p);
-  p = nullptr;
-}
-template <typename T>
-void host_free(T *&p) {
-  if (p) cudaFreeHost(p);
-  p = nullptr;
-}
-
 void release_model64(Context *c) {
   dev_free(c->d_nodes64); dev_free(c->d_leaf64); dev_free(c->d_cart64); dev_free(c->d_w64); dev_free(c->d_mean64);
   dev_free(c->d_norms64);
@@ -349,19 +396,16 @@ void release_model64(Context *c) {
 void ctx_release_device(Context *c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   dev_free(c->d_nodes); dev_free(c->d_leaf); dev_free(c->d_cart); dev_free(c->d_w); dev_free(c->d_mean);
-  dev_free(c->d_norms); dev_free(c->d_counters);
+  dev_free(c->d_norms);
   release_model64(c);
   c->d_tables64.release(); c->d_hits64.release(); c->d_trace_s64.release(); c->d_trace_n64.release();
-  host_free(c->h_counters);
-  host_free(c->h_eager);
-  host_free(c->h_stage);
-  c->d_tables.release(); c->d_dims.release(); c->d_packed.release(); c->d_unpack.release(); c->d_frames.release(); c->d_hq.release(); c->d_trace_leaf.release();
-  c->d_surv.release(); c->d_shape0.release(); c->d_surv_leaves.release(); c->d_hits.release(); c->d_trace_n.release(); c->d_trace_s.release();
-  for (auto &e : c->ev) { if (e) cudaEventDestroy(e); e = nullptr; }
-  for (auto &e : c->ev_copy) { if (e) cudaEventDestroy(e); e = nullptr; }
+  c->d_tables.release(); c->d_trace_leaf.release(); c->d_trace_n.release(); c->d_trace_s.release();
+  for (auto &sl : c->slot) slot_free(sl);
+  c->sc = &c->slot[0];
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
-  c->copy_stream = nullptr; c->own_stream = nullptr;
+  c->copy_stream = nullptr; c->d2h_stream = nullptr; c->own_stream = nullptr;
   c->geo.valid = false; c->geo64.valid = false;
   cudaGetLastError();
 }
@@ -600,7 +644,13 @@ struct Run {
   float r;             // 1.f / sqrtf(2.f) as the reference computes it (c/jda.c:341)
   int hw, hh, qw, qh;
   size_t hq_stride;
+  size_t eager;        // hit records that travel with the counters (collect_start)
+  bool async;          // submitted batch: its copies must not queue behind the batch before it
+  size_t cap_surv, cap_hit;  // queue capacities the kernels of this attempt were launched with
+  bool done;           // nothing to run (no frames, or no pyramid level fits)
 };
+
+void run_delete(Run *r) { delete r; }
 
 // mixed-size batch: host -> canvas slots for the frames of chunk `ch` (each chunk once per call).  Every frame is
 // copied as one contiguous blob into the packed staging area (frames that are neighbours in host memory share a
@@ -610,7 +660,7 @@ bool copy_mixed_chunk(Run &R, int ch) {
   const jdaB200Batch &b = *R.b;
   if (ch >= R.nchunks || ch < R.chunks_copied) return true;
   const int f0 = chunk_begin(b.n_frames, ch, R.nchunks, c->tune.even_chunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks, c->tune.even_chunks);
-  const UnpackFrame *tab = c->h_unpack.data();
+  const UnpackFrame *tab = c->sc->h_unpack.data();
   int run0 = f0;
   for (int f = f0; f <= f1; f++) {
     // [run0, f) is a run of frames that are contiguous in host memory (and therefore in the staging area)
@@ -620,17 +670,17 @@ bool copy_mixed_chunk(Run &R, int ch) {
     if (f > run0) {
       const size_t bytes = tab[f - 1].src_off + frame_bytes(R.mixed[f - 1]) - tab[run0].src_off;
       if (bytes > 0)
-        CU_OK(cudaMemcpyAsync(c->d_packed.p + tab[run0].src_off, R.mixed[run0].data, bytes, cudaMemcpyHostToDevice,
+        CU_OK(cudaMemcpyAsync(c->sc->d_packed.p + tab[run0].src_off, R.mixed[run0].data, bytes, cudaMemcpyHostToDevice,
                               c->copy_stream));
     }
     run0 = f;
   }
   if (f1 > f0) {
     dim3 grid((b.height + 7) / 8, f1 - f0);
-    k0_unpack<<<grid, 128, 0, c->copy_stream>>>(c->d_packed.p, c->d_unpack.p, f0, c->d_frames.p, R.fstride, R.pitch);
+    k0_unpack<<<grid, 128, 0, c->copy_stream>>>(c->sc->d_packed.p, c->sc->d_unpack.p, f0, c->sc->d_frames.p, R.fstride, R.pitch);
     CU_OK(cudaGetLastError());
   }
-  CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
+  CU_OK(cudaEventRecord(c->sc->ev_copy[ch], c->copy_stream));
   R.chunks_copied = ch + 1;
   return true;
 }
@@ -650,70 +700,76 @@ bool stage_frames(Run &R, const unsigned char *frames) {
   }
   R.pitch = (b.width + 15) & ~15;
   R.fstride = (size_t)R.pitch * b.height;
-  if (!c->d_frames.ensure(R.fstride * b.n_frames + 256)) return false;
+  if (!c->sc->d_frames.ensure(R.fstride * b.n_frames + 256)) return false;
   if (b.n_frames >= 128 && !m.any_scaled && R.use_scan && !R.tracing && !c->tune.no_chunks) {
     R.nchunks = kMaxChunks;
     R.host_chunks = true;
   }
-  CU_OK(cudaEventRecord(c->ev_copy[kMaxChunks], R.s));
-  CU_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
+  if (R.async) {
+    // this scratch set's previous batch was collected (jdaB200Collect waited for it), so its frame store is free: the
+    // copies start at once, next to the kernels of the batch submitted before
+    CU_OK(cudaEventRecord(c->sc->ev_copy[kMaxChunks], c->copy_stream));
+  } else {
+    CU_OK(cudaEventRecord(c->sc->ev_copy[kMaxChunks], R.s));
+    CU_OK(cudaStreamWaitEvent(c->copy_stream, c->sc->ev_copy[kMaxChunks], 0));  // scratch of the previous call is free
+  }
   if (R.mixed) {
     // every frame goes to the top-left corner of its canvas slot; what lies outside a frame inside its slot is
     // never sampled (windows are enumerated from the frame's own width and height), so it is left as it is.
     // Only the first chunk's copies are issued here: launch_scan issues chunk i+1 right after the scan of
     // chunk i, so the host-side cost of thousands of small copy calls hides behind the running scan too.
-    if (!c->d_dims.ensure(b.n_frames)) return false;
+    if (!c->sc->d_dims.ensure(b.n_frames)) return false;
     std::vector<int2> dims(b.n_frames);
     for (int f = 0; f < b.n_frames; f++) dims[f] = make_int2(std::max(R.mixed[f].width, 0), std::max(R.mixed[f].height, 0));
-    CU_OK(cudaMemcpyAsync(c->d_dims.p, dims.data(), dims.size() * sizeof(int2), cudaMemcpyHostToDevice, c->copy_stream));
+    CU_OK(cudaMemcpyAsync(c->sc->d_dims.p, dims.data(), dims.size() * sizeof(int2), cudaMemcpyHostToDevice, c->copy_stream));
     // staging layout: host neighbours stay neighbours (one copy per run), everything else starts 16-byte aligned
-    c->h_unpack.resize(b.n_frames);
+    c->sc->h_unpack.resize(b.n_frames);
     size_t off = 0;
     for (int f = 0; f < b.n_frames; f++) {
       const jdaB200Frame &fr = R.mixed[f];
       const bool adjacent = f > 0 && frame_bytes(R.mixed[f - 1]) > 0 && fr.data == R.mixed[f - 1].data + frame_bytes(R.mixed[f - 1]);
       if (!adjacent) off = (off + 15) & ~(size_t)15;
-      c->h_unpack[f] = UnpackFrame{(unsigned long long)off, std::max(fr.width, 0), std::max(fr.height, 0),
+      c->sc->h_unpack[f] = UnpackFrame{(unsigned long long)off, std::max(fr.width, 0), std::max(fr.height, 0),
                                    fr.pitch > 0 ? fr.pitch : fr.width, 0};
       off += frame_bytes(fr);
     }
-    if (!c->d_packed.ensure(off + 16) || !c->d_unpack.ensure(b.n_frames)) return false;
-    CU_OK(cudaMemcpyAsync(c->d_unpack.p, c->h_unpack.data(), (size_t)b.n_frames * sizeof(UnpackFrame), cudaMemcpyHostToDevice,
+    if (!c->sc->d_packed.ensure(off + 16) || !c->sc->d_unpack.ensure(b.n_frames)) return false;
+    CU_OK(cudaMemcpyAsync(c->sc->d_unpack.p, c->sc->h_unpack.data(), (size_t)b.n_frames * sizeof(UnpackFrame), cudaMemcpyHostToDevice,
                           c->copy_stream));
     R.chunks_copied = 0;
     if (!copy_mixed_chunk(R, 0)) return false;
-    if (!R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[0], 0));
-    R.d_frames = c->d_frames.p;
+    if (!R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->sc->ev_copy[0], 0));
+    R.d_frames = c->sc->d_frames.p;
     return true;
   }
   bool staged = false;
-  if (R.nchunks == 1 && R.fstride * b.n_frames <= c->h_stage_cap) {
+  if (R.nchunks == 1 && R.fstride * b.n_frames <= c->sc->h_stage_cap) {
     cudaPointerAttributes pa;
     const bool pageable = cudaPointerGetAttributes(&pa, frames) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
     cudaGetLastError();
     if (pageable) {
       for (int f = 0; f < b.n_frames; f++)
         for (int y = 0; y < b.height; y++)
-          memcpy(c->h_stage + f * R.fstride + (size_t)y * R.pitch, frames + f * b.frame_stride + (size_t)y * b.pitch, b.width);
-      CU_OK(cudaMemcpyAsync(c->d_frames.p, c->h_stage, R.fstride * b.n_frames, cudaMemcpyHostToDevice, c->copy_stream));
-      CU_OK(cudaEventRecord(c->ev_copy[0], c->copy_stream));
+          memcpy(c->sc->h_stage + f * R.fstride + (size_t)y * R.pitch, frames + f * b.frame_stride + (size_t)y * b.pitch, b.width);
+      CU_OK(cudaMemcpyAsync(c->sc->d_frames.p, c->sc->h_stage, R.fstride * b.n_frames, cudaMemcpyHostToDevice, c->copy_stream));
+      CU_OK(cudaEventRecord(c->sc->ev_copy[0], c->copy_stream));
       staged = true;
     }
   }
   for (int ch = 0; ch < R.nchunks && !staged; ch++) {
     const int f0 = chunk_begin(b.n_frames, ch, R.nchunks, c->tune.even_chunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks, c->tune.even_chunks);
     if (b.frame_stride == (size_t)b.pitch * b.height) {
-      CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f0 * R.fstride, R.pitch, frames + f0 * b.frame_stride, b.pitch, b.width,
+      CU_OK(cudaMemcpy2DAsync(c->sc->d_frames.p + f0 * R.fstride, R.pitch, frames + f0 * b.frame_stride, b.pitch, b.width,
                               (size_t)b.height * (f1 - f0), cudaMemcpyHostToDevice, c->copy_stream));
     } else {
       for (int f = f0; f < f1; f++)
-        CU_OK(cudaMemcpy2DAsync(c->d_frames.p + f * R.fstride, R.pitch, frames + f * b.frame_stride, b.pitch, b.width,
+        CU_OK(cudaMemcpy2DAsync(c->sc->d_frames.p + f * R.fstride, R.pitch, frames + f * b.frame_stride, b.pitch, b.width,
                                 b.height, cudaMemcpyHostToDevice, c->copy_stream));
     }
-    CU_OK(cudaEventRecord(c->ev_copy[ch], c->copy_stream));
+    CU_OK(cudaEventRecord(c->sc->ev_copy[ch], c->copy_stream));
   }
-  if (!R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[0], 0));
-  R.d_frames = c->d_frames.p;
+  if (!R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->sc->ev_copy[0], 0));
+  R.d_frames = c->sc->d_frames.p;
   return true;
 }
 
@@ -725,15 +781,15 @@ bool make_planes(Run &R) {
   R.hw = (int)(b.width * R.r); R.hh = (int)(b.height * R.r); R.qw = b.width / 2; R.qh = b.height / 2;
   R.hq_stride = (size_t)R.hw * R.hh + (size_t)R.qw * R.qh;
   if (!c->m.any_scaled) return true;
-  if (!c->d_hq.ensure(R.hq_stride * b.n_frames)) return false;
+  if (!c->sc->d_hq.ensure(R.hq_stride * b.n_frames)) return false;
   const int big = std::max(R.hw * R.hh, R.qw * R.qh);
   for (int f0 = 0; f0 < b.n_frames; f0 += 32768) {  // gridDim.z limit
     dim3 grid((big + 255) / 256, 2, std::min(32768, b.n_frames - f0));
     k1_resize<<<grid, 256, 0, R.s>>>(R.d_frames + (size_t)f0 * R.fstride, R.fstride, R.pitch, b.width, b.height,
-                                    c->d_hq.p + (size_t)f0 * R.hq_stride, R.hq_stride, R.hw, R.hh, R.qw, R.qh);
+                                    c->sc->d_hq.p + (size_t)f0 * R.hq_stride, R.hq_stride, R.hw, R.hh, R.qw, R.qh);
     CU_OK(cudaGetLastError());
   }
-  c->last.resize_launches = 1;
+  c->sc->last.resize_launches = 1;
   return true;
 }
 
@@ -756,7 +812,7 @@ bool launch_scan(Run &R) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;
   const Geometry &g = *R.geo;
-  jdaB200Stats &st = c->last;
+  jdaB200Stats &st = c->sc->last;
   ScanParams P;
   memset(&P, 0, sizeof P);
   for (int i = 0; i < g.n_levels; i++) P.lv[i] = g.lv[i];
@@ -767,10 +823,10 @@ bool launch_scan(Run &R) {
   P.n_sched = 0;
   for (size_t i = 0; i < c->sched.size() && c->sched[i] < R.scan_K; i++) P.sched[P.n_sched++] = c->sched[i];
   P.sched[P.n_sched++] = (short)R.scan_K;  // the last phase ends at the last cart the scan walks
-  P.surv = c->d_surv.p; P.surv_count = c->d_counters + kCntSurv; P.surv_cap = (unsigned)c->surv_cap;
-  P.surv_leaves = R.t_run > 0 ? c->d_surv_leaves.p : nullptr;  // the leaves feed the stage-0 regression only
+  P.surv = c->sc->d_surv.p; P.surv_count = c->sc->d_counters + kCntSurv; P.surv_cap = (unsigned)c->surv_cap;
+  P.surv_leaves = R.t_run > 0 ? c->sc->d_surv_leaves.p : nullptr;  // the leaves feed the stage-0 regression only
   P.leaf_pad = R.leaf_pad;
-  P.frame_dims = R.mixed ? c->d_dims.p : nullptr;
+  P.frame_dims = R.mixed ? c->sc->d_dims.p : nullptr;
   // TMA needs 16-byte aligned base and strides
   const bool tma_ok = c->encode && !(b.flags & JDA_B200_NO_TMA) && ((uintptr_t)R.d_frames % 16 == 0) &&
                       R.pitch % 16 == 0 && R.fstride % 16 == 0;
@@ -806,7 +862,7 @@ bool launch_scan(Run &R) {
     P.frames = R.d_frames + (size_t)f0 * R.fstride;
     P.n_frames = f1 - f0;
     P.frame_base = f0;
-    P.tile_counters = c->d_counters + ch * kMaxLevels;
+    P.tile_counters = c->sc->d_counters + ch * kMaxLevels;
     for (int i = 0; i < g.n_levels && tma_ok; i++) {
       if (!g.lv[i].use_smem) continue;
       cuuint64_t dims[3] = {(cuuint64_t)b.width, (cuuint64_t)b.height, (cuuint64_t)(f1 - f0)};
@@ -822,7 +878,7 @@ bool launch_scan(Run &R) {
       }
     }
     if (R.mixed && !copy_mixed_chunk(R, ch)) return false;  // no-op unless an earlier chunk was empty
-    if (R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->ev_copy[ch], 0));
+    if (R.host_chunks) CU_OK(cudaStreamWaitEvent(R.s, c->sc->ev_copy[ch], 0));
     const int nw = c->tune.nw;
     if (R.mixed) {  // per-frame window grids: always the MIXED instantiation (4 windows per lane whatever the A/B knob says)
       k2_scan<4, false, true><<<grid, K2_WARPS * 32, smem, R.s>>>(P);
@@ -852,14 +908,14 @@ bool launch_cascade(Run &R) {
   const jdaB200Batch &b = *R.b;
   const Geometry &g = *R.geo;
   const HostModel &m = c->m;
-  jdaB200Stats &st = c->last;
+  jdaB200Stats &st = c->sc->last;
   if (R.staged0) {
     Stage0Params S;
     memset(&S, 0, sizeof S);
-    S.surv_leaves = c->d_surv_leaves.p;
+    S.surv_leaves = c->sc->d_surv_leaves.p;
     S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
-    S.surv_count = c->d_counters + kCntSurv; S.surv_cap = (unsigned)c->surv_cap;
-    S.out_shape = c->d_shape0.p;
+    S.surv_count = c->sc->d_counters + kCntSurv; S.surv_cap = (unsigned)c->surv_cap;
+    S.out_shape = c->sc->d_shape0.p;
     if (R.D <= 64) k3_stage0<1><<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
     else k3_stage0<2><<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
     CU_OK(cudaGetLastError());
@@ -868,7 +924,7 @@ bool launch_cascade(Run &R) {
   CascadeParams Q;
   memset(&Q, 0, sizeof Q);
   Q.frames = R.d_frames; Q.frame_stride = R.fstride; Q.pitch = R.pitch; Q.W = b.width; Q.H = b.height;
-  Q.hq = m.any_scaled ? c->d_hq.p : nullptr; Q.hq_stride = R.hq_stride; Q.hw = R.hw; Q.hh = R.hh; Q.qw = R.qw; Q.qh = R.qh;
+  Q.hq = m.any_scaled ? c->sc->d_hq.p : nullptr; Q.hq_stride = R.hq_stride; Q.hw = R.hw; Q.hh = R.hh; Q.qw = R.qw; Q.qh = R.qh;
   Q.nodes = c->d_nodes; Q.leaf = c->d_leaf; Q.cart = c->d_cart; Q.w = c->d_w; Q.mean_shape = c->d_mean;
   Q.depth = m.depth; Q.nn = m.nn; Q.nl = m.nl;
   Q.T = m.T; Q.K = m.K; Q.L = m.L; Q.t_run = R.t_run; Q.k_extra = R.k_extra; Q.r = R.r;
@@ -883,10 +939,10 @@ bool launch_cascade(Run &R) {
   // truncated cascade ended inside stage 0: the scan walked all of its k_extra carts)
   Q.t_start = (R.staged0 || (R.use_scan && R.t_run == 0)) ? 1 : 0;
   Q.n_eval0 = R.scan_K;
-  Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
-  Q.init_shape = R.staged0 ? c->d_shape0.p : nullptr;
-  Q.work_counter = c->d_counters + kCntWork;
-  Q.hits = c->d_hits.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
+  Q.surv = c->sc->d_surv.p; Q.surv_count = c->sc->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
+  Q.init_shape = R.staged0 ? c->sc->d_shape0.p : nullptr;
+  Q.work_counter = c->sc->d_counters + kCntWork;
+  Q.hits = c->sc->d_hits.p; Q.hit_count = c->sc->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit_cap;
   Q.rec_words = R.rec_words; Q.th = b.th; Q.use_th = (b.flags & JDA_B200_NO_FINAL_TH) ? 0 : 1;
   if (R.tracing) {
     Q.trace_n = c->d_trace_n.p; Q.trace_s = c->d_trace_s.p;
@@ -907,19 +963,30 @@ bool launch_cascade(Run &R) {
   return true;
 }
 
-// Counters + hit records back to the host.  overflow = a queue was too small (capacities already grown).
-bool collect(Run &R, std::vector<HitRec> &hits, bool &overflow) {
+// Counters + the first hit records start their way back to pinned memory right behind the kernels; ev_done marks
+// their arrival.  (A submitted batch is collected later: the stream may by then hold the next batch's kernels, so
+// nothing in collect_finish may wait for the stream itself.)
+bool collect_start(Run &R) {
   Context *c = R.c;
-  jdaB200Stats &st = c->last;
   cudaStream_t s = R.s;
-  overflow = false;
-  CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  CU_OK(cudaMemcpyAsync(c->sc->h_counters, c->sc->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
   // the first records ride along with the counters: a call with few hits needs a single round trip
-  const size_t eager = std::min<size_t>(kEagerHits, c->hit_cap);
-  CU_OK(cudaMemcpyAsync(c->h_eager, c->d_hits.p, eager * R.rec_words * 4, cudaMemcpyDeviceToHost, s));
-  CU_OK(cudaStreamSynchronize(s));
-  const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
-  if (ns > c->surv_cap || nh > c->hit_cap) {
+  R.eager = std::min<size_t>(kEagerHits, c->hit_cap);
+  CU_OK(cudaMemcpyAsync(c->sc->h_eager, c->sc->d_hits.p, R.eager * R.rec_words * 4, cudaMemcpyDeviceToHost, s));
+  CU_OK(cudaEventRecord(c->sc->ev_done, s));
+  return true;
+}
+
+// Waits for the batch, reads the rest of the hit records and sorts them into scan order.
+// overflow = a queue was too small (capacities already grown): run the batch again.
+bool collect_finish(Run &R, std::vector<HitRec> &hits, bool &overflow) {
+  Context *c = R.c;
+  jdaB200Stats &st = c->sc->last;
+  overflow = false;
+  CU_OK(cudaEventSynchronize(c->sc->ev_done));
+  const size_t eager = R.eager;
+  const size_t ns = c->sc->h_counters[kCntSurv], nh = c->sc->h_counters[kCntHit];
+  if (ns > R.cap_surv || nh > R.cap_hit) {  // (the capacities this batch ran with: another batch may have grown them since)
     if (ns > c->surv_cap) c->surv_cap = ns + ns / 4;
     if (nh > c->hit_cap) c->hit_cap = nh + nh / 4;
     overflow = true;
@@ -927,26 +994,27 @@ bool collect(Run &R, std::vector<HitRec> &hits, bool &overflow) {
   }
   st.stage0_survivors = R.use_scan ? (long long)ns : 0;
   st.raw_hits = (long long)nh;
+  cudaStream_t d = c->d2h_stream;  // the records are complete (ev_done): no need to queue behind the compute stream
+  c->sc->h_hits.resize(std::max(nh, (size_t)1) * R.rec_words);
+  memcpy(c->sc->h_hits.data(), c->sc->h_eager, std::min(nh, eager) * R.rec_words * 4);
   bool more = false;
-  c->h_hits.resize(std::max(nh, (size_t)1) * R.rec_words);
-  memcpy(c->h_hits.data(), c->h_eager, std::min(nh, eager) * R.rec_words * 4);
   if (nh > eager) {
-    CU_OK(cudaMemcpyAsync(c->h_hits.data() + eager * R.rec_words, c->d_hits.p + eager * R.rec_words,
-                          (nh - eager) * R.rec_words * 4, cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaMemcpyAsync(c->sc->h_hits.data() + eager * R.rec_words, c->sc->d_hits.p + eager * R.rec_words,
+                          (nh - eager) * R.rec_words * 4, cudaMemcpyDeviceToHost, d));
     more = true;
   }
   if (R.tracing) {
     const TraceOut *t = R.trace;
-    if (t->n) CU_OK(cudaMemcpyAsync(t->n, c->d_trace_n.p, R.total_windows * 4, cudaMemcpyDeviceToHost, s));
-    if (t->s) CU_OK(cudaMemcpyAsync(t->s, c->d_trace_s.p, R.total_windows * 4, cudaMemcpyDeviceToHost, s));
+    if (t->n) CU_OK(cudaMemcpyAsync(t->n, c->d_trace_n.p, R.total_windows * 4, cudaMemcpyDeviceToHost, d));
+    if (t->s) CU_OK(cudaMemcpyAsync(t->s, c->d_trace_s.p, R.total_windows * 4, cudaMemcpyDeviceToHost, d));
     if (t->leaf && t->w1 > t->w0)
-      CU_OK(cudaMemcpyAsync(t->leaf, c->d_trace_leaf.p, (size_t)(t->w1 - t->w0) * R.leaf_stride, cudaMemcpyDeviceToHost, s));
+      CU_OK(cudaMemcpyAsync(t->leaf, c->d_trace_leaf.p, (size_t)(t->w1 - t->w0) * R.leaf_stride, cudaMemcpyDeviceToHost, d));
   }
-  if (R.timing) CU_OK(cudaEventRecord(c->ev[5], s));
-  if (more || R.tracing || R.timing) CU_OK(cudaStreamSynchronize(s));
+  if (R.timing) CU_OK(cudaEventRecord(c->sc->ev[5], d));
+  if (more || R.tracing || R.timing) CU_OK(cudaStreamSynchronize(d));
   hits.resize(nh);
   for (size_t i = 0; i < nh; i++) {
-    const float *rec = c->h_hits.data() + i * R.rec_words;
+    const float *rec = c->sc->h_hits.data() + i * R.rec_words;
     const int *ri = reinterpret_cast<const int *>(rec);
     hits[i] = HitRec{ri[0], (uint32_t)ri[1], ri[2], ri[3], ri[4], rec[5], rec + kHitHeader};
   }
@@ -959,20 +1027,23 @@ bool collect(Run &R, std::vector<HitRec> &hits, bool &overflow) {
 
 // Runs the device path for one batch; on success `hits` holds the raw hit records sorted into scan
 // order (frame, level, y, x).  The record floats stay alive in the context until the next call.
-bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, std::vector<HitRec> &hits,
-                const TraceOut *trace, bool timing, const jdaB200Frame *mixed = nullptr) {
-  hits.clear();
-  jdaB200Stats &st = c->last;
+// run_device = run_prepare (geometry, frames to HBM, planes) -> [run_enqueue (kernels + start of the read-back) ->
+// run_finish (wait, hit records, scan order)] repeated with larger queues while one overflows.  jdaB200Submit stops
+// after run_enqueue, jdaB200Collect picks up at run_finish.
+// R.done = nothing to do (no frames / no levels): `hits` stays empty.
+bool run_prepare(Context *c, Run &R, const unsigned char *frames, const jdaB200Batch &b, const TraceOut *trace,
+                 bool timing, const jdaB200Frame *mixed, bool async = false) {
+  jdaB200Stats &st = c->sc->last;
   memset(&st, 0, sizeof st);
+  memset(&R, 0, sizeof R);
+  R.done = true;
+  R.async = async;
   if (b.n_frames <= 0) return true;
   if (b.width <= 0 || b.height <= 0 ||
       (!mixed && (b.pitch < b.width || b.frame_stride < (size_t)b.pitch * (b.height - 1) + b.width))) {
     set_err("bad batch descriptor");
     return false;
   }
-  if (!ctx_init(c)) return false;
-  Run R;
-  memset(&R, 0, sizeof R);
   R.c = c; R.b = &b; R.mixed = mixed; R.trace = trace; R.timing = timing; R.tracing = trace != nullptr;
   R.latency_plan = b.n_frames <= kLatencyFrames;
   if (c->tune.force_plan) R.latency_plan = c->tune.force_plan == 1;
@@ -987,6 +1058,7 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
       st.windows += count_windows(mixed[f].width, mixed[f].height, b.scale, b.min_size, b.max_size);
   }
   if (g.n_levels == 0) return true;
+  R.done = false;
   const HostModel &m = c->m;
   R.s = c->stream();
   R.D = m.D();
@@ -1011,9 +1083,9 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
   R.staged0 = R.use_scan && !R.latency_plan && R.t_run > 0;
   cudaStream_t s = R.s;
 
-  if (timing) CU_OK(cudaEventRecord(c->ev[0], s));
+  if (timing) CU_OK(cudaEventRecord(c->sc->ev[0], s));
   if (!stage_frames(R, frames)) return false;
-  if (timing) CU_OK(cudaEventRecord(c->ev[1], s));
+  if (timing) CU_OK(cudaEventRecord(c->sc->ev[1], s));
   if (!make_planes(R) || !prepare_trace(R)) return false;
 
   if (c->tune.tiny_queues) {  // test hook (read in ctx_init): start with queues that overflow, exercise grow-and-retry
@@ -1024,31 +1096,62 @@ bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, 
     c->surv_cap = std::max(c->surv_cap, (size_t)b.n_frames * 1024);
     c->hit_cap = std::max(c->hit_cap, (size_t)b.n_frames * 128);
   }
+  return true;
+}
 
+bool run_enqueue(Run &R) {
+  Context *c = R.c;
+  cudaStream_t s = R.s;
+  if (!c->sc->d_surv.ensure(c->surv_cap) || !c->sc->d_hits.ensure(c->hit_cap * R.rec_words)) return false;
+  if (R.use_scan && (!c->sc->d_shape0.ensure(c->surv_cap * R.D) || !c->sc->d_surv_leaves.ensure(c->surv_cap * R.leaf_pad))) return false;
+  R.cap_surv = c->surv_cap; R.cap_hit = c->hit_cap;
+  CU_OK(cudaMemsetAsync(c->sc->d_counters, 0, kCntTotal * sizeof(unsigned), s));
+  if (R.timing) CU_OK(cudaEventRecord(c->sc->ev[2], s));
+  if (R.use_scan && !launch_scan(R)) return false;
+  if (R.timing) CU_OK(cudaEventRecord(c->sc->ev[3], s));
+  if (!launch_cascade(R)) return false;
+  if (R.timing) CU_OK(cudaEventRecord(c->sc->ev[4], s));
+  return collect_start(R);
+}
+
+bool run_finish(Run &R, std::vector<HitRec> &hits, bool &overflow) {
+  Context *c = R.c;
+  jdaB200Stats &st = c->sc->last;
+  if (!collect_finish(R, hits, overflow)) return false;
+  if (overflow || !R.timing) return true;
+  if (R.b->flags & JDA_B200_DEVICE_INPUT) st.ms_h2d = 0.f;
+  else cudaEventElapsedTime(&st.ms_h2d, c->sc->ev_copy[kMaxChunks], c->sc->ev_copy[R.host_chunks ? R.nchunks - 1 : 0]);
+  cudaEventElapsedTime(&st.ms_resize, c->sc->ev[1], c->sc->ev[2]);
+  cudaEventElapsedTime(&st.ms_scan, c->sc->ev[2], c->sc->ev[3]);
+  cudaEventElapsedTime(&st.ms_cascade, c->sc->ev[3], c->sc->ev[4]);
+  cudaEventElapsedTime(&st.ms_d2h, c->sc->ev[4], c->sc->ev[5]);
+  return true;
+}
+
+// finish + the rare re-runs with larger queues; on success `hits` holds the raw hit records sorted into scan order
+// (frame, level, y, x).  The record floats stay alive in the scratch set until its next batch.
+bool run_finish_retrying(Run &R, std::vector<HitRec> &hits) {
   for (int attempt = 0; attempt < 4; attempt++) {
-    if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits.ensure(c->hit_cap * R.rec_words)) return false;
-    if (R.use_scan && (!c->d_shape0.ensure(c->surv_cap * R.D) || !c->d_surv_leaves.ensure(c->surv_cap * R.leaf_pad))) return false;
-    CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
-    if (timing) CU_OK(cudaEventRecord(c->ev[2], s));
-    if (R.use_scan && !launch_scan(R)) return false;
-    if (timing) CU_OK(cudaEventRecord(c->ev[3], s));
-    if (!launch_cascade(R)) return false;
-    if (timing) CU_OK(cudaEventRecord(c->ev[4], s));
     bool overflow = false;
-    if (!collect(R, hits, overflow)) return false;
-    if (overflow) continue;  // queues were too small: they have been grown, run again
-    if (timing) {
-      if (b.flags & JDA_B200_DEVICE_INPUT) st.ms_h2d = 0.f;
-      else cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[R.host_chunks ? R.nchunks - 1 : 0]);
-      cudaEventElapsedTime(&st.ms_resize, c->ev[1], c->ev[2]);
-      cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
-      cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);
-      cudaEventElapsedTime(&st.ms_d2h, c->ev[4], c->ev[5]);
-    }
-    return true;
+    if (!run_finish(R, hits, overflow)) return false;
+    if (!overflow) return true;
+    if (attempt < 3 && !run_enqueue(R)) return false;  // queues were too small: they have been grown, run again
   }
   set_err("survivor / hit queues kept overflowing");
   return false;
+}
+
+bool run_device(Context *c, const unsigned char *frames, const jdaB200Batch &b, std::vector<HitRec> &hits,
+                const TraceOut *trace, bool timing, const jdaB200Frame *mixed = nullptr) {
+  hits.clear();
+  if (b.n_frames > 0 && !ctx_init(c)) return false;
+  for (const Scratch &sl : c->slot)
+    if (sl.busy) { set_err("a submitted batch is waiting for jdaB200Collect: collect it before a synchronous call"); return false; }
+  c->sc = &c->slot[0];
+  Run R;
+  if (!run_prepare(c, R, frames, b, trace, timing, mixed)) return false;
+  if (R.done) return true;
+  return run_enqueue(R) && run_finish_retrying(R, hits);
 }
 
 // =============================================================================== double-precision detector
@@ -1172,12 +1275,15 @@ bool ensure_geometry64(Context *c, int w, int h, int minimum_size, int step, dou
 bool run_device64(Context *c, const unsigned char *frames, int n_frames, int width, int height,
                   const jdaB200CppParams &prm, std::vector<Hit64> &hits, int *trace_n, double *trace_s, bool timing) {
   hits.clear();
-  jdaB200Stats &st = c->last;
+  jdaB200Stats &st = c->sc->last;
   memset(&st, 0, sizeof st);
   if (n_frames <= 0) return true;
   if (width <= 0 || height <= 0) { set_err("bad frame size"); return false; }
   if (prm.step <= 0 || prm.minimum_size <= 0) { set_err("fddb.step and fddb.minimum_size must be positive"); return false; }
   if (!ctx_init(c) || !ensure_model64(c)) return false;
+  for (const Scratch &sl : c->slot)
+    if (sl.busy) { set_err("a submitted batch is waiting for jdaB200Collect: collect it before a synchronous call"); return false; }
+  c->sc = &c->slot[0];
   const HostModelD &m = c->md;
   jdaB200Batch b;
   memset(&b, 0, sizeof b);
@@ -1201,9 +1307,9 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
   R.total_windows = st.windows;
   R.use_scan = c->filter64_ok && !(prm.flags & JDA_B200_NO_STAGE0_SCAN) && !tracing;
   cudaStream_t s = R.s;
-  if (timing) CU_OK(cudaEventRecord(c->ev[0], s));
+  if (timing) CU_OK(cudaEventRecord(c->sc->ev[0], s));
   if (!stage_frames(R, frames)) return false;
-  if (timing) CU_OK(cudaEventRecord(c->ev[1], s));
+  if (timing) CU_OK(cudaEventRecord(c->sc->ev[1], s));
   if (tracing) {
     if (!c->d_trace_n64.ensure(R.total_windows) || !c->d_trace_s64.ensure(R.total_windows)) return false;
     CU_OK(cudaMemsetAsync(c->d_trace_n64.p, 0, R.total_windows * 4, s));
@@ -1215,14 +1321,14 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
   c->hit64_cap = std::max(c->hit64_cap, (size_t)n_frames * 512);
   const int rec = kHit64Header + R.D;
   for (int attempt = 0; attempt < 4; attempt++) {
-    if (!c->d_surv.ensure(c->surv_cap) || !c->d_hits64.ensure(c->hit64_cap * rec)) return false;
-    if (R.use_scan && !c->d_surv_leaves.ensure(c->surv_cap * R.leaf_pad)) return false;
-    CU_OK(cudaMemsetAsync(c->d_counters, 0, kCntTotal * sizeof(unsigned), s));
-    if (timing) CU_OK(cudaEventRecord(c->ev[2], s));
+    if (!c->sc->d_surv.ensure(c->surv_cap) || !c->d_hits64.ensure(c->hit64_cap * rec)) return false;
+    if (R.use_scan && !c->sc->d_surv_leaves.ensure(c->surv_cap * R.leaf_pad)) return false;
+    CU_OK(cudaMemsetAsync(c->sc->d_counters, 0, kCntTotal * sizeof(unsigned), s));
+    if (timing) CU_OK(cudaEventRecord(c->sc->ev[2], s));
     if (R.use_scan && !launch_scan(R)) return false;
     if (!R.use_scan && R.host_chunks)  // dense mode reads every frame: wait for the whole copy
-      CU_OK(cudaStreamWaitEvent(s, c->ev_copy[R.nchunks - 1], 0));
-    if (timing) CU_OK(cudaEventRecord(c->ev[3], s));
+      CU_OK(cudaStreamWaitEvent(s, c->sc->ev_copy[R.nchunks - 1], 0));
+    if (timing) CU_OK(cudaEventRecord(c->sc->ev[3], s));
     Cascade64Params Q;
     memset(&Q, 0, sizeof Q);
     Q.frames = R.d_frames; Q.frame_stride = R.fstride; Q.pitch = R.pitch;
@@ -1234,20 +1340,20 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
       Q.lv_base[i] = g.lv[i].win_base;
     }
     Q.windows_per_frame = g.windows_per_frame;
-    Q.surv = c->d_surv.p; Q.surv_count = c->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
+    Q.surv = c->sc->d_surv.p; Q.surv_count = c->sc->d_counters + kCntSurv; Q.surv_cap = (unsigned)c->surv_cap;
     Q.dense = R.use_scan ? 0 : 1; Q.dense_total = R.total_windows;
-    Q.hits = c->d_hits64.p; Q.hit_count = c->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit64_cap;
+    Q.hits = c->d_hits64.p; Q.hit_count = c->sc->d_counters + kCntHit; Q.hit_cap = (unsigned)c->hit64_cap;
     Q.rec_doubles = rec;
-    Q.work_counter = c->d_counters + kCntWork;
+    Q.work_counter = c->sc->d_counters + kCntWork;
     Q.trace_n = tracing ? c->d_trace_n64.p : nullptr;
     Q.trace_s = tracing ? c->d_trace_s64.p : nullptr;
     k4_cascade_f64<<<c->sm_count * 8, K4_WARPS * 32, K4_WARPS * (kMaxDim * 8 + ((m.K + 15) & ~15)), s>>>(Q);
     CU_OK(cudaGetLastError());
     st.cascade_launches++;
-    if (timing) CU_OK(cudaEventRecord(c->ev[4], s));
-    CU_OK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    if (timing) CU_OK(cudaEventRecord(c->sc->ev[4], s));
+    CU_OK(cudaMemcpyAsync(c->sc->h_counters, c->sc->d_counters, kCntTotal * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     CU_OK(cudaStreamSynchronize(s));
-    const size_t ns = c->h_counters[kCntSurv], nh = c->h_counters[kCntHit];
+    const size_t ns = c->sc->h_counters[kCntSurv], nh = c->sc->h_counters[kCntHit];
     if ((R.use_scan && ns > c->surv_cap) || nh > c->hit64_cap) {
       if (ns > c->surv_cap) c->surv_cap = ns + ns / 4;
       if (nh > c->hit64_cap) c->hit64_cap = nh + nh / 4;
@@ -1259,7 +1365,7 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
     if (nh) CU_OK(cudaMemcpyAsync(c->h_hits64.data(), c->d_hits64.p, nh * rec * 8, cudaMemcpyDeviceToHost, s));
     if (trace_n) CU_OK(cudaMemcpyAsync(trace_n, c->d_trace_n64.p, R.total_windows * 4, cudaMemcpyDeviceToHost, s));
     if (trace_s) CU_OK(cudaMemcpyAsync(trace_s, c->d_trace_s64.p, R.total_windows * 8, cudaMemcpyDeviceToHost, s));
-    if (timing) CU_OK(cudaEventRecord(c->ev[5], s));
+    if (timing) CU_OK(cudaEventRecord(c->sc->ev[5], s));
     CU_OK(cudaStreamSynchronize(s));
     hits.resize(nh);
     for (size_t i = 0; i < nh; i++) {
@@ -1271,10 +1377,10 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
       return a.frame != b2.frame ? a.frame < b2.frame : a.key < b2.key;
     });
     if (timing) {
-      cudaEventElapsedTime(&st.ms_h2d, c->ev_copy[kMaxChunks], c->ev_copy[R.host_chunks ? R.nchunks - 1 : 0]);
-      cudaEventElapsedTime(&st.ms_scan, c->ev[2], c->ev[3]);
-      cudaEventElapsedTime(&st.ms_cascade, c->ev[3], c->ev[4]);
-      cudaEventElapsedTime(&st.ms_d2h, c->ev[4], c->ev[5]);
+      cudaEventElapsedTime(&st.ms_h2d, c->sc->ev_copy[kMaxChunks], c->sc->ev_copy[R.host_chunks ? R.nchunks - 1 : 0]);
+      cudaEventElapsedTime(&st.ms_scan, c->sc->ev[2], c->sc->ev[3]);
+      cudaEventElapsedTime(&st.ms_cascade, c->sc->ev[3], c->sc->ev[4]);
+      cudaEventElapsedTime(&st.ms_d2h, c->sc->ev[4], c->sc->ev[5]);
     }
     return true;
   }
@@ -1447,12 +1553,12 @@ int detect_batch(Context *c, const unsigned char *frames, const jdaB200Batch &b,
   bool fin = true;
   if (flat) {
     fin = finish_flat(c, hits, b.n_frames, (b.flags & JDA_B200_RAW_HITS) != 0, flat);
-    c->last.detections = fin ? flat->total : 0;
+    c->sc->last.detections = fin ? flat->total : 0;
   } else {
-    c->last.detections = finish_frames(c, hits, b.n_frames, (b.flags & JDA_B200_RAW_HITS) != 0, results, nullptr);
+    c->sc->last.detections = finish_frames(c, hits, b.n_frames, (b.flags & JDA_B200_RAW_HITS) != 0, results, nullptr);
   }
-  c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (stats) *stats = c->last;
+  c->sc->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = c->sc->last;
   if (prev_dev >= 0) cudaSetDevice(prev_dev);
   return fin ? 0 : -1;
 }
@@ -1498,8 +1604,8 @@ int detect_mixed(Context *c, const jdaB200Frame *frames, int n, float scale, int
     }
     if (wc <= 0 || hc <= 0) {  // nothing but empty frames
       for (int f = 0; f < n; f++) results[f] = finish_frame(c->m, nullptr, 0, raw);
-      memset(&c->last, 0, sizeof c->last);
-      if (stats) *stats = c->last;
+      memset(&c->sc->last, 0, sizeof c->sc->last);
+      if (stats) *stats = c->sc->last;
       if (prev_dev >= 0) cudaSetDevice(prev_dev);
       return 0;
     }
@@ -1509,9 +1615,9 @@ int detect_mixed(Context *c, const jdaB200Frame *frames, int n, float scale, int
     b.max_size = user_max > 0 ? std::min(user_max, top) : top;
     if (!run_device(c, nullptr, b, hits, nullptr, stats != nullptr, frames)) return fail();
     const auto t0 = std::chrono::steady_clock::now();
-    c->last.detections = finish_frames(c, hits, n, raw, results, nullptr);
-    c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (stats) *stats = c->last;
+    c->sc->last.detections = finish_frames(c, hits, n, raw, results, nullptr);
+    c->sc->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = c->sc->last;
     if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return 0;
   }
@@ -1537,11 +1643,11 @@ int detect_mixed(Context *c, const jdaB200Frame *frames, int n, float scale, int
       return fail();
     }
     const auto t0 = std::chrono::steady_clock::now();
-    c->last.detections = finish_frames(c, hits, cnt, raw, results, g.second.data());
-    c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    add_stats(total, c->last);
+    c->sc->last.detections = finish_frames(c, hits, cnt, raw, results, g.second.data());
+    c->sc->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    add_stats(total, c->sc->last);
   }
-  c->last = total;
+  c->sc->last = total;
   if (stats) *stats = total;
   if (prev_dev >= 0) cudaSetDevice(prev_dev);
   return 0;
@@ -1556,7 +1662,7 @@ void *create(const char *path, bool dbl) {
     delete c;
     return nullptr;
   }
-  memset(&c->last, 0, sizeof c->last);
+  memset(&c->sc->last, 0, sizeof c->sc->last);
   c->path = path;
   c->path_dbl = dbl;
   return c;
@@ -1659,9 +1765,9 @@ int jdaB200JoinCascadorDetect(void *cascador, const unsigned char *frames, int n
     dets += results[f].n > 0 ? results[f].n : 0;
     i = j;
   }
-  c->last.detections = dets;
-  c->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (stats) *stats = c->last;
+  c->sc->last.detections = dets;
+  c->sc->last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = c->sc->last;
   if (prev_dev >= 0) cudaSetDevice(prev_dev);
   return 0;
 }
@@ -1682,7 +1788,7 @@ long long jdaB200JoinCascadorTrace(void *cascador, const unsigned char *frame, i
   std::vector<Hit64> hits;
   // pass both pointers: run_device64 traces when either is set
   if (!run_device64(c, frame, 1, width, height, *params, hits, carts_evaluated, exit_score, false)) return -1;
-  return c->last.windows;
+  return c->sc->last.windows;
 }
 
 int jdaB200JoinCascadorFilterMargins(void *cascador, double *margins, int cap) {
@@ -1697,6 +1803,98 @@ int jdaB200JoinCascadorFilterMargins(void *cascador, double *margins, int cap) {
 
 int jdaB200JoinCascadorLevels(int width, int height, int minimum_size, double scale, int *wins, int cap) {
   return enumerate_levels_f64(width, height, minimum_size, scale, wins, cap);
+}
+
+// ---- submit / collect: two batches in flight ----------------------------------------------------------------
+// While batch i is scanned, batch i + 1 is already being copied in; while batch i + 1 is scanned, the host sorts,
+// suppresses and relocates the hits of batch i.  Set t & 1 of the handle's two scratch sets serves ticket t.
+static bool same_geometry(const Context *c, const jdaB200Batch &b, bool latency) {
+  const Geometry &g = c->geo;
+  return g.valid && g.w == b.width && g.h == b.height && g.scale == b.scale && g.min_size == b.min_size &&
+         g.max_size == b.max_size && g.latency == latency;
+}
+
+static bool plan_is_latency(const Context *c, const jdaB200Batch &b) {
+  return c->tune.force_plan ? c->tune.force_plan == 1 : b.n_frames <= kLatencyFrames;
+}
+
+int jdaB200Submit(void *cascador, const unsigned char *frames, const jdaB200Batch *batch) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !batch || (!frames && batch->n_frames > 0)) {
+    set_err("null argument");
+    return -2;
+  }
+  std::lock_guard<std::mutex> lock(c->mu);
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  auto done = [&](int rc) { if (prev_dev >= 0) cudaSetDevice(prev_dev); return rc; };
+  if (!ctx_init(c)) return done(-1);
+  const int ticket = c->next_ticket;
+  Scratch &sl = c->slot[ticket & 1], &other = c->slot[(ticket & 1) ^ 1];
+  if (sl.busy) {
+    set_err("two batches are already in flight: jdaB200Collect ticket %d first", sl.ticket);
+    return done(-3);
+  }
+  if (!slot_init(sl)) return done(-1);
+  // the stage-0 tables belong to a geometry: a batch of another size or pyramid may only rebuild them once the
+  // batch that is still using them has finished
+  if (other.busy && !same_geometry(c, *batch, plan_is_latency(c, *batch))) cudaEventSynchronize(other.ev_done);
+  c->sc = &sl;
+  sl.batch = *batch;
+  sl.frames = frames;
+  if (!sl.run) sl.run = new Run();
+  Run &R = *sl.run;
+  if (!run_prepare(c, R, frames, sl.batch, nullptr, true, nullptr, true) || (!R.done && !run_enqueue(R))) {
+    c->sc = &c->slot[0];
+    return done(-1);
+  }
+  sl.busy = true;
+  sl.ticket = ticket;
+  c->next_ticket++;
+  c->sc = &c->slot[0];
+  return done(ticket);
+}
+
+int jdaB200Collect(void *cascador, int ticket, jdaB200FlatResult *result, jdaB200Stats *stats) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c || !result || ticket < 0) {
+    set_err("null argument");
+    return -2;
+  }
+  std::lock_guard<std::mutex> lock(c->mu);
+  Scratch &sl = c->slot[ticket & 1], &other = c->slot[(ticket & 1) ^ 1];
+  memset(result, 0, sizeof *result);
+  result->n_frames = -1; result->landmark_n = c->m.L;
+  if (!sl.busy || sl.ticket != ticket) {
+    set_err("ticket %d is not in flight", ticket);
+    return -3;
+  }
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  cudaSetDevice(c->device);
+  c->sc = &sl;
+  Run &R = *sl.run;
+  std::vector<HitRec> hits;
+  bool ok = true;
+  for (int attempt = 0; attempt < 4 && ok && !R.done; attempt++) {
+    bool overflow = false;
+    ok = run_finish(R, hits, overflow);
+    if (!ok || !overflow) break;
+    // a queue overflowed (the capacities have grown): the batch runs again from its frames -- which the caller keeps
+    // valid until the ticket is collected -- after the other batch in flight has let go of the shared tables
+    if (attempt == 3) { set_err("survivor / hit queues kept overflowing"); ok = false; break; }
+    if (other.busy) cudaEventSynchronize(other.ev_done);
+    ok = run_prepare(c, R, sl.frames, sl.batch, nullptr, true, nullptr, false) && (R.done || run_enqueue(R));
+  }
+  sl.busy = false;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (ok) ok = finish_flat(c, hits, sl.batch.n_frames, (sl.batch.flags & JDA_B200_RAW_HITS) != 0, result);
+  sl.last.detections = ok ? result->total : 0;
+  sl.last.ms_host = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = sl.last;
+  c->sc = &c->slot[0];
+  if (prev_dev >= 0) cudaSetDevice(prev_dev);
+  return ok ? 0 : -1;
 }
 
 int jdaB200DetectBatchFlat(void *cascador, const unsigned char *frames, const jdaB200Batch *batch,
@@ -1819,7 +2017,7 @@ long long jdaB200TraceK(void *cascador, const unsigned char *frame, int width, i
   t.n = carts_evaluated; t.s = exit_score; t.leaf = leaves; t.w0 = leaf_w0; t.w1 = leaf_w1;
   std::vector<HitRec> hits;
   if (!run_device(c, frame, b, hits, &t, false)) return -1;
-  return c->last.windows;
+  return c->sc->last.windows;
 }
 
 int jdaB200Resize(void *cascador, const unsigned char *src, int sw, int sh, unsigned char *dst, int dw, int dh) {

@@ -523,6 +523,52 @@ def test_mining_mode_cart_granular(casc, oracle, oracle_shipped, tk, n_frames):
         np.testing.assert_array_equal(lv, olv)
 
 
+def test_submit_collect_pipeline(casc):
+    """jdaB200Submit / jdaB200Collect: two batches in flight give the results of the synchronous call, whatever the
+    order of sizes and pyramids; overflowing queues are re-run at collect time; misuse is refused, not undefined."""
+    batches = [synth.make_frames("mix", 9, seed0=800), synth.make_frames("facemix", 7, 320, 240, seed0=810),
+               synth.make_frames("mix", 9, seed0=820), synth.make_frames("blur6", 3, seed0=830),
+               synth.make_frames("facemix", 140, 200, 150, seed0=840)]
+    kws = [dict(max_size=192, th=-0.5), dict(th=0.0), dict(max_size=192, th=-0.5), dict(scale=1.3, min_size=30, th=-1.0),
+           dict(th=-0.5)]
+    want = [casc.detect_batch(b, flat=True, **kw) for b, kw in zip(batches, kws)]
+    c = api.Cascador(SHIPPED_F32, double=False)
+    tickets = [c.submit(batches[0], **kws[0])]
+    got = []
+    for i in range(1, len(batches)):
+        tickets.append(c.submit(batches[i], **kws[i]))      # batch i goes in while batch i - 1 is still running
+        got.append(c.collect(tickets[i - 1]))
+        assert c.last_stats["windows"] > 0 and c.last_stats["scan_launches"] >= 1
+    got.append(c.collect(tickets[-1]))
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            np.testing.assert_array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+    # misuse
+    t0 = c.submit(batches[0], **kws[0])
+    t1 = c.submit(batches[2], **kws[2])
+    with pytest.raises(RuntimeError, match="already in flight"):
+        c.submit(batches[0], **kws[0])
+    with pytest.raises(RuntimeError, match="waiting for jdaB200Collect"):
+        c.detect(batches[0][0])
+    c.collect(t0); c.collect(t1)
+    with pytest.raises(RuntimeError, match="not in flight"):
+        c.collect(t1)
+    _same(c.detect(batches[0][0], max_size=192, th=-0.5), casc.detect(batches[0][0], max_size=192, th=-0.5))
+    c.close()
+    # queues that overflow: the batch is re-run when it is collected
+    os.environ["JDA_B200_TINY_QUEUES"] = "1"
+    try:
+        c2 = api.Cascador(SHIPPED_F32, double=False)
+    finally:
+        del os.environ["JDA_B200_TINY_QUEUES"]
+    ta = c2.submit(batches[0], **kws[0])
+    tb = c2.submit(batches[2], **kws[2])
+    for g, w in ((c2.collect(ta), want[0]), (c2.collect(tb), want[2])):
+        for a, b in zip(g, w):
+            np.testing.assert_array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+    c2.close()
+
+
 def test_concurrent_callers_and_changing_arguments(casc, oracle, oracle_shipped):
     """jdaDetect is re-entrant in the reference: threads share one handle; calls with different
     sizes / pyramids interleave (the per-handle geometry cache is rebuilt as needed)."""

@@ -35,7 +35,8 @@ if [ "${AB:-0}" = "1" ]; then
 source tools/ab.sh
 {
 run default
-run nw8 JDA_B200_NW=8
+run span12 JDA_B200_MAX_SPAN=12
+run span12_min64 JDA_B200_MAX_SPAN=12 JDA_B200_MIN_TILE_WINDOWS=64
 } > $O/${tag}_ab.txt 2>&1
 cat $O/${tag}_ab.txt
 fi
