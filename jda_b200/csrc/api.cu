@@ -332,7 +332,11 @@ bool ctx_init_impl(Context *c) {
             cudaSuccess && q == cudaDriverEntryPointSuccess)
       c->encode = (EncodeTiledFn)fn;
   }
-  const size_t s2 = k2_smem_bytes(std::min((c->m.K * kCartBytes + 127) & ~127, kMaxStage0TableBytes));  // larger K: no scan kernel
+  // Function attributes belong to the device context, not to a handle: every handle asks for the largest amount any
+  // model may need, so that a handle with a small model cannot lower the limit under a handle with a large one
+  // (r2: a K = 70 handle created between two calls of a K = 540 handle made the latter's scan launch fail).
+  constexpr int kMaxK = 4096;  // load_model's bound
+  const size_t s2 = k2_smem_bytes(kMaxStage0TableBytes);
   CU_OK(cudaFuncSetAttribute(k2_scan<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
@@ -341,10 +345,10 @@ bool ctx_init_impl(Context *c) {
   CU_OK(cudaFuncSetAttribute(k2_scan<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k2_scan<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
   CU_OK(cudaFuncSetAttribute(k3_stage0<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)k3s_smem_bytes(c->m.K, c->m.D())));
+                             (int)k3s_smem_bytes(kMaxK, kMaxDim)));
   CU_OK(cudaFuncSetAttribute(k3_stage0<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)k3s_smem_bytes(c->m.K, c->m.D())));
-  const size_t s3 = k3_smem_bytes(c->m.K);
+                             (int)k3s_smem_bytes(kMaxK, kMaxDim)));
+  const size_t s3 = k3_smem_bytes(kMaxK);
   CU_OK(cudaFuncSetAttribute(k3_cascade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   CU_OK(cudaFuncSetAttribute(k3_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   CU_OK(cudaFuncSetAttribute(k3_cascade<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
@@ -1207,7 +1211,7 @@ bool ensure_model64_impl(Context *c) {
   CU_OK(cudaMemcpy(c->d_w64, m.w.data(), m.w.size() * 8, cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(c->d_mean64, m.mean_shape.data(), m.mean_shape.size() * 8, cudaMemcpyHostToDevice));
   CU_OK(cudaFuncSetAttribute(k4_cascade_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(K4_WARPS * (kMaxDim * 8 + ((m.K + 15) & ~15)))));
+                             (int)(K4_WARPS * (kMaxDim * 8 + 4096))));  // largest K (see ctx_init: the attribute is per device)
   return true;
 }
 

@@ -331,8 +331,9 @@ __device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, i
     if (!__any_sync(0xffffffffu, any)) break;
     const uint32_t co = (uint32_t)k * kCartBytes;
     const uint2 n0 = *reinterpret_cast<const uint2 *>(smem + co);
-    const float cth = *reinterpret_cast<const float *>(smem + co + 88);
-    const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + co + 92);
+    const uint2 tf = *reinterpret_cast<const uint2 *>(smem + co + 88);  // cart threshold | norm-table index + 1: one load
+    const float cth = __uint_as_float(tf.x);
+    const uint32_t nflag = tf.y;
     int idx[NWG];
     float s[NWG];
 #pragma unroll
@@ -739,13 +740,19 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
 // the regression is a leaf-index gather: lane i sums row (8k + leaf_k) of w[t] into shape[i]
 // for k = 0..K-1 in ascending order -- 2L independent chains, each in the reference's order.
 
+#ifndef JDA_K3_MIN_BLOCKS
+#define JDA_K3_MIN_BLOCKS 1  /* blocks per SM the register allocation must allow (A/B: more warps against fewer registers) */
+#endif
+#ifndef JDA_K3_G
+#define JDA_K3_G 4
+#endif
 constexpr int K3_WARPS = 4;
-constexpr int K3_G = 4;  // chunks of 32 carts walked together per survivor
+constexpr int K3_G = JDA_K3_G;  // chunks of 32 carts walked together per survivor
 
 // D4 = true: depth-4 carts (7 nodes, 8 leaves) as compile-time constants -- the shipped model and the only depth the
 // reference's C path can load (c/jda.c:24-32).  D4 = false: depth 2..6 from the model header.
 template <bool TRACE, bool D4 = true>
-__global__ void __launch_bounds__(K3_WARPS * 32) k3_cascade(const __grid_constant__ CascadeParams P) {
+__global__ void __launch_bounds__(K3_WARPS * 32, JDA_K3_MIN_BLOCKS) k3_cascade(const __grid_constant__ CascadeParams P) {
   extern __shared__ __align__(16) uint8_t smem3[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = 2 * P.L;

@@ -322,6 +322,19 @@ def test_tree_depth_from_the_header(oracle, tmp_path, depth):
     c.close(); oracle.release(ho)
 
 
+def test_handles_with_different_models_do_not_disturb_each_other(casc, oracle, oracle_shipped, tmp_path):
+    """Kernel attributes (dynamic shared-memory limits) belong to the device, not to a handle: a handle with a small
+    model initialised between two calls of a handle with a large one must not lower the limit under it (r2 bug)."""
+    img = synth.face_canvas()
+    want = oracle.detect(oracle_shipped, img)
+    _same(casc.detect(img), want)
+    small = api.Cascador(synth.write_model(str(tmp_path / "small.model"), seed=3, T=2, K=40, L=6), double=True)
+    small.detect(synth.noise_frame(1, 64, 48))          # first use: this handle's ctx_init sets the attributes again
+    _same(casc.detect(img), want)
+    _same(casc.detect_batch(np.stack([img] * 6))[3], want)
+    small.close()
+
+
 def test_against_reference_library_directly(reflib, tmp_path):
     path = synth.write_model(str(tmp_path / "syn.model"), seed=21, mode="reject")
     c = api.Cascador(path, double=True)
