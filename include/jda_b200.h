@@ -168,7 +168,11 @@ JDA_API int jdaB200DetectMixed(void *cascador, const jdaB200Frame *frames, int n
  * round()ed pixel coordinates (data.cpp:18-58), no final score threshold, multimap NMS (cascador.cpp:387-429),
  * results in pick order.  Scope: models whose nodes are all at scale 0 and face.similarity_transform = false (the
  * shipped model and config.json); anything else is refused with an error.  A handle created from a float-flavour
- * file runs the exactly widened values. */
+ * file runs the exactly widened values.
+ * This is the DETERMINISTIC Validate: every window starts from mean_shape + 0, i.e. DataSet::RandomShape with
+ * shift_size = 0 as src/test.cpp:17,75 (test, fddb) force it.  src/live.cpp leaves config.json's random_shift = 0.02
+ * in place, a tick-count-seeded shift per window that no two runs of the reference share; that variant is not
+ * reproduced. */
 typedef struct {
   int n;
   int landmark_n;

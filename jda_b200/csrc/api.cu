@@ -953,7 +953,7 @@ bool launch_cascade(Run &R) {
     Q.trace_leaf = (R.trace->leaf && R.trace->w1 > R.trace->w0) ? c->d_trace_leaf.p : nullptr;
     Q.leaf_w0 = R.trace->w0; Q.leaf_w1 = R.trace->w1; Q.leaf_stride = R.leaf_stride;
   }
-  const int grid = c->sm_count * 8;
+  const int grid = c->sm_count * 16;  // survivors are handed out by an atomic counter: enough blocks to fill every SM
   const size_t smem = k3_smem_bytes(m.K);
   if (m.depth == kDepth) {
     if (R.tracing) k3_cascade<true><<<grid, K3_WARPS * 32, smem, R.s>>>(Q);

@@ -741,10 +741,11 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
 // for k = 0..K-1 in ascending order -- 2L independent chains, each in the reference's order.
 
 #ifndef JDA_K3_MIN_BLOCKS
-#define JDA_K3_MIN_BLOCKS 1  /* blocks per SM the register allocation must allow (A/B: more warps against fewer registers) */
+#define JDA_K3_MIN_BLOCKS 8  /* blocks per SM the register allocation must allow: the kernel waits on L2, so warps in flight
+                                count for more than registers (r2k A/B: 1 block / 4 chunks 3.55 ms, 8 / 2 chunks 2.93 ms) */
 #endif
 #ifndef JDA_K3_G
-#define JDA_K3_G 4
+#define JDA_K3_G 2
 #endif
 constexpr int K3_WARPS = 4;
 constexpr int K3_G = JDA_K3_G;  // chunks of 32 carts walked together per survivor

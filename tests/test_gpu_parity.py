@@ -634,14 +634,37 @@ def test_full_size_batch_properties(casc, oracle, oracle_shipped):
     for i, p in enumerate(perm):
         _same(c[i], a[p])
     s0 = 0
-    for f in (0, 1, 2, 50):
-        _same(a[f], oracle.detect(oracle_shipped, frames[f], max_size=192, th=0.0))
+    # every one of the 96 frames against the oracle (the restatement releases the GIL inside ctypes: host threads)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
+        want = list(ex.map(lambda f: oracle.detect(oracle_shipped, frames[f], max_size=192, th=0.0), range(96)))
+    for f in range(96):
+        _same(a[f], want[f])
+    assert sum(len(w[1]) for w in want) > 20
     raw = casc.detect_batch(frames[:4], max_size=192, flags=api.RAW_HITS | api.NO_FINAL_TH)
     for f in range(4):
         ob, osc, osh, ost = oracle.detect_raw(oracle_shipped, frames[f], max_size=192, use_th=False)
         _same(raw[f], (ob, osc, osh))
         s0 += ost["stage_survivors"][0]
     assert casc.last_stats["stage0_survivors"] == s0
+
+
+def test_1080p_five_octave_frames(casc, oracle, oracle_shipped):
+    """BASELINE config 3 (1920x1080, min 24, max 768: 16 levels, 1,245,202 windows per frame) through plain jdaDetect:
+    four frames of three kinds against the oracle, beside the golden reference output of `hd_blur`"""
+    from concurrent.futures import ThreadPoolExecutor
+    frames = [synth.facemix_frame(7000, 1920, 1080), synth.facemix_frame(7001, 1920, 1080), synth.blur_frame(7002, 1920, 1080),
+              np.kron(synth.face_canvas(), np.ones((2, 2), np.uint8))[:1080, :1920].copy()]
+    kw = dict(scale=1.25, min_size=24, max_size=768, th=0.0)
+    assert api.count_windows(1920, 1080, 1.25, 24, 768) == 1245202
+    with ThreadPoolExecutor(4) as ex:
+        want = list(ex.map(lambda f: oracle.detect(oracle_shipped, f, **kw), frames))
+    for f, w in zip(frames, want):
+        _same(casc.detect(f, **kw), w)
+    assert sum(len(w[1]) for w in want) >= 3
+    got = casc.detect_batch(np.stack(frames + frames[:2]), **kw)          # and as a batch (throughput tile plan)
+    for g, w in zip(got, want + want[:2]):
+        _same(g, w)
 
 
 def test_cli_detect_fddb_format(tmp_path, oracle, oracle_shipped):

@@ -35,8 +35,8 @@ if [ "${AB:-0}" = "1" ]; then
 source tools/ab.sh
 {
 run default
-run span12 JDA_B200_MAX_SPAN=12
-run span12_min64 JDA_B200_MAX_SPAN=12 JDA_B200_MIN_TILE_WINDOWS=64
+run k3g1b8 JDA_B200_LIB=libjda_b200_k3g1b8.so
+run k3g2b12 JDA_B200_LIB=libjda_b200_k3g2b12.so
 } > $O/${tag}_ab.txt 2>&1
 cat $O/${tag}_ab.txt
 fi
