@@ -653,8 +653,9 @@ def test_1080p_five_octave_frames(casc, oracle, oracle_shipped):
     """BASELINE config 3 (1920x1080, min 24, max 768: 16 levels, 1,245,202 windows per frame) through plain jdaDetect:
     four frames of three kinds against the oracle, beside the golden reference output of `hd_blur`"""
     from concurrent.futures import ThreadPoolExecutor
-    frames = [synth.facemix_frame(7000, 1920, 1080), synth.facemix_frame(7001, 1920, 1080), synth.blur_frame(7002, 1920, 1080),
-              np.kron(synth.face_canvas(), np.ones((2, 2), np.uint8))[:1080, :1920].copy()]
+    big = np.full((1080, 1920), 100, np.uint8)                         # flat background, the known-answer canvas at 2x
+    big[60:60 + 960, 300:300 + 1280] = np.kron(synth.face_canvas(), np.ones((2, 2), np.uint8))
+    frames = [synth.facemix_frame(7000, 1920, 1080), synth.facemix_frame(7001, 1920, 1080), synth.blur_frame(7002, 1920, 1080), big]
     kw = dict(scale=1.25, min_size=24, max_size=768, th=0.0)
     assert api.count_windows(1920, 1080, 1.25, 24, 768) == 1245202
     with ThreadPoolExecutor(4) as ex:
