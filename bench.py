@@ -495,27 +495,38 @@ def main():
         last = {"table": None, "n_local": 0}
 
         def run5(n_frames, from_host):
+            """the rank's frames in batches of B, two batches in flight (jdaB200Submit / jdaB200Collect)"""
             tot = {k: 0 for k in keys}
+            inflight = []       # (ticket, first frame of the batch)
+
+            def collect_one():
+                t, f0 = inflight.pop(0)
+                res = c.collect(t)
+                for k in keys:
+                    tot[k] += c.last_stats[k]
+                last["n_local"] = len(res[2])
+                if dist_on:
+                    if exchange["fut"] is not None:
+                        last["table"] = exchange["fut"].result()
+                    exchange["fut"] = exchange["pool"].submit(_exchange5, res, lo + f0)
+                else:
+                    last["table"] = shard.pack_records_flat(*res, frame0=lo + f0)
+
             f = 0
             bi = 0
             while f < n_frames:
                 nb = min(B, n_frames - f)
                 if from_host:
-                    res = c.detect_batch(host5[bi & 1].numpy()[:nb], flat=True, **mine_kw)
+                    t = c.submit(host5[bi & 1].numpy()[:nb], **mine_kw)
                 else:
-                    res = c.detect_batch(None, device_ptr=dev5[bi & 1].data_ptr(), shape=(nb, H, W), flat=True, **mine_kw)
-                for k in keys:
-                    tot[k] += c.last_stats[k]
-                if dist_on:
-                    if exchange["fut"] is not None:
-                        last["table"] = exchange["fut"].result()
-                    last["n_local"] = len(res[2])
-                    exchange["fut"] = exchange["pool"].submit(_exchange5, res, lo + f)
-                else:
-                    last["table"] = shard.pack_records_flat(*res, frame0=lo + f)
-                    last["n_local"] = len(res[2])
+                    t = c.submit(None, device_ptr=dev5[bi & 1].data_ptr(), shape=(nb, H, W), **mine_kw)
+                inflight.append((t, f))
+                if len(inflight) == 2:
+                    collect_one()
                 f += nb
                 bi += 1
+            while inflight:
+                collect_one()
             return tot
 
         def _exchange5(res, frame0):
@@ -719,6 +730,9 @@ def main():
             lat.append((time.perf_counter() - t0) * 1e3)
         ex["cfg3_1080p_5oct_jdaDetect_ms"] = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                                               "windows_per_frame": 1245202}
+        if not a.no_cpu_baseline:   # the reference's own jdaDetect on the same frames, one host thread per frame
+            dt, kind = cpu_frames_run(hd, min(4, os.cpu_count() or 1), dict(scale=1.25, min_size=24, max_size=768, th=0.0))
+            ex["cfg3_1080p_5oct_jdaDetect_ms"]["cpu_%s_ms_per_frame" % kind] = dt * 1e3 / len(hd) * min(4, os.cpu_count() or 1)
         vga = synth.noise_frame(1)
         for i in range(10):
             c.detect(vga, 1.25, 0.1, 24, 192, 0.0)

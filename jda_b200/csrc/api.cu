@@ -242,7 +242,7 @@ int chunk_begin(int n_frames, int ch, int nchunks, bool even = false) {
 
 size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size_t)K2_WARPS * K2_WARP_BYTES; }
 size_t k3s_smem_bytes(int K, int D) {
-  return (size_t)K3S_COHORT * ((K + 15) & ~15) + (size_t)2 * K3S_CHUNK * kLeaves * D * 4;
+  return (size_t)K3S_COHORT * leaf_bytes(K) + (size_t)2 * K3S_CHUNK * kLeaves * D * 4;
 }
 size_t k3_smem_bytes(int K) { return (size_t)K3_WARPS * (kMaxDim * 4 + ((K + 15) & ~15)); }
 
@@ -1075,7 +1075,7 @@ bool run_prepare(Context *c, Run &R, const unsigned char *frames, const jdaB200B
   }
   R.scan_K = R.t_run == 0 ? R.k_extra : m.K;
   R.leaf_stride = m.T * m.K;
-  R.leaf_pad = (m.K + 15) & ~15;
+  R.leaf_pad = leaf_bytes(m.K);
   R.total_windows = st.windows;
   R.use_scan = m.stage0_lut_ok && !(b.flags & JDA_B200_NO_STAGE0_SCAN);
   if (mixed && (!R.use_scan || m.any_scaled)) {
@@ -1306,7 +1306,7 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
   const bool tracing = trace_n || trace_s;
   R.s = c->stream();
   R.D = m.D();
-  R.leaf_pad = (m.K + 15) & ~15;
+  R.leaf_pad = leaf_bytes(m.K);
   R.scan_K = m.K;  // (R.t_run stays 0: the prefilter's survivors are re-evaluated from cart 0, no leaf records needed)
   R.total_windows = st.windows;
   R.use_scan = c->filter64_ok && !(prm.flags & JDA_B200_NO_STAGE0_SCAN) && !tracing;

@@ -76,7 +76,7 @@ struct ScanParams {
   uint4 *surv;                   // stage-0 survivors: {frame, level<<26 | yi<<13 | xi, score bits, 0}
   unsigned *surv_count;
   unsigned surv_cap;
-  uint8_t *surv_leaves;          // [surv_cap][leaf_pad]: the K stage-0 leaf indices of every survivor
+  uint8_t *surv_leaves;          // [surv_cap][leaf_pad]: the K stage-0 leaf indices of every survivor, two per byte
   int leaf_pad;
   long long windows_per_frame;
   int n_sched;
@@ -400,6 +400,9 @@ __device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, i
 // sequential adds / compares as the reference, so reject cart and score bits are unchanged.  A tail
 // that would take hundreds of nearly empty warp iterations becomes a few dense chunk steps.
 // On return the list holds the windows that passed every cart; n is updated.
+#ifndef JDA_K2_STRAGGLER_V2
+#define JDA_K2_STRAGGLER_V2 1  /* two windows per walk step + score walk eight carts per loop step (0: round-1 loop, for A/B) */
+#endif
 constexpr int K2_STRAGGLERS = 15;
 constexpr int K2_LS_STRIDE = 33;  // conflict-free both for the lane = cart writes and lane = window reads
 static_assert(K2_STRAGGLERS * K2_LS_STRIDE <= K2_LIST_CAP, "leaf-score scratch reuses the score list");
@@ -422,6 +425,86 @@ __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int car
     const int k = min(k0 + lane, K - 1);
     const uint32_t co = (uint32_t)k * kCartBytes;
     const uint2 n0 = *reinterpret_cast<const uint2 *>(smem + co);
+#if JDA_K2_STRAGGLER_V2
+    // two windows per step of the walk: the tree walk is a chain of dependent shared-memory reads
+    for (unsigned rest = live; rest;) {
+      const int w0 = __ffs(rest) - 1;
+      rest &= rest - 1;
+      const int w1 = rest ? __ffs(rest) - 1 : w0;  // odd count: the last window walks twice (same values, same slots)
+      rest &= rest - 1;
+      const PixBase<SMEM> pa = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, w0), true);
+      const PixBase<SMEM> pb = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, w1), true);
+      int ia = node_test<SMEM>(smem, n0, pa, c.pitch), ib = node_test<SMEM>(smem, n0, pb, c.pitch);
+      uint2 na = *reinterpret_cast<const uint2 *>(smem + co + ia * 8), nb = *reinterpret_cast<const uint2 *>(smem + co + ib * 8);
+      ia = 2 * ia + node_test<SMEM>(smem, na, pa, c.pitch);
+      ib = 2 * ib + node_test<SMEM>(smem, nb, pb, c.pitch);
+      na = *reinterpret_cast<const uint2 *>(smem + co + ia * 8);
+      nb = *reinterpret_cast<const uint2 *>(smem + co + ib * 8);
+      ia = 2 * ia + node_test<SMEM>(smem, na, pa, c.pitch) - kNodes;
+      ib = 2 * ib + node_test<SMEM>(smem, nb, pb, c.pitch) - kNodes;
+      ls[w0 * K2_LS_STRIDE + lane] = *reinterpret_cast<const float *>(smem + co + 56 + 4 * ia);
+      ls[w1 * K2_LS_STRIDE + lane] = *reinterpret_cast<const float *>(smem + co + 56 + 4 * ib);
+      if constexpr (TRACE) { lf[w0] = (uint8_t)ia; lf[w1] = (uint8_t)ib; }
+    }
+    __syncwarp();
+    const int cnt = min(32, K - k0);
+    [[maybe_unused]] int died_at = alive ? cnt : -1;  // chunk-local cart after which this lane's window stopped
+    // the score walk, eight carts per step of the loop: their leaf scores and thresholds are fetched together, only
+    // the adds and compares form a chain (c/jda.c:395-401, same order)
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+      float v[8], th8[8];
+      uint32_t nf = 0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint2 tf = *reinterpret_cast<const uint2 *>(smem + (uint32_t)min(k0 + j0 + u, K - 1) * kCartBytes + 88);
+        th8[u] = __uint_as_float(tf.x);
+        nf |= tf.y;
+        v[u] = ls[lrow + j0 + u];  // lanes past the stragglers re-read row 0 (in bounds)
+      }
+      if (nf == 0u) {  // (uniform) no cart of the eight has a real (mean, std)
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (j0 + u < cnt) {
+            const float s = __fadd_rn(score, v[u]);
+            if (alive) {
+              score = s;
+              if (s < th8[u]) {  // c/jda.c:399
+                alive = false;
+                if constexpr (TRACE) {
+                  died_at = j0 + u;
+                  const long long gw = trace_index(c, wid);
+                  if (P.trace_n) P.trace_n[gw] = k0 + j0 + u + 1;
+                  if (P.trace_s) P.trace_s[gw] = s;
+                }
+              }
+            }
+          }
+        }
+      } else {
+        for (int u = 0; u < 8 && j0 + u < cnt; u++) {
+          const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + (uint32_t)(k0 + j0 + u) * kCartBytes + 92);
+          float s = __fadd_rn(score, v[u]);
+          if (nflag) {
+            const Stage0Norm nm = c.norms[nflag - 1];
+            s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
+          }
+          if (alive) {
+            score = s;
+            if (s < th8[u]) {
+              alive = false;
+              if constexpr (TRACE) {
+                died_at = j0 + u;
+                const long long gw = trace_index(c, wid);
+                if (P.trace_n) P.trace_n[gw] = k0 + j0 + u + 1;
+                if (P.trace_s) P.trace_s[gw] = s;
+              }
+            }
+          }
+        }
+      }
+      if (!__any_sync(0xffffffffu, alive)) break;
+    }
+#else
     for (unsigned rest = live; rest; rest &= rest - 1) {
       const int w = __ffs(rest) - 1;
       const PixBase<SMEM> pb = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, w), true);
@@ -460,6 +543,7 @@ __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int car
       }
       if (!__any_sync(0xffffffffu, alive)) break;
     }
+#endif
     if constexpr (TRACE) {
       // leaves of the carts the reference would have evaluated: up to and including the rejecting one
       if (P.trace_leaf) {
@@ -574,7 +658,10 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
         int idx = node_test<SMEM>(smem, *reinterpret_cast<const uint2 *>(smem + co), pb, c.pitch);
         idx = 2 * idx + node_test<SMEM>(smem, *reinterpret_cast<const uint2 *>(smem + co + idx * 8), pb, c.pitch);
         idx = 2 * idx + node_test<SMEM>(smem, *reinterpret_cast<const uint2 *>(smem + co + idx * 8), pb, c.pitch);
-        if (k0 + lane < P.K) out[k0 + lane] = (uint8_t)(idx - kNodes);
+        // two 3-bit leaves per byte (cart k in the low nibble of byte k / 2): half the bytes of round 1's records
+        const int lf = (k0 + lane < P.K) ? idx - kNodes : 0;
+        const int hi = __shfl_down_sync(0xffffffffu, lf, 1);
+        if (!(lane & 1) && k0 + lane < P.K) out[(k0 + lane) >> 1] = (uint8_t)(lf | (hi << 4));
       }
     }
   }
@@ -978,9 +1065,11 @@ constexpr int K3S_PER_WARP = 4;
 constexpr int K3S_COHORT = K3S_WARPS * K3S_PER_WARP;
 constexpr int K3S_CHUNK = 4;  // carts staged per step (6.9 KB x 2 buffers: the block fits on an SM next to a scan block)
 static_assert(K3S_CHUNK % 4 == 0, "leaf indices are fetched four at a time");
+// bytes of one survivor's stage-0 leaf record: two leaves per byte, padded to 16
+__host__ __device__ constexpr int leaf_bytes(int K) { return (((K + 1) >> 1) + 15) & ~15; }
 
 struct Stage0Params {
-  const uint8_t *surv_leaves;    // [surv_cap][(K + 15) & ~15] leaf indices written by k2_scan
+  const uint8_t *surv_leaves;    // [surv_cap][leaf_bytes(K)] leaf indices written by k2_scan, two per byte
   const float *w0;               // w[0]: [8K][2L]
   const float *mean_shape;
   int K, L;
@@ -1000,7 +1089,7 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
   extern __shared__ __align__(16) uint8_t smem0[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = 2 * P.L, K = P.K;
-  const int kpad = (K + 15) & ~15;
+  const int kpad = leaf_bytes(K);
   const int chunk_floats = K3S_CHUNK * kLeaves * D;
   uint8_t *leaves = smem0;                                                   // [cohort][kpad]
   float *rows = reinterpret_cast<float *>(smem0 + (size_t)K3S_COHORT * kpad);  // [2][chunk_floats]
@@ -1049,15 +1138,15 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
 #pragma unroll
       for (int s = 0; s < K3S_PER_WARP; s++) {
         if (c0 + warp * K3S_PER_WARP + s >= total) continue;  // no survivor in this seat: its leaves are stale
-        // the chunk's leaf indices of this survivor, four per 32-bit load (kpad and k0 are multiples of 4)
-        const uint32_t *lp = reinterpret_cast<const uint32_t *>(leaves + (warp * K3S_PER_WARP + s) * kpad + k0);
+        // the chunk's leaf indices of this survivor, four per 16-bit load (two per byte; k0 is a multiple of 4)
+        const uint16_t *lp = reinterpret_cast<const uint16_t *>(leaves + (warp * K3S_PER_WARP + s) * kpad + (k0 >> 1));
         uint32_t lq[K3S_CHUNK / 4];
 #pragma unroll
         for (int q = 0; q < K3S_CHUNK / 4; q++) lq[q] = lp[q];
 #pragma unroll
         for (int cl = 0; cl < K3S_CHUNK; cl++) {
           if (cl < carts) {
-            const uint32_t leaf = (lq[cl >> 2] >> (8 * (cl & 3))) & 0xffu;
+            const uint32_t leaf = (lq[cl >> 2] >> (4 * (cl & 3))) & 0xfu;
             const float2 *row = reinterpret_cast<const float2 *>(rb + (cl * kLeaves + leaf) * D);
 #pragma unroll
             for (int h = 0; h < HALVES; h++) {

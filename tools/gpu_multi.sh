@@ -2,6 +2,7 @@
 # Multi-GPU measurements on ONE box (run under `gpurun --gpus 8`): the 2-GPU NCCL parity test, then config 4 and
 # config 5 at 1 / 2 / 4 / 8 ranks and the headline workload at 8.  One JSON line per run in gpurun_out/<tag>_<workload>_n<N>.json.
 tag=${1:-multi}
+maxn=${2:-8}   # GPUs on the box
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=index,name,clocks.sm --format=csv > $O/${tag}_gpus.txt 2>&1
@@ -26,7 +27,7 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-for n in 1 2 4 8; do run cfg4 $n --steps 3 --warmup 3; done
-for n in 8 4 2 1; do run cfg5 $n --steps 1 --warmup 3; done
-run vga 8 --steps 10 --warmup 3 --no-breakdown
-run vga 2 --steps 10 --warmup 3 --no-breakdown
+for n in 1 2 4 8; do [ $n -le $maxn ] && run cfg4 $n --steps 3 --warmup 3; done
+for n in 8 4 2 1; do [ $n -le $maxn ] && run cfg5 $n --steps 1 --warmup 3; done
+run vga $maxn --steps 10 --warmup 3 --no-breakdown
+[ $maxn -gt 2 ] && run vga 2 --steps 10 --warmup 3 --no-breakdown
