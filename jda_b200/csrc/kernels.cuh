@@ -393,82 +393,122 @@ __device__ __forceinline__ void scan_group(const TileCtx &c, int ph, int base, i
   }
 }
 
-// Straggler mode.  Once a tile is down to n <= K2_STRAGGLERS windows the parallel axis flips: for
-// each remaining window the 32 lanes walk 32 CONSECUTIVE CARTS (the shape is the constant mean
-// shape in stage 0, so the carts of a window are independent), park the 32 leaf scores in shared
-// memory, and then the running scores are replayed cart by cart with lane = window -- the same
-// sequential adds / compares as the reference, so reject cart and score bits are unchanged.  A tail
-// that would take hundreds of nearly empty warp iterations becomes a few dense chunk steps.
-// On return the list holds the windows that passed every cart; n is updated.
-#ifndef JDA_K2_STRAGGLER_V2
-#define JDA_K2_STRAGGLER_V2 1  /* two windows per walk step + score walk eight carts per loop step (0: round-1 loop, for A/B) */
+// Straggler mode.  Once a tile is down to n <= K2_STRAG_MAX windows the parallel axis flips: for each remaining window
+// the 32 lanes walk 32 CONSECUTIVE CARTS (the shape is the constant mean shape in stage 0, so the carts of a window are
+// independent), park the 32 leaf scores in shared memory, and then the running scores are replayed cart by cart with
+// lane = window -- the same sequential adds / compares as the reference, so reject cart and score bits are unchanged.
+// A short list keeps a window-parallel warp waiting on one chain of dependent shared-memory reads per cart with most
+// lanes idle; here every lane works and the chains of several windows overlap.  Round 2 measurements (512 mix frames):
+// threshold 8 -> 24.6 ms, 15 -> 23.2, 23 -> 22.55, 32 -> 22.50, 48 -> 22.67, 64 -> 23.19 (profiles/r2p_ab.txt, r2q_ab.txt), hence batches: the list may be longer than the
+// leaf-score scratch has rows and is walked chunk by chunk (32 carts), K2_STRAG_ROWS windows at a time, survivors
+// compacted in place.  On return the list holds the windows that passed every cart; n is updated.
+#ifndef JDA_K2_STRAG_MAX
+#define JDA_K2_STRAG_MAX 32
 #endif
-constexpr int K2_STRAGGLERS = 15;
-constexpr int K2_LS_STRIDE = 33;  // conflict-free both for the lane = cart writes and lane = window reads
-static_assert(K2_STRAGGLERS * K2_LS_STRIDE <= K2_LIST_CAP, "leaf-score scratch reuses the score list");
+constexpr int K2_STRAG_MAX = JDA_K2_STRAG_MAX;  // <= 64: the moved list (below) has 64 slots
+constexpr int K2_STRAG_ROWS = 20;               // windows per batch = rows of leaf scores
+constexpr int K2_LS_STRIDE = 33;                // conflict-free both for the lane = cart writes and lane = window reads
+// scratch = the tile's own lists, WarpLists::lscore[512] followed by ::lwid[512], viewed as 768 floats:
+//   [0, 660) leaf scores [row][33]   [672, 736) scores of the list   [736, 768) window ids of the list (64 x u16)
+static_assert(K2_STRAG_ROWS * K2_LS_STRIDE <= 672 && K2_STRAG_MAX <= 64 && K2_LIST_CAP == 512, "straggler scratch layout");
 
 template <bool SMEM, bool TRACE>
 __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int cart) {
   const ScanParams &P = *c.P;
   const uint8_t *smem = c.smem;
   const int lane = c.lane, K = P.K;
-  bool alive = lane < n;
-  const int wid = alive ? (int)c.lwid[lane] : 0;
-  float score = alive ? c.lscore[lane] : 0.f;
-  __syncwarp();  // the score list is reused as ls[window][cart] from here on
   float *ls = c.lscore;
-  const int lrow = (lane < K2_STRAGGLERS ? lane : 0) * K2_LS_STRIDE;
-  [[maybe_unused]] uint8_t lf[K2_STRAGGLERS];
-  for (int k0 = cart; k0 < K; k0 += 32) {
-    unsigned live = __ballot_sync(0xffffffffu, alive);
-    if (!live) break;
+  float *sc = c.lscore + 672;
+  uint16_t *wd = reinterpret_cast<uint16_t *>(c.lscore + 736);
+  {  // move the list (<= 64 entries at the front of lscore / lwid) out of the leaf-score rows' way
+    const bool v0 = lane < n, v1 = lane + 32 < n;
+    const int a0 = v0 ? (int)c.lwid[lane] : 0, a1 = v1 ? (int)c.lwid[lane + 32] : 0;
+    const float s0 = v0 ? c.lscore[lane] : 0.f, s1 = v1 ? c.lscore[lane + 32] : 0.f;
+    __syncwarp();
+    if (v0) { wd[lane] = (uint16_t)a0; sc[lane] = s0; }
+    if (v1) { wd[lane + 32] = (uint16_t)a1; sc[lane + 32] = s1; }
+    __syncwarp();
+  }
+  const int lrow = min(lane, K2_STRAG_ROWS - 1) * K2_LS_STRIDE;
+  for (int k0 = cart; k0 < K && n > 0; k0 += 32) {
     const int k = min(k0 + lane, K - 1);
     const uint32_t co = (uint32_t)k * kCartBytes;
     const uint2 n0 = *reinterpret_cast<const uint2 *>(smem + co);
-#if JDA_K2_STRAGGLER_V2
-    // two windows per step of the walk: the tree walk is a chain of dependent shared-memory reads
-    for (unsigned rest = live; rest;) {
-      const int w0 = __ffs(rest) - 1;
-      rest &= rest - 1;
-      const int w1 = rest ? __ffs(rest) - 1 : w0;  // odd count: the last window walks twice (same values, same slots)
-      rest &= rest - 1;
-      const PixBase<SMEM> pa = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, w0), true);
-      const PixBase<SMEM> pb = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, w1), true);
-      int ia = node_test<SMEM>(smem, n0, pa, c.pitch), ib = node_test<SMEM>(smem, n0, pb, c.pitch);
-      uint2 na = *reinterpret_cast<const uint2 *>(smem + co + ia * 8), nb = *reinterpret_cast<const uint2 *>(smem + co + ib * 8);
-      ia = 2 * ia + node_test<SMEM>(smem, na, pa, c.pitch);
-      ib = 2 * ib + node_test<SMEM>(smem, nb, pb, c.pitch);
-      na = *reinterpret_cast<const uint2 *>(smem + co + ia * 8);
-      nb = *reinterpret_cast<const uint2 *>(smem + co + ib * 8);
-      ia = 2 * ia + node_test<SMEM>(smem, na, pa, c.pitch) - kNodes;
-      ib = 2 * ib + node_test<SMEM>(smem, nb, pb, c.pitch) - kNodes;
-      ls[w0 * K2_LS_STRIDE + lane] = *reinterpret_cast<const float *>(smem + co + 56 + 4 * ia);
-      ls[w1 * K2_LS_STRIDE + lane] = *reinterpret_cast<const float *>(smem + co + 56 + 4 * ib);
-      if constexpr (TRACE) { lf[w0] = (uint8_t)ia; lf[w1] = (uint8_t)ib; }
-    }
-    __syncwarp();
     const int cnt = min(32, K - k0);
-    [[maybe_unused]] int died_at = alive ? cnt : -1;  // chunk-local cart after which this lane's window stopped
-    // the score walk, eight carts per step of the loop: their leaf scores and thresholds are fetched together, only
-    // the adds and compares form a chain (c/jda.c:395-401, same order)
-    for (int j0 = 0; j0 < cnt; j0 += 8) {
-      float v[8], th8[8];
-      uint32_t nf = 0;
+    int out = 0;
+    for (int b0 = 0; b0 < n; b0 += K2_STRAG_ROWS) {
+      const int nb = min(K2_STRAG_ROWS, n - b0);
+      bool alive = lane < nb;
+      const int wid = alive ? (int)wd[b0 + lane] : 0;
+      float score = alive ? sc[b0 + lane] : 0.f;
+      [[maybe_unused]] uint8_t lf[K2_STRAG_ROWS];
+      // two windows per step of the walk: the tree walk is a chain of dependent shared-memory reads
+      for (int w = 0; w < nb; w += 2) {
+        const int wb = min(w + 1, nb - 1);  // odd count: the last window walks twice (same values, same slots)
+        const PixBase<SMEM> pa = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, w), true);
+        const PixBase<SMEM> pb = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, wb), true);
+        int ia = node_test<SMEM>(smem, n0, pa, c.pitch), ib = node_test<SMEM>(smem, n0, pb, c.pitch);
+        uint2 na = *reinterpret_cast<const uint2 *>(smem + co + ia * 8), nb2 = *reinterpret_cast<const uint2 *>(smem + co + ib * 8);
+        ia = 2 * ia + node_test<SMEM>(smem, na, pa, c.pitch);
+        ib = 2 * ib + node_test<SMEM>(smem, nb2, pb, c.pitch);
+        na = *reinterpret_cast<const uint2 *>(smem + co + ia * 8);
+        nb2 = *reinterpret_cast<const uint2 *>(smem + co + ib * 8);
+        ia = 2 * ia + node_test<SMEM>(smem, na, pa, c.pitch) - kNodes;
+        ib = 2 * ib + node_test<SMEM>(smem, nb2, pb, c.pitch) - kNodes;
+        ls[w * K2_LS_STRIDE + lane] = *reinterpret_cast<const float *>(smem + co + 56 + 4 * ia);
+        ls[wb * K2_LS_STRIDE + lane] = *reinterpret_cast<const float *>(smem + co + 56 + 4 * ib);
+        if constexpr (TRACE) {
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const uint2 tf = *reinterpret_cast<const uint2 *>(smem + (uint32_t)min(k0 + j0 + u, K - 1) * kCartBytes + 88);
-        th8[u] = __uint_as_float(tf.x);
-        nf |= tf.y;
-        v[u] = ls[lrow + j0 + u];  // lanes past the stragglers re-read row 0 (in bounds)
+          for (int q = 0; q < K2_STRAG_ROWS; q++) {
+            if (q == w) lf[q] = (uint8_t)ia;
+            if (q == wb) lf[q] = (uint8_t)ib;
+          }
+        }
       }
-      if (nf == 0u) {  // (uniform) no cart of the eight has a real (mean, std)
+      __syncwarp();
+      [[maybe_unused]] int died_at = alive ? cnt : -1;  // chunk-local cart after which this lane's window stopped
+      // the score walk, eight carts per step of the loop: their leaf scores and thresholds are fetched together, only
+      // the adds and compares form a chain (c/jda.c:395-401, same order)
+      for (int j0 = 0; j0 < cnt; j0 += 8) {
+        float v[8], th8[8];
+        uint32_t nf = 0;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          if (j0 + u < cnt) {
-            const float s = __fadd_rn(score, v[u]);
+          const uint2 tf = *reinterpret_cast<const uint2 *>(smem + (uint32_t)min(k0 + j0 + u, K - 1) * kCartBytes + 88);
+          th8[u] = __uint_as_float(tf.x);
+          nf |= tf.y;
+          v[u] = ls[lrow + j0 + u];  // lanes past the batch re-read its last row (in bounds)
+        }
+        if (nf == 0u) {  // (uniform) no cart of the eight has a real (mean, std)
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            if (j0 + u < cnt) {
+              const float s = __fadd_rn(score, v[u]);
+              if (alive) {
+                score = s;
+                if (s < th8[u]) {  // c/jda.c:399
+                  alive = false;
+                  if constexpr (TRACE) {
+                    died_at = j0 + u;
+                    const long long gw = trace_index(c, wid);
+                    if (P.trace_n) P.trace_n[gw] = k0 + j0 + u + 1;
+                    if (P.trace_s) P.trace_s[gw] = s;
+                  }
+                }
+              }
+            }
+          }
+        } else {
+          for (int u = 0; u < 8 && j0 + u < cnt; u++) {
+            const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + (uint32_t)(k0 + j0 + u) * kCartBytes + 92);
+            float s = __fadd_rn(score, v[u]);
+            if (nflag) {
+              const Stage0Norm nm = c.norms[nflag - 1];
+              s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
+            }
             if (alive) {
               score = s;
-              if (s < th8[u]) {  // c/jda.c:399
+              if (s < th8[u]) {
                 alive = false;
                 if constexpr (TRACE) {
                   died_at = j0 + u;
@@ -480,93 +520,43 @@ __device__ __forceinline__ void straggler_tail(const TileCtx &c, int &n, int car
             }
           }
         }
-      } else {
-        for (int u = 0; u < 8 && j0 + u < cnt; u++) {
-          const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + (uint32_t)(k0 + j0 + u) * kCartBytes + 92);
-          float s = __fadd_rn(score, v[u]);
-          if (nflag) {
-            const Stage0Norm nm = c.norms[nflag - 1];
-            s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
-          }
-          if (alive) {
-            score = s;
-            if (s < th8[u]) {
-              alive = false;
-              if constexpr (TRACE) {
-                died_at = j0 + u;
-                const long long gw = trace_index(c, wid);
-                if (P.trace_n) P.trace_n[gw] = k0 + j0 + u + 1;
-                if (P.trace_s) P.trace_s[gw] = s;
-              }
+        if (!__any_sync(0xffffffffu, alive)) break;
+      }
+      if constexpr (TRACE) {
+        // leaves of the carts the reference would have evaluated: up to and including the rejecting one
+        if (P.trace_leaf) {
+#pragma unroll
+          for (int q = 0; q < K2_STRAG_ROWS; q++) {
+            if (q < nb) {
+              const int dw = __shfl_sync(0xffffffffu, died_at, q);
+              const long long gw = trace_index(c, __shfl_sync(0xffffffffu, wid, q));
+              if (gw >= P.leaf_w0 && gw < P.leaf_w1 && k0 + lane < K && lane <= min(dw, cnt - 1))
+                P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + k0 + lane] = lf[q];
             }
           }
         }
       }
-      if (!__any_sync(0xffffffffu, alive)) break;
-    }
-#else
-    for (unsigned rest = live; rest; rest &= rest - 1) {
-      const int w = __ffs(rest) - 1;
-      const PixBase<SMEM> pb = window_base<SMEM>(c, __shfl_sync(0xffffffffu, wid, w), true);
-      int idx = node_test<SMEM>(smem, n0, pb, c.pitch);
-      uint2 nd = *reinterpret_cast<const uint2 *>(smem + co + idx * 8);
-      idx = 2 * idx + node_test<SMEM>(smem, nd, pb, c.pitch);
-      nd = *reinterpret_cast<const uint2 *>(smem + co + idx * 8);
-      idx = 2 * idx + node_test<SMEM>(smem, nd, pb, c.pitch);
-      const int leaf = idx - kNodes;
-      ls[w * K2_LS_STRIDE + lane] = *reinterpret_cast<const float *>(smem + co + 56 + 4 * leaf);
-      if constexpr (TRACE) lf[w] = (uint8_t)leaf;
-    }
-    __syncwarp();
-    const int cnt = min(32, K - k0);
-    [[maybe_unused]] int died_at = alive ? cnt : -1;  // chunk-local cart after which this lane's window stopped
-    for (int j = 0; j < cnt; j++) {
-      const uint32_t cj = (uint32_t)(k0 + j) * kCartBytes;
-      const float cth = *reinterpret_cast<const float *>(smem + cj + 88);
-      const uint32_t nflag = *reinterpret_cast<const uint32_t *>(smem + cj + 92);
-      float s = __fadd_rn(score, ls[lrow + j]);  // lanes past the stragglers re-read row 0 (in bounds)
-      if (nflag) {
-        const Stage0Norm nm = c.norms[nflag - 1];
-        s = __fdiv_rn(__fsub_rn(s, nm.mean), nm.std);
-      }
+      __syncwarp();  // everyone is done with this batch's list entries and leaf scores
+      const unsigned m = __ballot_sync(0xffffffffu, alive);
       if (alive) {
-        score = s;
-        if (s < cth) {  // c/jda.c:399
-          alive = false;
-          if constexpr (TRACE) {
-            died_at = j;
-            const long long gw = trace_index(c, wid);
-            if (P.trace_n) P.trace_n[gw] = k0 + j + 1;
-            if (P.trace_s) P.trace_s[gw] = s;
-          }
-        }
+        const int pos = out + __popc(m & ((1u << lane) - 1u));
+        wd[pos] = (uint16_t)wid;
+        sc[pos] = score;
       }
-      if (!__any_sync(0xffffffffu, alive)) break;
+      out += __popc(m);
+      __syncwarp();
     }
-#endif
-    if constexpr (TRACE) {
-      // leaves of the carts the reference would have evaluated: up to and including the rejecting one
-      if (P.trace_leaf) {
-        for (unsigned rest = live; rest; rest &= rest - 1) {
-          const int w = __ffs(rest) - 1;
-          const int dw = __shfl_sync(0xffffffffu, died_at, w);
-          const long long gw = trace_index(c, __shfl_sync(0xffffffffu, wid, w));
-          if (gw >= P.leaf_w0 && gw < P.leaf_w1 && k0 + lane < K && lane <= min(dw, cnt - 1))
-            P.trace_leaf[(size_t)(gw - P.leaf_w0) * P.leaf_stride + k0 + lane] = lf[w];
-        }
-      }
-    }
+    n = out;
+  }
+  {  // the windows that passed every cart, back at the front of the tile's lists
+    const bool v0 = lane < n, v1 = lane + 32 < n;
+    const int a0 = v0 ? (int)wd[lane] : 0, a1 = v1 ? (int)wd[lane + 32] : 0;
+    const float s0 = v0 ? sc[lane] : 0.f, s1 = v1 ? sc[lane + 32] : 0.f;
+    __syncwarp();
+    if (v0) { c.lwid[lane] = (uint16_t)a0; c.lscore[lane] = s0; }
+    if (v1) { c.lwid[lane + 32] = (uint16_t)a1; c.lscore[lane + 32] = s1; }
     __syncwarp();
   }
-  // compact the windows that passed every cart back into the list
-  const unsigned m = __ballot_sync(0xffffffffu, alive);
-  __syncwarp();
-  if (alive) {
-    c.lwid[__popc(m & ((1u << lane) - 1u))] = (uint16_t)wid;
-    c.lscore[__popc(m & ((1u << lane) - 1u))] = score;  // the leaf-score scratch is free again
-  }
-  n = __popc(m);
-  __syncwarp();
 }
 
 // Windows of tile (x0w, y0w) that exist in `frame`: the level's own nx x ny grid, or -- in a mixed-size batch,
@@ -625,7 +615,7 @@ __device__ __forceinline__ void scan_tile(const ScanParams &P, const LevelInfo &
     n = out;
     cart = cend;
     if (n == 0) break;
-    if (n <= K2_STRAGGLERS && cart < P.K && P.stragglers) {
+    if (n <= K2_STRAG_MAX && cart < P.K && P.stragglers) {
       straggler_tail<SMEM, TRACE>(c, n, cart);
       break;
     }
