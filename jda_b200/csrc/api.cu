@@ -20,6 +20,8 @@
 #include "../../include/jda_b200.h"
 #include "host_model.hpp"
 #include "kernels.cuh"
+#include "kernels_stages.cuh"
+#include "kernels_regress.cuh"
 #include "kernels_f64.cuh"
 
 using namespace jda;
@@ -108,11 +110,14 @@ struct Tuning {
   int min_tile_windows = 128;     // JDA_B200_MIN_TILE_WINDOWS: a tile with fewer windows per warp pools buffers instead (r1n)
   int max_span = -1;              // JDA_B200_MAX_SPAN: -1 = by plan (throughput: up to 4 warps' buffers; latency: the whole block's)
   int latency_tile_windows = 256; // JDA_B200_LATENCY_TILE
+  int global_tile_rows = 0;       // JDA_B200_GLOBAL_TILE_ROWS: window rows (of 32) per global-memory virtual tile; 0 = by plan
   int tune_pitch = 0;             // JDA_B200_TUNE_PITCH: also try wider pitches and pick by the bank-conflict model (no gain, r1)
   std::string pitch_extra;        // JDA_B200_PITCH_EXTRA="24:16,30:32": extra tile pitch per window size (A/B)
   bool even_chunks = false;       // JDA_B200_EVEN_CHUNKS
   bool no_chunks = false;         // JDA_B200_NO_CHUNKS (test hook)
   bool tiny_queues = false;       // JDA_B200_TINY_QUEUES (test hook: start with queues that overflow)
+  bool old_regress = false;       // JDA_B200_OLD_REGRESS: the regression gather through k3_stage0 (round 1 kernel) instead of k3_regress (A/B)
+  bool no_stage_kernels = false;  // JDA_B200_NO_STAGE_KERNELS: stages >= 1 through k3_cascade (one warp per survivor) as in round 1 (A/B)
   double level_weight_exp = 1.0;  // JDA_B200_LEVEL_WEIGHT_EXP (r1q: scan -1.7 % against flat weights)
   std::string sched;              // JDA_B200_SCHED="4,8,16,...": phase ends of k2_scan
   int force_plan = 0;             // JDA_B200_FORCE_PLAN=latency|throughput (test hook: the per-window trace is a one-frame
@@ -131,10 +136,14 @@ Tuning read_tuning() {
   t.min_tile_windows = std::max(1, t.min_tile_windows);
   if (getenv("JDA_B200_MAX_SPAN")) { geti("JDA_B200_MAX_SPAN", t.max_span); t.max_span = std::max(1, t.max_span); }
   geti("JDA_B200_LATENCY_TILE", t.latency_tile_windows);
+  geti("JDA_B200_GLOBAL_TILE_ROWS", t.global_tile_rows);
+  t.global_tile_rows = std::max(0, std::min(K2_LIST_CAP / 32, t.global_tile_rows));
   t.latency_tile_windows = std::max(64, std::min(K2_LIST_CAP, t.latency_tile_windows));
   geti("JDA_B200_TUNE_PITCH", t.tune_pitch);
   if (const char *e = getenv("JDA_B200_PITCH_EXTRA")) t.pitch_extra = e;
   t.even_chunks = getenv("JDA_B200_EVEN_CHUNKS") != nullptr;
+  t.no_stage_kernels = getenv("JDA_B200_NO_STAGE_KERNELS") != nullptr;
+  t.old_regress = getenv("JDA_B200_OLD_REGRESS") != nullptr;
   t.no_chunks = getenv("JDA_B200_NO_CHUNKS") != nullptr;
   if (const char *e = getenv("JDA_B200_TINY_QUEUES")) t.tiny_queues = atoi(e) != 0;
   if (const char *e = getenv("JDA_B200_LEVEL_WEIGHT_EXP")) t.level_weight_exp = atof(e);
@@ -145,7 +154,9 @@ Tuning read_tuning() {
 
 constexpr int kSlots = 2;
 constexpr int kCntSurv = kMaxChunks * kMaxLevels, kCntWork = kCntSurv + kMaxChunks, kCntHit = kCntWork + kMaxChunks,
-              kCntTotal = kCntHit + 1;
+              kCntStage = kCntHit + 1,                     // [kMaxStages + 1] windows that passed stage t (kernels_stages.cuh)
+              kCntStageWork = kCntStage + kMaxStages + 1,  // [kMaxStages + 1] next list position k3_walk hands out at stage t
+              kCntTotal = kCntStageWork + kMaxStages + 1;
 
 struct Run;
 
@@ -159,6 +170,7 @@ struct Scratch {
   DevBuf<uint4> d_surv;
   DevBuf<float> d_shape0;
   DevBuf<uint8_t> d_surv_leaves;
+  DevBuf<uint2> d_stage_list[2];   // {queue entry, score} of the windows entering stage t (t & 1), kernels_stages.cuh
   DevBuf<float> d_hits;
   unsigned *d_counters = nullptr;  // [kMaxChunks][kMaxLevels] tile counters, surv_count, work, hit_count
   unsigned *h_counters = nullptr;  // pinned mirror
@@ -192,6 +204,7 @@ struct Context {
   float *d_leaf = nullptr;
   float4 *d_cart = nullptr;
   float *d_w = nullptr;
+  float *d_wp = nullptr;  // w with every row padded to a multiple of four floats (16-byte rows for k3_regress)
   float *d_mean = nullptr;
   // geometry + stage-0 tables
   Geometry geo;
@@ -244,6 +257,13 @@ size_t k2_smem_bytes(int table_bytes) { return (size_t)table_bytes + 256 + (size
 size_t k3s_smem_bytes(int K, int D) {
   return (size_t)K3S_COHORT * leaf_bytes(K) + (size_t)2 * K3S_CHUNK * kLeaves * D * 4;
 }
+constexpr size_t kSmemOptIn = 227 * 1024;  // dynamic shared memory a block may opt in to on sm_100
+// k3_walk: warps (= batches of survivors in flight) that fit next to the stage's tables; 0 = the tables do not fit
+int k3w_warps(int K, bool trace) {
+  const size_t tab = (k3w_table_bytes(K) + 15) & ~(size_t)15;
+  if (tab + 8 * k3w_warp_bytes(trace) > kSmemOptIn) return 0;
+  return (int)std::min<size_t>(K3W_MAX_WARPS, (kSmemOptIn - tab) / k3w_warp_bytes(trace));
+}
 size_t k3_smem_bytes(int K) { return (size_t)K3_WARPS * (kMaxDim * 4 + ((K + 15) & ~15)); }
 
 void ctx_release_device(Context *c);
@@ -282,6 +302,7 @@ void slot_free(Scratch &sc) {
   host_free(sc.h_counters); host_free(sc.h_eager); host_free(sc.h_stage);
   sc.d_dims.release(); sc.d_packed.release(); sc.d_unpack.release(); sc.d_frames.release(); sc.d_hq.release();
   sc.d_surv.release(); sc.d_shape0.release(); sc.d_surv_leaves.release(); sc.d_hits.release();
+  sc.d_stage_list[0].release(); sc.d_stage_list[1].release();
   for (auto &e : sc.ev) { if (e) cudaEventDestroy(e); e = nullptr; }
   for (auto &e : sc.ev_copy) { if (e) cudaEventDestroy(e); e = nullptr; }
   if (sc.ev_done) cudaEventDestroy(sc.ev_done);
@@ -324,6 +345,14 @@ bool ctx_init_impl(Context *c) {
   CU_OK(cudaMemcpy(c->d_leaf, m.leaf.data(), m.leaf.size() * 4, cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(c->d_cart, m.cart.data(), m.cart.size() * 4, cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(c->d_w, m.w.data(), m.w.size() * 4, cudaMemcpyHostToDevice));
+  {
+    const int D = m.D(), Dp = k3r_dpad(D);
+    const size_t rows = m.w.size() / D;
+    std::vector<float> wp(rows * Dp, 0.f);
+    for (size_t r = 0; r < rows; r++) memcpy(&wp[r * Dp], &m.w[r * D], (size_t)D * 4);
+    CU_OK(cudaMalloc(&c->d_wp, wp.size() * 4));
+    CU_OK(cudaMemcpy(c->d_wp, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
+  }
   CU_OK(cudaMemcpy(c->d_mean, m.mean_shape.data(), m.mean_shape.size() * 4, cudaMemcpyHostToDevice));
   {
     void *fn = nullptr;
@@ -353,8 +382,13 @@ bool ctx_init_impl(Context *c) {
   CU_OK(cudaFuncSetAttribute(k3_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   CU_OK(cudaFuncSetAttribute(k3_cascade<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
   CU_OK(cudaFuncSetAttribute(k3_cascade<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
-  // tuning knobs (not behaviour): windows per lane and the phase schedule of k2_scan
-  c->tune = read_tuning();
+  CU_OK(cudaFuncSetAttribute(k3_regress<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3r_smem_bytes(kMaxK, 64)));
+  CU_OK(cudaFuncSetAttribute(k3_regress<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3r_smem_bytes(kMaxK, kMaxDim)));
+  CU_OK(cudaFuncSetAttribute(k3_walk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemOptIn));
+  CU_OK(cudaFuncSetAttribute(k3_walk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemOptIn));
+  CU_OK(cudaFuncSetAttribute(k3_walk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemOptIn));
+  CU_OK(cudaFuncSetAttribute(k3_walk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemOptIn));
+  // tuning knobs (not behaviour; read from the environment when the handle was created): the phase schedule of k2_scan
   c->sched.clear();
   if (!c->tune.sched.empty()) {
     const char *p = c->tune.sched.c_str();
@@ -399,7 +433,7 @@ void release_model64(Context *c) {
 // frees every device / pinned resource of the handle (safe on a partially initialised one)
 void ctx_release_device(Context *c) {
   if (c->device >= 0) cudaSetDevice(c->device);
-  dev_free(c->d_nodes); dev_free(c->d_leaf); dev_free(c->d_cart); dev_free(c->d_w); dev_free(c->d_mean);
+  dev_free(c->d_nodes); dev_free(c->d_leaf); dev_free(c->d_cart); dev_free(c->d_w); dev_free(c->d_wp); dev_free(c->d_mean);
   dev_free(c->d_norms);
   release_model64(c);
   c->d_tables64.release(); c->d_hits64.release(); c->d_trace_s64.release(); c->d_trace_n64.release();
@@ -551,7 +585,10 @@ void plan_level(const Tuning &tn, LevelInfo &L, bool latency) {
     }
     L = pick;
   }
-  if (!L.use_smem) { L.tw_log2 = 5; L.th = latency ? 4 : K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0; }  // global-memory virtual tiles
+  if (!L.use_smem) {  // global-memory virtual tiles
+    L.tw_log2 = 5; L.th = latency ? 4 : K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0;
+    if (tn.global_tile_rows > 0) L.th = tn.global_tile_rows;
+  }
   const int tw = 1 << L.tw_log2;
   L.ntx = (L.nx + tw - 1) / tw;
   L.nty = (L.ny + L.th - 1) / L.th;
@@ -650,6 +687,8 @@ struct Run {
   size_t hq_stride;
   size_t eager;        // hit records that travel with the counters (collect_start)
   bool async;          // submitted batch: its copies must not queue behind the batch before it
+  bool one_chunk;      // submitted while the batch before it is still running: the whole copy hides under that batch, so
+                       // the scan is ONE launch (every chunk's launch ends in a tail of half-idle SMs)
   size_t cap_surv, cap_hit;  // queue capacities the kernels of this attempt were launched with
   bool done;           // nothing to run (no frames, or no pyramid level fits)
 };
@@ -705,7 +744,7 @@ bool stage_frames(Run &R, const unsigned char *frames) {
   R.pitch = (b.width + 15) & ~15;
   R.fstride = (size_t)R.pitch * b.height;
   if (!c->sc->d_frames.ensure(R.fstride * b.n_frames + 256)) return false;
-  if (b.n_frames >= 128 && !m.any_scaled && R.use_scan && !R.tracing && !c->tune.no_chunks) {
+  if (b.n_frames >= 128 && !m.any_scaled && R.use_scan && !R.tracing && !c->tune.no_chunks && !(R.one_chunk && !R.mixed)) {
     R.nchunks = kMaxChunks;
     R.host_chunks = true;
   }
@@ -907,24 +946,43 @@ bool launch_scan(Run &R) {
 // k3_stage0 (batches) + k3_cascade, once, over the whole survivor queue (or over every window in dense mode).
 // Running them per chunk on a second stream under the next chunk's scan was tried -- they fit on the SMs next
 // to the scan blocks -- and slowed the scan by more than the cascade time it hid (r1: 31.9 vs 30.2 ms / step).
+// The regression of stage t for the windows of `list` (NULL: every queue entry; then the shapes start from the mean
+// shape), c/jda.c:403-411.  k3_regress; k3_stage0 is the round-1 kernel, kept for A/B (JDA_B200_OLD_REGRESS).
+bool launch_regress(Run &R, int t, const uint2 *list, const unsigned *count) {
+  Context *c = R.c;
+  const HostModel &m = c->m;
+  const float *in_shape = t > 0 ? c->sc->d_shape0.p : nullptr;
+  if (c->tune.old_regress) {
+    Stage0Params S;
+    memset(&S, 0, sizeof S);
+    S.surv_leaves = c->sc->d_surv_leaves.p;
+    S.w0 = c->d_w + (size_t)t * m.K * kLeaves * R.D; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
+    S.surv_count = count; S.surv_cap = (unsigned)c->surv_cap;
+    S.list = list; S.in_shape = in_shape; S.out_shape = c->sc->d_shape0.p;
+    if (R.D <= 64) k3_stage0<1><<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
+    else k3_stage0<2><<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
+  } else {
+    RegressParams G;
+    memset(&G, 0, sizeof G);
+    G.leaves = c->sc->d_surv_leaves.p;
+    G.wp = c->d_wp + (size_t)t * m.K * kLeaves * k3r_dpad(R.D); G.mean_shape = c->d_mean; G.K = m.K; G.L = m.L;
+    G.count = count; G.cap = (unsigned)c->surv_cap;
+    G.list = list; G.in_shape = in_shape; G.out_shape = c->sc->d_shape0.p;
+    if (R.D <= 64) k3_regress<true><<<c->sm_count * 4, K3R_WARPS * 32, k3r_smem_bytes(m.K, R.D), R.s>>>(G);
+    else k3_regress<false><<<c->sm_count * 3, K3R_WARPS * 32, k3r_smem_bytes(m.K, R.D), R.s>>>(G);
+  }
+  CU_OK(cudaGetLastError());
+  c->sc->last.cascade_launches++;
+  return true;
+}
+
 bool launch_cascade(Run &R) {
   Context *c = R.c;
   const jdaB200Batch &b = *R.b;
   const Geometry &g = *R.geo;
   const HostModel &m = c->m;
   jdaB200Stats &st = c->sc->last;
-  if (R.staged0) {
-    Stage0Params S;
-    memset(&S, 0, sizeof S);
-    S.surv_leaves = c->sc->d_surv_leaves.p;
-    S.w0 = c->d_w; S.mean_shape = c->d_mean; S.K = m.K; S.L = m.L;
-    S.surv_count = c->sc->d_counters + kCntSurv; S.surv_cap = (unsigned)c->surv_cap;
-    S.out_shape = c->sc->d_shape0.p;
-    if (R.D <= 64) k3_stage0<1><<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
-    else k3_stage0<2><<<c->sm_count * 4, K3S_WARPS * 32, k3s_smem_bytes(m.K, R.D), R.s>>>(S);
-    CU_OK(cudaGetLastError());
-    st.cascade_launches++;
-  }
+  if (R.staged0 && !launch_regress(R, 0, nullptr, c->sc->d_counters + kCntSurv)) return false;
   CascadeParams Q;
   memset(&Q, 0, sizeof Q);
   Q.frames = R.d_frames; Q.frame_stride = R.fstride; Q.pitch = R.pitch; Q.W = b.width; Q.H = b.height;
@@ -952,6 +1010,49 @@ bool launch_cascade(Run &R) {
     Q.trace_n = c->d_trace_n.p; Q.trace_s = c->d_trace_s.p;
     Q.trace_leaf = (R.trace->leaf && R.trace->w1 > R.trace->w0) ? c->d_trace_leaf.p : nullptr;
     Q.leaf_w0 = R.trace->w0; Q.leaf_w1 = R.trace->w1; Q.leaf_stride = R.leaf_stride;
+  }
+  // Batches: stages >= 1 one at a time (kernels_stages.cuh) -- the stage's tables in shared memory, the running scores
+  // replayed with lane = survivor.  One frame / dense mode / other tree depths: one warp per window through k3_cascade.
+  const int walk_warps = k3w_warps(m.K, R.tracing);
+  if (R.staged0 && m.depth == kDepth && walk_warps > 0 && !c->tune.no_stage_kernels) {
+    if (!c->sc->d_stage_list[0].ensure(c->surv_cap) || !c->sc->d_stage_list[1].ensure(c->surv_cap)) return false;
+    WalkParams W;
+    memset(&W, 0, sizeof W);
+    W.C = Q;
+    W.shape = c->sc->d_shape0.p;
+    W.leaf_pad = R.leaf_pad;
+    unsigned *cnt = c->sc->d_counters + kCntStage, *work = c->sc->d_counters + kCntStageWork;
+    const size_t wsmem = ((k3w_table_bytes(m.K) + 15) & ~(size_t)15) + (size_t)walk_warps * k3w_warp_bytes(R.tracing);
+    const uint2 *in = nullptr;
+    const unsigned *in_cnt = Q.surv_count;
+    int n_before = R.scan_K;
+    const int t_end = R.t_run + (R.k_extra > 0 ? 1 : 0);
+    for (int t = 1; t < t_end; t++) {
+      const bool full = t < R.t_run;  // a whole stage, regression after it; else Validate's unfinished stage (cascador.cpp:199-209)
+      uint2 *out = c->sc->d_stage_list[t & 1].p;
+      W.t = t; W.Kt = full ? m.K : R.k_extra; W.n_eval_before = n_before;
+      W.in_list = in; W.in_count = in_cnt; W.out_list = out; W.out_count = cnt + t; W.work = work + t;
+      W.leaves = full ? c->sc->d_surv_leaves.p : nullptr;
+      const dim3 wb(walk_warps * 32);
+      if (R.tracing) {
+        if (m.any_scaled) k3_walk<true, true><<<c->sm_count, wb, wsmem, R.s>>>(W);
+        else k3_walk<true, false><<<c->sm_count, wb, wsmem, R.s>>>(W);
+      } else {
+        if (m.any_scaled) k3_walk<false, true><<<c->sm_count, wb, wsmem, R.s>>>(W);
+        else k3_walk<false, false><<<c->sm_count, wb, wsmem, R.s>>>(W);
+      }
+      CU_OK(cudaGetLastError());
+      st.cascade_launches++;
+      // c/jda.c:403-411 for the windows that passed: shape += sum_k w[t][8k + leaf_k], in place
+      if (full && !launch_regress(R, t, out, cnt + t)) return false;
+      in = out; in_cnt = cnt + t; n_before += W.Kt;
+    }
+    W.in_list = in; W.in_count = in_cnt; W.n_eval_before = n_before;
+    if (R.tracing) k3_emit<true><<<c->sm_count * 8, 128, 0, R.s>>>(W);
+    else k3_emit<false><<<c->sm_count * 8, 128, 0, R.s>>>(W);
+    CU_OK(cudaGetLastError());
+    st.cascade_launches++;
+    return true;
   }
   const int grid = c->sm_count * 16;  // survivors are handed out by an atomic counter: enough blocks to fill every SM
   const size_t smem = k3_smem_bytes(m.K);
@@ -1036,12 +1137,13 @@ bool collect_finish(Run &R, std::vector<HitRec> &hits, bool &overflow) {
 // after run_enqueue, jdaB200Collect picks up at run_finish.
 // R.done = nothing to do (no frames / no levels): `hits` stays empty.
 bool run_prepare(Context *c, Run &R, const unsigned char *frames, const jdaB200Batch &b, const TraceOut *trace,
-                 bool timing, const jdaB200Frame *mixed, bool async = false) {
+                 bool timing, const jdaB200Frame *mixed, int async = 0 /* 1: submitted batch, 2: + the batch before it is still running */) {
   jdaB200Stats &st = c->sc->last;
   memset(&st, 0, sizeof st);
   memset(&R, 0, sizeof R);
   R.done = true;
-  R.async = async;
+  R.async = async != 0;
+  R.one_chunk = async == 2;
   if (b.n_frames <= 0) return true;
   if (b.width <= 0 || b.height <= 0 ||
       (!mixed && (b.pitch < b.width || b.frame_stride < (size_t)b.pitch * (b.height - 1) + b.width))) {
@@ -1667,6 +1769,7 @@ void *create(const char *path, bool dbl) {
     return nullptr;
   }
   memset(&c->sc->last, 0, sizeof c->sc->last);
+  c->tune = read_tuning();  // A/B knobs and test hooks: the environment is read once per handle, here
   c->path = path;
   c->path_dbl = dbl;
   return c;
@@ -1848,7 +1951,9 @@ int jdaB200Submit(void *cascador, const unsigned char *frames, const jdaB200Batc
   sl.frames = frames;
   if (!sl.run) sl.run = new Run();
   Run &R = *sl.run;
-  if (!run_prepare(c, R, frames, sl.batch, nullptr, true, nullptr, true) || (!R.done && !run_enqueue(R))) {
+  const bool prev_running = other.busy && cudaEventQuery(other.ev_done) == cudaErrorNotReady;
+  cudaGetLastError();
+  if (!run_prepare(c, R, frames, sl.batch, nullptr, true, nullptr, prev_running ? 2 : 1) || (!R.done && !run_enqueue(R))) {
     c->sc = &c->slot[0];
     return done(-1);
   }

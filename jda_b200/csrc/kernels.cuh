@@ -1059,13 +1059,17 @@ static_assert(K3S_CHUNK % 4 == 0, "leaf indices are fetched four at a time");
 __host__ __device__ constexpr int leaf_bytes(int K) { return (((K + 1) >> 1) + 15) & ~15; }
 
 struct Stage0Params {
-  const uint8_t *surv_leaves;    // [surv_cap][leaf_bytes(K)] leaf indices written by k2_scan, two per byte
-  const float *w0;               // w[0]: [8K][2L]
+  const uint8_t *surv_leaves;    // [surv_cap][leaf_bytes(K)] leaf indices written by k2_scan (k3_walk for t >= 1), two per byte
+  const float *w0;               // w[t]: [8K][2L]
   const float *mean_shape;
   int K, L;
-  const unsigned *surv_count;
+  const unsigned *surv_count;    // entries to process: of the survivor queue, or of `list`
   unsigned surv_cap;
   float *out_shape;              // [surv_cap][2L]
+  // stages >= 1 (kernels_stages.cuh): the windows that passed stage t are named by a list of queue entries and the
+  // regression continues from their shape after stage t - 1, in place (c/jda.c:403-411: shape[i] += w[...], k ascending)
+  const uint2 *list;             // {queue entry, -}; NULL: entry i is queue entry i
+  const float *in_shape;         // [surv_cap][2L]; NULL: the mean shape
 };
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
@@ -1088,11 +1092,16 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
 
   for (int c0 = blockIdx.x * K3S_COHORT; c0 < total; c0 += gridDim.x * K3S_COHORT) {
     // ---- leaves of my K3S_PER_WARP survivors: computed by k2_scan while the window was in shared memory
+    unsigned ent[K3S_PER_WARP];  // queue entries of my seats
 #pragma unroll
     for (int s = 0; s < K3S_PER_WARP; s++) {
-      const int e = c0 + warp * K3S_PER_WARP + s;
-      if (e >= total) continue;
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(P.surv_leaves + (size_t)e * kpad);
+      const int i = c0 + warp * K3S_PER_WARP + s;
+      ent[s] = (i < total) ? (P.list ? P.list[i].x : (unsigned)i) : 0u;
+    }
+#pragma unroll
+    for (int s = 0; s < K3S_PER_WARP; s++) {
+      if (c0 + warp * K3S_PER_WARP + s >= total) continue;
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(P.surv_leaves + (size_t)ent[s] * kpad);
       uint32_t *dst = reinterpret_cast<uint32_t *>(leaves + (size_t)(warp * K3S_PER_WARP + s) * kpad);
       for (int i = lane; i < kpad / 4; i += 32) dst[i] = __ldg(src + i);
     }
@@ -1103,7 +1112,8 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
 #pragma unroll
       for (int h = 0; h < HALVES; h++) {
         const int p = lane + 32 * h;
-        acc[s][h] = (2 * p + 1 < D) ? make_float2(P.mean_shape[2 * p], P.mean_shape[2 * p + 1]) : make_float2(0.f, 0.f);
+        const float *from = (P.in_shape && c0 + warp * K3S_PER_WARP + s < total) ? P.in_shape + (size_t)ent[s] * D : P.mean_shape;
+        acc[s][h] = (2 * p + 1 < D) ? make_float2(from[2 * p], from[2 * p + 1]) : make_float2(0.f, 0.f);
       }
     auto stage = [&](int ci, int buf) {
       const int carts = min(K3S_CHUNK, K - ci * K3S_CHUNK);
@@ -1154,12 +1164,11 @@ __global__ void __launch_bounds__(K3S_WARPS * 32) k3_stage0(const __grid_constan
     }
 #pragma unroll
     for (int s = 0; s < K3S_PER_WARP; s++) {
-      const int e = c0 + warp * K3S_PER_WARP + s;
-      if (e < total) {
+      if (c0 + warp * K3S_PER_WARP + s < total) {
 #pragma unroll
         for (int h = 0; h < HALVES; h++) {
           const int p = lane + 32 * h;
-          if (2 * p + 1 < D) reinterpret_cast<float2 *>(P.out_shape + (size_t)e * D)[p] = acc[s][h];
+          if (2 * p + 1 < D) reinterpret_cast<float2 *>(P.out_shape + (size_t)ent[s] * D)[p] = acc[s][h];
         }
       }
     }

@@ -699,3 +699,48 @@ def test_queue_overflow_grows_and_retries(oracle, oracle_shipped):
         c.close()
     finally:
         del os.environ["JDA_B200_TINY_QUEUES"]
+
+
+# ---- stages >= 1: the stage-synchronous kernels (k3_walk / k3_regress / k3_emit) against the one-warp-per-window
+# ---- kernel (k3_cascade) and the round-1 regression kernel (k3_stage0)
+
+def _with_env(name, **kw):
+    """(a handle reads its A/B knobs and test hooks from the environment once, when it is created)"""
+    os.environ[name] = "1"
+    try:
+        return api.Cascador(SHIPPED_F32, double=False, **kw)
+    finally:
+        del os.environ[name]
+
+
+@pytest.mark.parametrize("mode", ["full", "t2_k101", "t3"])
+def test_stage_kernels_equal_one_warp_per_window(casc, oracle, oracle_shipped, mode):
+    """A 40-frame batch (throughput plan) with many deep survivors: faces pass all five stages, blurred frames die in
+    stages 1-3.  Default = k3_walk + k3_regress + k3_emit; JDA_B200_NO_STAGE_KERNELS = k3_cascade for stages >= 1;
+    JDA_B200_OLD_REGRESS = k3_stage0 for every regression.  All three give the same bits, and frames 0 / 1 / 21 equal
+    the oracle's."""
+    frames = np.stack([synth.face_canvas()] + [synth.facemix_frame(300 + i) for i in range(19)] +
+                      list(synth.make_frames("blur6", 10, seed0=340)) + list(synth.make_frames("mix", 10, seed0=350)))
+    kw = dict(flags=api.RAW_HITS | api.NO_FINAL_TH)
+    okw = dict(use_th=False)
+    if mode == "t2_k101":
+        kw.update(t_limit=2, k_limit=101); okw.update(t_limit=2, k_limit=101)
+    elif mode == "t3":
+        kw.update(t_limit=3); okw.update(t_limit=3)
+    got = casc.detect_batch(frames, **kw)
+    launches = casc.last_stats["cascade_launches"]
+    c1 = _with_env("JDA_B200_NO_STAGE_KERNELS")
+    c2 = _with_env("JDA_B200_OLD_REGRESS")
+    try:
+        old = c1.detect_batch(frames, **kw)
+        assert c1.last_stats["cascade_launches"] == 2 < launches   # (k3_stage0 + k3_cascade) against one pair per stage + emit
+        oldr = c2.detect_batch(frames, **kw)
+    finally:
+        c1.close(); c2.close()
+    assert sum(len(g[1]) for g in got) > 50
+    for a, b, d in zip(got, old, oldr):
+        _same(a, b)
+        _same(a, d)
+    for f in (0, 1, 21):
+        ob, osc, osh, _ = oracle.detect_raw(oracle_shipped, frames[f], **okw)
+        _same(got[f], (ob, osc, osh))
