@@ -233,6 +233,13 @@ JDA_API int jdaB200SerializeTo(void *cascador, const char *model, int flags);
 /* model dimensions: out[0..3] = T, K, landmark_n, tree_depth (2..6 accepted; the reference fixes 4, c/jda.c:28) */
 JDA_API void jdaB200ModelDims(void *cascador, int *out4);
 
+/* jdaDetect (part 1) may be called from any number of host threads on one handle, like the reference's (c/jda.c:443-480
+ * keeps no state in the cascador).  Calls that arrive while an earlier one is running are coalesced: the caller that finds
+ * nobody serving runs every queued call with the same (scale, min_size, max_size, th) as ONE mixed-size batch (each
+ * frame's result is bit for bit what it gives alone) and wakes the others; a lone caller is served at once.  Counters since
+ * the handle was created: jdaDetect calls, device batches they were served in, frames of the largest batch. */
+JDA_API void jdaB200CoalescingStats(void *cascador, long long *calls, long long *batches, int *largest);
+
 /* last error text of the calling thread ("" if none) */
 JDA_API const char *jdaB200LastError(void);
 

@@ -131,6 +131,8 @@ def lib():
     L.jdaB200SetStream.argtypes = [vp, vp]
     L.jdaB200ModelDims.restype = None
     L.jdaB200ModelDims.argtypes = [vp, C.POINTER(ci)]
+    L.jdaB200CoalescingStats.restype = None
+    L.jdaB200CoalescingStats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(ci)]
     L.jdaB200LastError.restype = cp
     L.jdaB200LastError.argtypes = []
     L.jdaB200DeviceCount.restype = ci
@@ -164,7 +166,8 @@ EXPORTS = ["jdaCascadorCreateDouble", "jdaCascadorCreateFloat", "jdaCascadorSeri
            "jdaB200Trace", "jdaB200Resize", "jdaB200DescribePlan", "jdaB200ResultsRelease",
            "jdaB200DetectMixed", "jdaB200JoinCascadorDetect", "jdaB200ResultF64Release",
            "jdaB200JoinCascadorTrace", "jdaB200JoinCascadorLevels", "jdaB200JoinCascadorFilterMargins",
-           "jdaB200DetectBatchFlat", "jdaB200FlatResultRelease", "jdaB200TraceK", "jdaB200SerializeTo", "jdaB200Submit", "jdaB200Collect"]
+           "jdaB200DetectBatchFlat", "jdaB200FlatResultRelease", "jdaB200TraceK", "jdaB200SerializeTo", "jdaB200Submit", "jdaB200Collect",
+           "jdaB200CoalescingStats"]
 
 
 def last_error():
@@ -276,6 +279,12 @@ class Cascador:
         res = lib().jdaDetect(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), a.shape[1], a.shape[0],
                               scale, step, min_size, max_size, th)
         return _unpack(res)
+
+    def coalescing_stats(self):
+        """(jdaDetect calls, device batches they were served in, frames of the largest batch) since creation."""
+        a, b, m = C.c_longlong(0), C.c_longlong(0), C.c_int(0)
+        lib().jdaB200CoalescingStats(self._h, C.byref(a), C.byref(b), C.byref(m))
+        return a.value, b.value, m.value
 
     def detect_batch(self, frames, scale=1.25, min_size=24, max_size=-1, th=0.0, t_limit=0, flags=0,
                      device_ptr=None, shape=None, pitch=None, frame_stride=None, unpack=True, flat=False, k_limit=0):

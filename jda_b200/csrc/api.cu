@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdlib>
 #include <map>
@@ -191,9 +192,27 @@ struct Scratch {
   Run *run = nullptr;
 };
 
+// One jdaDetect call waiting to be served (see jdaDetect: concurrent callers are coalesced into batches).
+struct DetectReq {
+  const unsigned char *data;
+  int width, height;
+  float scale;
+  int min_size, max_size;
+  float th;
+  jdaResult res;
+  bool done;
+};
+
 struct Context {
   HostModel m;
   std::mutex mu;
+  // jdaDetect's combiner: callers queue here; whoever finds no leader serves the oldest group of the queue
+  std::mutex cq_mu;
+  std::condition_variable cq_cv;
+  std::vector<DetectReq *> cq;
+  bool cq_leader = false;
+  long long cq_calls = 0, cq_batches = 0;
+  int cq_largest = 0;
   int device = -1;
   bool inited = false;
   cudaStream_t own_stream = nullptr, user_stream = nullptr, copy_stream = nullptr;
@@ -1799,26 +1818,91 @@ void jdaCascadorRelease(void *cascador) {
   if (cascador) ctx_free(static_cast<Context *>(cascador));
 }
 
+// c/jda.h:52-60.  The reference's jdaDetect is a pure function of a read-only cascador, so a host may call it from as
+// many threads as it likes and they all make progress.  Here one device serves the handle: calls that arrive while an
+// earlier one is running are COALESCED -- the caller that finds nobody serving takes every queued call with the same
+// (scale, min_size, max_size, th) and runs them as one mixed-size batch (detect_mixed: result f is bit for bit what
+// frame f alone gives), hands out the results and wakes the others.  A lone caller takes the one-frame path at once:
+// nobody ever waits for a batch to fill.
+constexpr int kMaxCoalesced = 256;
+
 jdaResult jdaDetect(void *cascador, unsigned char *data, int width, int height, float scale, float step,
                     int min_size, int max_size, float th) {
   (void)step;  // ignored by the reference as well (c/jda.c:333)
   Context *c = static_cast<Context *>(cascador);
   if (!c || !data) return empty_result(c ? c->m.L : 0, -1);
-  jdaB200Batch b;
-  memset(&b, 0, sizeof b);
-  b.n_frames = 1; b.width = width; b.height = height; b.pitch = width;
-  b.frame_stride = (size_t)width * height;
-  b.scale = scale; b.min_size = min_size; b.max_size = max_size; b.th = th;
-  jdaResult r = empty_result(c->m.L, -1);
   if (width <= 0 || height <= 0) return finish_frame(c->m, nullptr, 0, false);
-  detect_batch(c, data, b, &r, nullptr);
-  return r;
+  DetectReq rq;
+  rq.data = data; rq.width = width; rq.height = height;
+  rq.scale = scale; rq.min_size = min_size; rq.max_size = max_size; rq.th = th;
+  rq.res = empty_result(c->m.L, -1);
+  rq.done = false;
+  std::unique_lock<std::mutex> lk(c->cq_mu);
+  c->cq.push_back(&rq);
+  c->cq_calls++;
+  while (!rq.done) {
+    if (c->cq_leader) {
+      c->cq_cv.wait(lk);
+      continue;
+    }
+    // serve the oldest call and everything queued with its parameters (mine may be in a later group)
+    c->cq_leader = true;
+    std::vector<DetectReq *> grp;
+    const DetectReq &lead = *c->cq.front();
+    const bool can_mix = c->m.stage0_lut_ok && !c->m.any_scaled;  // (else a mixed batch would run shape by shape anyway)
+    for (size_t i = 0; i < c->cq.size();) {
+      DetectReq *r = c->cq[i];
+      const bool same = r->scale == lead.scale && r->min_size == lead.min_size && r->max_size == lead.max_size && r->th == lead.th;
+      if (same && (grp.empty() || (can_mix && (int)grp.size() < kMaxCoalesced))) {
+        grp.push_back(r);
+        c->cq.erase(c->cq.begin() + i);
+      } else {
+        i++;
+      }
+    }
+    c->cq_batches++;
+    c->cq_largest = std::max(c->cq_largest, (int)grp.size());
+    lk.unlock();
+    if (grp.size() == 1) {
+      DetectReq &r = *grp[0];
+      jdaB200Batch b;
+      memset(&b, 0, sizeof b);
+      b.n_frames = 1; b.width = r.width; b.height = r.height; b.pitch = r.width;
+      b.frame_stride = (size_t)r.width * r.height;
+      b.scale = r.scale; b.min_size = r.min_size; b.max_size = r.max_size; b.th = r.th;
+      detect_batch(c, r.data, b, &r.res, nullptr);
+    } else {
+      std::vector<jdaB200Frame> fr(grp.size());
+      std::vector<jdaResult> out(grp.size());
+      for (size_t i = 0; i < grp.size(); i++) {
+        memset(&fr[i], 0, sizeof fr[i]);
+        fr[i].data = grp[i]->data; fr[i].width = grp[i]->width; fr[i].height = grp[i]->height; fr[i].pitch = grp[i]->width;
+      }
+      const DetectReq &g0 = *grp[0];
+      detect_mixed(c, fr.data(), (int)grp.size(), g0.scale, g0.min_size, g0.max_size, g0.th, 0, 0, out.data(), nullptr);
+      for (size_t i = 0; i < grp.size(); i++) grp[i]->res = out[i];
+    }
+    lk.lock();
+    for (DetectReq *r : grp) r->done = true;
+    c->cq_leader = false;
+    c->cq_cv.notify_all();
+  }
+  return rq.res;
 }
 
 void jdaResultRelease(jdaResult result) {
   free(result.bboxes);
   free(result.shapes);
   free(result.scores);
+}
+
+void jdaB200CoalescingStats(void *cascador, long long *calls, long long *batches, int *largest) {
+  Context *c = static_cast<Context *>(cascador);
+  if (!c) return;
+  std::lock_guard<std::mutex> lk(c->cq_mu);
+  if (calls) *calls = c->cq_calls;
+  if (batches) *batches = c->cq_batches;
+  if (largest) *largest = c->cq_largest;
 }
 
 int jdaB200DetectBatch(void *cascador, const unsigned char *frames, const jdaB200Batch *batch, jdaResult *results,

@@ -744,3 +744,29 @@ def test_stage_kernels_equal_one_warp_per_window(casc, oracle, oracle_shipped, m
     for f in (0, 1, 21):
         ob, osc, osh, _ = oracle.detect_raw(oracle_shipped, frames[f], **okw)
         _same(got[f], (ob, osc, osh))
+
+
+def test_concurrent_jdadetect_calls_are_coalesced(oracle, oracle_shipped):
+    """Sixteen host threads on one handle, every one calling the reference's own entry point (jdaDetect) on frames of
+    different sizes: calls that arrive while another is running are served together as one mixed-size batch -- and every
+    caller still gets, bit for bit, what its frame gives alone (compared with the serial results of the same handle and,
+    for a sample, with the oracle).  Calls with other parameters are never merged into the same batch."""
+    from concurrent.futures import ThreadPoolExecutor
+    c = api.Cascador(SHIPPED_F32, double=False)
+    frames = [synth.facemix_frame(500 + i, *synth.fddb_shape(i)) for i in range(40)] + \
+             [synth.face_canvas(), synth.blur_frame(2, 30, 27), synth.noise_frame(3, 23, 64)] + \
+             [synth.facemix_frame(560 + i) for i in range(21)]
+    kws = [dict(th=-0.5) if i % 7 else dict(scale=1.3, min_size=30, th=-1.0) for i in range(len(frames))]
+    want = [c.detect(f, **kw) for f, kw in zip(frames, kws)]
+    calls0, batches0, _ = c.coalescing_stats()
+    assert calls0 == batches0 == len(frames)            # serial calls: one batch each
+    with ThreadPoolExecutor(16) as ex:
+        got = list(ex.map(lambda a: c.detect(a[0], **a[1]), zip(frames, kws)))
+    for g, w in zip(got, want):
+        _same(g, w)
+    calls, batches, largest = c.coalescing_stats()
+    assert calls - calls0 == len(frames)
+    assert batches - batches0 < len(frames) and largest >= 2, (calls, batches, largest)
+    for i in (0, 7, 40, 41, 42, 50):
+        _same(got[i], oracle.detect(oracle_shipped, frames[i], **kws[i]))
+    c.close()

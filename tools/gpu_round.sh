@@ -23,20 +23,23 @@ if [ "${NCU:-1}" = "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $O/${tag}_ncu_bench.log 2>&1
 grep -c k2_scan $O/${tag}_launches.csv
-# full capture: one launch of each kernel at 256 resident frames
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2_scan|k3_' -s 6 -c 3 -f -o /tmp/${tag}_full \
+# full capture: the kernels of ONE 256-frame step (k2_scan, k3_regress, 4 x (k3_walk, k3_regress), k3_emit), resident frames;
+# the traced instantiations the bench uses for its cart statistics are left out by name
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+  -k regex:'k2_scan<\(int\)4, \(bool\)0, \(bool\)0>|k3_walk<\(bool\)0|k3_regress|k3_emit<\(bool\)0' -s 11 -c 11 -f -o /tmp/${tag}_full \
   python bench.py --batch 256 --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $O/${tag}_ncu_full.log 2>&1
 python tools/ncu_digest.py /tmp/${tag}_full.ncu-rep $O/${tag}_full 256 >> $O/${tag}_ncu_full.log 2>&1
 cp $O/${tag}_full_k2_capture.json $O/k2_capture.json 2>/dev/null   # -> profiles/k2_capture.json (bench.py reads it)
 ls -la /tmp/${tag}_full.ncu-rep >> $O/${tag}_ncu_full.log 2>&1
 fi
 if [ "${AB:-0}" = "1" ]; then
-# A/B of scan-kernel knobs (resident frames, 6 steps each)
+# A/B of the cascade kernels (resident frames, 6 steps each)
 source tools/ab.sh
 {
 run default
-run k3g1b8 JDA_B200_LIB=libjda_b200_k3g1b8.so
-run k3g2b12 JDA_B200_LIB=libjda_b200_k3g2b12.so
+run k3_cascade_for_stages_ge_1 JDA_B200_NO_STAGE_KERNELS=1
+run k3_stage0_regression JDA_B200_OLD_REGRESS=1
+run round1_k3 JDA_B200_NO_STAGE_KERNELS=1 JDA_B200_OLD_REGRESS=1
 } > $O/${tag}_ab.txt 2>&1
 cat $O/${tag}_ab.txt
 fi
