@@ -716,6 +716,7 @@ def main():
                                       "frac": wf_rate / (148 * sm_hz), "wavefronts_per_window": wf_per_window,
                                       "bank_conflict_share": cap["smem_bank_conflicts"] / cap["smem_wavefronts"],
                                       "capture_matches_tree": fresh,
+                                      "ncu_pipe_pct_in_capture": cap.get("lsu_data_pipe_pct"),  # shared + global wavefronts of the whole launch
                                       "peak_source": "1 wavefront/clk/SM measured by tools/probes/lds_probe.cu x 148 SMs x SM clock"}
         if not a.no_cpu_baseline and world == 1:  # the reported CPU baseline is an N=1 item
             cores = os.cpu_count() or 1

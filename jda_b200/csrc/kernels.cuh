@@ -41,9 +41,6 @@ struct LevelInfo {
 #ifndef JDA_K2_TILE_BYTES
 #define JDA_K2_TILE_BYTES 8192
 #endif
-#ifndef JDA_K2_POOL_DYNAMIC
-#define JDA_K2_POOL_DYNAMIC 0  /* > 0: pooled tiles hand their window rows out dynamically, about this many slices per warp */
-#endif
 constexpr int K2_WARPS = JDA_K2_WARPS;            // warps per scan block (one block per SM)
 constexpr int K2_TILE_BYTES = JDA_K2_TILE_BYTES;  // per-warp pixel tile
 constexpr int K2_LIST_CAP = 512;     // windows per tile (fits u16 ids)
@@ -666,7 +663,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ int s_skip;
   __shared__ unsigned s_item[K2_WARPS];
-  __shared__ int s_row[K2_WARPS];  // pooled tiles: next window row of the group's tile to hand out
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t table_sz = (uint32_t)(P.table_bytes + 127) & ~127u;
   const uint32_t norm_off = table_sz;
@@ -725,7 +721,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
             if (loaded && P.use_tma) lead->parity ^= 1u;
             const unsigned it2 = atomicAdd(&P.tile_counters[li], 1u);
             s_item[grp] = it2;
-            s_row[grp] = 0;
             if (it2 < total && P.use_tma) {
               const int f = it2 / tiles_per_frame, r = it2 - f * tiles_per_frame;
               const int ty = r / lv.ntx, tx = r - ty * lv.ntx;
@@ -762,26 +757,10 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_scan(const __grid_constan
           }
           asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthr) : "memory");
         }
-#if JDA_K2_POOL_DYNAMIC
-        // the tile's window rows are handed out a few at a time: a warp that meets a deep window (hundreds of carts)
-        // keeps its slice while the others take the rest, instead of everybody waiting at the tile's barrier for the
-        // warp whose static quarter held it
-        const int rows_per = max(1, ch / (lv.span * JDA_K2_POOL_DYNAMIC));
-        for (;;) {
-          int r0 = 0;
-          if (lane == 0) r0 = atomicAdd(&s_row[grp], rows_per);
-          r0 = __shfl_sync(0xffffffffu, r0, 0);
-          if (r0 >= ch) break;
-          const int r1 = min(ch, r0 + rows_per);
-          scan_tile<true, NW, TRACE>(P, lv, li, smem, norm_off, gtile_off + (uint32_t)(xs + r0 * lv.step * lv.box_w),
-                                     wl->lscore, wl->lwid, frame, x0w, y0w + r0, cw, r1 - r0, lane);
-        }
-#else
         const int r0 = ch * gl / lv.span, r1 = ch * (gl + 1) / lv.span;
         if (r1 > r0)
           scan_tile<true, NW, TRACE>(P, lv, li, smem, norm_off, gtile_off + (uint32_t)(xs + r0 * lv.step * lv.box_w),
                                      wl->lscore, wl->lwid, frame, x0w, y0w + r0, cw, r1 - r0, lane);
-#endif
       }
       continue;
     }
