@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/jda_b200.h"
@@ -177,7 +178,7 @@ struct Scratch {
   unsigned *h_counters = nullptr;  // pinned mirror
   std::vector<float> h_hits;
   float *h_eager = nullptr;        // pinned: the first kEagerHits hit records
-  uint8_t *h_stage = nullptr;      // pinned staging for small pageable inputs
+  uint8_t *h_stage = nullptr;      // pinned staging for pageable inputs (8 MB to start with, grows to the largest batch seen)
   size_t h_stage_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_copy[kMaxChunks + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -747,6 +748,31 @@ bool copy_mixed_chunk(Run &R, int ch) {
   return true;
 }
 
+// Frames [f0, f1) from the caller's (pageable) memory into the 16-byte-pitched pinned staging area, rows split over a
+// few host threads: one memcpy stream runs at 6-10 GB/s, a 157 MB batch should not take longer than its H2D copy.
+void repack_frames(uint8_t *dst, int dst_pitch, size_t dst_fstride, const unsigned char *src, int src_pitch, size_t src_fstride,
+                   int width, int height, int f0, int f1) {
+  const long long rows = (long long)(f1 - f0) * height;
+  const size_t bytes = (size_t)rows * width;
+  auto work = [=](long long r0, long long r1) {
+    if (dst_pitch == src_pitch && dst_fstride == src_fstride && dst_fstride == (size_t)dst_pitch * height) {
+      memcpy(dst + f0 * dst_fstride + r0 * dst_pitch, src + f0 * src_fstride + r0 * src_pitch, (size_t)(r1 - r0) * dst_pitch);
+      return;
+    }
+    for (long long r = r0; r < r1; r++) {
+      const long long f = f0 + r / height, y = r % height;
+      memcpy(dst + f * dst_fstride + y * dst_pitch, src + f * src_fstride + y * src_pitch, width);
+    }
+  };
+  unsigned hc = std::thread::hardware_concurrency();
+  int nt = (int)std::min<unsigned>(8u, hc ? hc / 2 : 1u);
+  if (bytes < ((size_t)4 << 20) || nt < 2) { work(0, rows); return; }
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; i++) th.emplace_back(work, rows * i / nt, rows * (i + 1) / nt);
+  work(0, rows / nt);
+  for (auto &t : th) t.join();
+}
+
 // Frames to HBM.  Device input is used in place; host input goes into a 16-byte-pitched store: large batches
 // in kMaxChunks pieces on the copy stream (the scan of chunk i then overlaps the copy of chunk i+1), a small
 // pageable input repacked through pinned staging (the driver's pageable path costs more than a one-frame detect).
@@ -804,23 +830,32 @@ bool stage_frames(Run &R, const unsigned char *frames) {
     R.d_frames = c->sc->d_frames.p;
     return true;
   }
-  bool staged = false;
-  if (R.nchunks == 1 && R.fstride * b.n_frames <= c->sc->h_stage_cap) {
-    cudaPointerAttributes pa;
-    const bool pageable = cudaPointerGetAttributes(&pa, frames) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
-    cudaGetLastError();
-    if (pageable) {
-      for (int f = 0; f < b.n_frames; f++)
-        for (int y = 0; y < b.height; y++)
-          memcpy(c->sc->h_stage + f * R.fstride + (size_t)y * R.pitch, frames + f * b.frame_stride + (size_t)y * b.pitch, b.width);
-      CU_OK(cudaMemcpyAsync(c->sc->d_frames.p, c->sc->h_stage, R.fstride * b.n_frames, cudaMemcpyHostToDevice, c->copy_stream));
-      CU_OK(cudaEventRecord(c->sc->ev_copy[0], c->copy_stream));
-      staged = true;
+  // Pageable input (plain malloc / numpy memory -- what a caller of the reference's API passes): the driver would stage
+  // it through its own bounce buffers on one thread (~6-8 GB/s: 157 MB of VGA frames cost more than their scan).  It
+  // is repacked into the scratch set's pinned staging by a few host threads instead and goes across with the same
+  // asynchronous copies as pinned input, chunk by chunk.
+  cudaPointerAttributes pa;
+  const bool pageable = cudaPointerGetAttributes(&pa, frames) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  const size_t total_bytes = R.fstride * b.n_frames;
+  if (pageable && total_bytes > c->sc->h_stage_cap) {
+    uint8_t *bigger = nullptr;
+    if (cudaMallocHost(&bigger, total_bytes + (total_bytes >> 3)) == cudaSuccess) {
+      host_free(c->sc->h_stage);
+      c->sc->h_stage = bigger;
+      c->sc->h_stage_cap = total_bytes + (total_bytes >> 3);
+    } else {
+      cudaGetLastError();  // no pinned memory to be had: the driver's pageable path below
     }
   }
-  for (int ch = 0; ch < R.nchunks && !staged; ch++) {
+  const bool staged = pageable && total_bytes <= c->sc->h_stage_cap;
+  for (int ch = 0; ch < R.nchunks; ch++) {
     const int f0 = chunk_begin(b.n_frames, ch, R.nchunks, c->tune.even_chunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks, c->tune.even_chunks);
-    if (b.frame_stride == (size_t)b.pitch * b.height) {
+    if (staged) {
+      repack_frames(c->sc->h_stage, R.pitch, R.fstride, frames, b.pitch, b.frame_stride, b.width, b.height, f0, f1);
+      CU_OK(cudaMemcpyAsync(c->sc->d_frames.p + f0 * R.fstride, c->sc->h_stage + f0 * R.fstride, (size_t)(f1 - f0) * R.fstride,
+                            cudaMemcpyHostToDevice, c->copy_stream));
+    } else if (b.frame_stride == (size_t)b.pitch * b.height) {
       CU_OK(cudaMemcpy2DAsync(c->sc->d_frames.p + f0 * R.fstride, R.pitch, frames + f0 * b.frame_stride, b.pitch, b.width,
                               (size_t)b.height * (f1 - f0), cudaMemcpyHostToDevice, c->copy_stream));
     } else {
