@@ -131,6 +131,16 @@ class RecordGather:
             event.record(self._side)
         return dict(rec=rec, cap=cap, recv=recv, send=send, work=None, event=event, back=back)
 
+    @staticmethod
+    def _next_cap(largest):
+        """Block capacity after seeing a rank send `largest` records.  Detections (a few hundred per batch): twice the
+        count, a power of two.  Mining (tens of thousands per batch, and every padded row crosses NVLink and PCIe to
+        every rank): a quarter above the count -- batches of one job differ by a few per cent, and a batch that does
+        overflow is simply exchanged again."""
+        if largest < 4096:
+            return 1 << int(np.ceil(np.log2(max(largest * 2, 1))))
+        return (int(largest * 1.25) + 4095) // 4096 * 4096
+
     def start(self, rec):
         assert self.pending is None, "finish() the previous exchange first"
         self.pending = self._launch(rec, self.cap, True)
@@ -144,14 +154,16 @@ class RecordGather:
                 p["work"].wait()
             if p["event"] is not None:
                 p["event"].synchronize()
-                allr = p["back"].numpy().reshape(self.world, p["cap"] + 1, self.width).copy()
+                # (a view of the pinned read-back block: np.concatenate below copies the used rows out, and the block is
+                # not written again before the next start())
+                allr = p["back"].numpy().reshape(self.world, p["cap"] + 1, self.width)
             else:
                 allr = p["recv"].numpy().reshape(self.world, p["cap"] + 1, self.width)
             counts = allr[:, 0, 0].astype(np.int64)
             if counts.max() <= p["cap"]:
-                self.cap = max(self.cap, 1 << int(np.ceil(np.log2(max(int(counts.max()) * 2, 1)))))
+                self.cap = max(self.cap, self._next_cap(int(counts.max())))
                 return np.concatenate([allr[r, 1:1 + int(counts[r])] for r in range(self.world)], axis=0)
             # some rank overflowed its block: every rank sees the same counts, so every rank repeats the exchange
-            cap = 1 << int(np.ceil(np.log2(int(counts.max()) * 2)))
+            cap = self._next_cap(int(counts.max()))
             self.cap = max(self.cap, cap)
             p = self._launch(p["rec"], cap, False)

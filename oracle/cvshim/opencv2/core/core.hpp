@@ -148,7 +148,11 @@ inline Scalar mean(const Mat_<double> &m) {
   return Scalar(m.rows * m.cols ? s / (m.rows * m.cols) : 0.);
 }
 
+// DataSet::RandomShape seeds an RNG with getTickCount() for every window (data.cpp:227): the reference's initial shift
+// is different on every run.  A test can fix the tick (and with it the seed and the shift) to pin that path too.
+inline int64 &shim_fixed_tick() { static int64 t = 0; return t; }
 inline int64 getTickCount() {
+  if (shim_fixed_tick()) return shim_fixed_tick();
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (int64)ts.tv_sec * 1000000000LL + ts.tv_nsec;

@@ -123,15 +123,70 @@ void jcpp_dims(void *m_, int *out) {
 
 /* ---------------------------------------------------------------- one window */
 
+/* face.similarity_transform (config.json) and the initial shift of DataSet::RandomShape (data.cpp:225-236).  The
+ * reference draws the shift from an RNG seeded with the tick count, per window: a caller that wants a non-zero shift
+ * passes the (x, y) that RNG produced.  Process-wide, like the reference's Config singleton. */
+static struct { int similarity; double shift_x, shift_y; } g_opt = {0, 0., 0.};
+void jcpp_set_options(int similarity, double shift_x, double shift_y) {
+  g_opt.similarity = similarity; g_opt.shift_x = shift_x; g_opt.shift_y = shift_y;
+}
+
+/* STParameter (include/jda/data.hpp:18-50): default = identity */
+typedef struct { double scale, r00, r01, r10, r11; } STP;
+static const STP STP_IDENTITY = {1., 1., 0., 0., 1.};
+
+/* data.hpp:42-45 */
+static void stp_apply(const STP *p, double x1, double y1, double *x2, double *y2) {
+  *x2 = p->scale * (p->r00 * x1 + p->r01 * y1);
+  *y2 = p->scale * (p->r10 * x1 + p->r11 * y1);
+}
+
+/* data.cpp:64-114, shape1 -> shape2.  cv::norm is OpenCV's; the reference binary this file is pinned against is built
+ * with oracle/cvshim's stand-in: the square root of the squares summed in index order.  tmp: 2 * D doubles. */
+static STP stp_calc(const double *shape1, const double *shape2, int L, double *tmp) {
+  STP p = STP_IDENTITY;
+  if (!g_opt.similarity) return p;
+  double x1c = 0., y1c = 0., x2c = 0., y2c = 0.;
+  for (int i = 0; i < L; i++) {
+    x1c += shape1[2 * i]; y1c += shape1[2 * i + 1];
+    x2c += shape2[2 * i]; y2c += shape2[2 * i + 1];
+  }
+  x1c /= L; y1c /= L; x2c /= L; y2c /= L;
+  double *t1 = tmp, *t2 = tmp + 2 * L;
+  for (int i = 0; i < L; i++) {
+    t1[2 * i] = shape1[2 * i] - x1c; t1[2 * i + 1] = shape1[2 * i + 1] - y1c;
+    t2[2 * i] = shape2[2 * i] - x2c; t2[2 * i + 1] = shape2[2 * i + 1] - y2c;
+  }
+  double s1 = 0., s2 = 0.;
+  for (int j = 0; j < 2 * L; j++) s1 += t1[j] * t1[j];
+  for (int j = 0; j < 2 * L; j++) s2 += t2[j] * t2[j];
+  const double scale1 = sqrt(s1), scale2 = sqrt(s2);
+  p.scale = scale1 / scale2;
+  for (int j = 0; j < 2 * L; j++) t1[j] /= scale1;
+  for (int j = 0; j < 2 * L; j++) t2[j] /= scale2;
+  double num = 0., den = 0.;
+  for (int i = 0; i < L; i++) {
+    num += t1[2 * i + 1] * t2[2 * i] - t1[2 * i] * t2[2 * i + 1];
+    den += t1[2 * i] * t2[2 * i] + t1[2 * i + 1] * t2[2 * i + 1];
+  }
+  const double norm = sqrt(num * num + den * den);
+  const double sin_theta = num / norm, cos_theta = den / norm;
+  p.r00 = cos_theta; p.r01 = -sin_theta; p.r10 = sin_theta; p.r11 = cos_theta;
+  return p;
+}
+
 /* data.cpp:18-58 for a scale == 0 node: the view is the win x win patch of the frame at (x, y) */
-static int feature_value(const ModelD *m, size_t n, const double *s, const unsigned char *img, int stride, int x, int y,
-                         int win) {
+static int feature_value(const ModelD *m, size_t n, const double *s, const STP *stp, const unsigned char *img, int stride,
+                         int x, int y, int win) {
   const double *o = m->nd_off + n * 4;
-  /* stp_mc.Apply(offset) with the identity transform: scale*(1*ox + 0*oy) == ox for every finite value */
-  const double x1 = (s[2 * m->nd_lm1[n]] + o[0]) * win;
-  const double y1 = (s[2 * m->nd_lm1[n] + 1] + o[1]) * win;
-  const double x2 = (s[2 * m->nd_lm2[n]] + o[2]) * win;
-  const double y2 = (s[2 * m->nd_lm2[n] + 1] + o[3]) * win;
+  /* stp_mc.Apply(offset): with the identity transform scale*(1*ox + 0*oy) == ox for every finite value */
+  double o1x, o1y, o2x, o2y;
+  stp_apply(stp, o[0], o[1], &o1x, &o1y);
+  stp_apply(stp, o[2], o[3], &o2x, &o2y);
+  const double x1 = (s[2 * m->nd_lm1[n]] + o1x) * win;
+  const double y1 = (s[2 * m->nd_lm1[n] + 1] + o1y) * win;
+  const double x2 = (s[2 * m->nd_lm2[n]] + o2x) * win;
+  const double y2 = (s[2 * m->nd_lm2[n] + 1] + o2y) * win;
   int x1_ = (int)round(x1), y1_ = (int)round(y1), x2_ = (int)round(x2), y2_ = (int)round(y2);
   if (x1_ < 0) x1_ = 0; if (y1_ < 0) y1_ = 0; if (x1_ >= win) x1_ = win - 1; if (y1_ >= win) y1_ = win - 1;
   if (x2_ < 0) x2_ = 0; if (y2_ < 0) y2_ = 0; if (x2_ >= win) x2_ = win - 1; if (y2_ >= win) y2_ = win - 1;
@@ -139,12 +194,13 @@ static int feature_value(const ModelD *m, size_t n, const double *s, const unsig
 }
 
 /* cart.cpp:392-404 (1-based heap there; node j of the heap is stored at j-1 here) */
-static int forward(const ModelD *m, size_t c, const double *s, const unsigned char *img, int stride, int x, int y, int win) {
+static int forward(const ModelD *m, size_t c, const double *s, const STP *stp, const unsigned char *img, int stride, int x,
+                   int y, int win) {
   int node_idx = 1;
   int len = m->depth - 1;
   while (len--) {
     const size_t n = c * m->nn + (node_idx - 1);
-    const int val = feature_value(m, n, s, img, stride, x, y, win);
+    const int val = feature_value(m, n, s, stp, img, stride, x, y, win);
     if (val <= m->nd_th[n]) node_idx = 2 * node_idx;
     else node_idx = 2 * node_idx + 1;
   }
@@ -155,18 +211,22 @@ static int forward(const ModelD *m, size_t c, const double *s, const unsigned ch
 static int validate(const ModelD *m, const unsigned char *img, int stride, int x, int y, int win, double *score_out,
                     double *shape, int *n_out, int *lbf, double *delta) {
   const int D = 2 * m->L;
-  for (int j = 0; j < D; j++) shape[j] = m->mean_shape[j] + 0.0; /* RandomShape with shift 0: mean + x, x = 0 */
+  /* RandomShape: mean + (x, y); test.cpp:17,75 force the shift to 0 */
+  for (int j = 0; j < D; j++) shape[j] = m->mean_shape[j] + ((j & 1) ? g_opt.shift_y : g_opt.shift_x);
   double score = 0;
   int n = 0;
+  STP stp = STP_IDENTITY; /* STParameter stp_mc; (cascador.cpp:176) */
+  double *stp_tmp = g_opt.similarity ? (double *)malloc((size_t)2 * D * sizeof(double)) : NULL;
   for (int t = 0; t < m->stage; t++) {
+    stp = stp_calc(shape, m->mean_shape, m->L, stp_tmp); /* cascador.cpp:180 */
     int offset = 0;
     for (int k = 0; k < m->K; k++) {
       const size_t c = (size_t)t * m->K + k;
-      const int idx = forward(m, c, shape, img, stride, x, y, win);
+      const int idx = forward(m, c, shape, &stp, img, stride, x, y, win);
       score += m->leaf[c * m->nl + idx];
       score = (score - m->cmean[c]) / m->cstd[c];
       n++;
-      if (score < m->cth[c]) { *score_out = score; *n_out = n; return 0; }
+      if (score < m->cth[c]) { *score_out = score; *n_out = n; free(stp_tmp); return 0; }
       lbf[k] = offset + idx;
       offset += m->nl;
     }
@@ -177,16 +237,21 @@ static int validate(const ModelD *m, const unsigned char *img, int stride, int x
       const double *w_ptr = wt + (size_t)lbf[i] * D;
       for (int j = 0; j < D; j++) delta[j] += w_ptr[j];
     }
+    /* stp_mc.Apply(delta_shape, delta_shape), btcart.cpp:422 */
+    for (int j = 0; j < m->L; j++) stp_apply(&stp, delta[2 * j], delta[2 * j + 1], &delta[2 * j], &delta[2 * j + 1]);
     for (int j = 0; j < D; j++) shape[j] += delta[j];
   }
-  for (int k = 0; k <= m->cart; k++) { /* unfinished stage of a training snapshot; empty for a finished model */
+  /* unfinished stage of a training snapshot (empty for a finished model): with the transform of the last finished
+   * stage -- the reference does not recompute it here (cascador.cpp:199-202) */
+  for (int k = 0; k <= m->cart; k++) {
     const size_t c = (size_t)m->stage * m->K + k;
-    const int idx = forward(m, c, shape, img, stride, x, y, win);
+    const int idx = forward(m, c, shape, &stp, img, stride, x, y, win);
     score += m->leaf[c * m->nl + idx];
     score = (score - m->cmean[c]) / m->cstd[c];
     n++;
-    if (score < m->cth[c]) { *score_out = score; *n_out = n; return 0; }
+    if (score < m->cth[c]) { *score_out = score; *n_out = n; free(stp_tmp); return 0; }
   }
+  free(stp_tmp);
   *score_out = score; *n_out = n;
   return 1;
 }

@@ -260,12 +260,21 @@ class RefCpp:
         self.lib.jref_dims(h, d)
         return dict(zip(("T", "K", "L", "depth", "stage", "cart"), d))
 
-    def detect(self, h, img, minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True):
+    def set_shift(self, shift_size=0.0, tick=0):
+        """face.random_shift with the tick that seeds RandomShape's RNG fixed (0: real ticks, shift_size 0 = what
+        src/test.cpp forces); returns the (x, y) the reference's RNG then draws for every window."""
+        self.lib.jref_set_shift.argtypes = [C.c_double, C.c_longlong, C.POINTER(C.c_double)]
+        self.lib.jref_set_shift.restype = None
+        xy = (C.c_double * 2)()
+        self.lib.jref_set_shift(float(shift_size), int(tick), xy)
+        return float(xy[0]), float(xy[1])
+
+    def detect(self, h, img, minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True, similarity=False):
         """JoinCascador::Detect: (rects[n,4], scores[n] f64, shapes[n,2L] f64, stats dict)"""
         a, p, w, hh = _img(img)
         r, s, sh = C.POINTER(C.c_int)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
         st = (C.c_double * 4)()
-        n = self.lib.jref_detect(h, p, w, hh, minimum_size, step, scale, overlap, 1 if nms else 0, 0,
+        n = self.lib.jref_detect(h, p, w, hh, minimum_size, step, scale, overlap, 1 if nms else 0, 1 if similarity else 0,
                                  C.byref(r), C.byref(s), C.byref(sh), st)
         D = 2 * self.dims(h)["L"]
         if n > 0:
@@ -278,13 +287,14 @@ class RefCpp:
                  "cart_gothrough_n": int(st[3])}
         return out + (stats,)
 
-    def trace(self, h, img, minimum_size=20, step=5, scale=1.2):
+    def trace(self, h, img, minimum_size=20, step=5, scale=1.2, similarity=False):
         """Validate on every window in detectMultiScale1's order: (carts evaluated, exit score)"""
         a, p, w, hh = _img(img)
-        n = self.lib.jref_trace(h, p, w, hh, minimum_size, step, scale, 0, None, None, 0)
+        sim = 1 if similarity else 0
+        n = self.lib.jref_trace(h, p, w, hh, minimum_size, step, scale, sim, None, None, 0)
         tn = np.zeros(max(n, 1), np.int32)
         ts = np.zeros(max(n, 1), np.float64)
-        m = self.lib.jref_trace(h, p, w, hh, minimum_size, step, scale, 0, tn.ctypes.data_as(C.POINTER(C.c_int)),
+        m = self.lib.jref_trace(h, p, w, hh, minimum_size, step, scale, sim, tn.ctypes.data_as(C.POINTER(C.c_int)),
                                 ts.ctypes.data_as(C.POINTER(C.c_double)), n)
         assert m == n
         return tn[:n], ts[:n]
@@ -326,6 +336,13 @@ class OracleCpp:
 
     def load(self, path, double=True):
         return self.lib.jcpp_load(os.fsencode(path), 1 if double else 0)
+
+    def set_options(self, similarity=False, shift=(0.0, 0.0)):
+        """face.similarity_transform and the initial shift (x, y) RandomShape adds to the mean shape; process-wide,
+        like the reference's Config singleton.  Defaults = what the shipped config / src/test.cpp run with."""
+        self.lib.jcpp_set_options.argtypes = [C.c_int, C.c_double, C.c_double]
+        self.lib.jcpp_set_options.restype = None
+        self.lib.jcpp_set_options(1 if similarity else 0, float(shift[0]), float(shift[1]))
 
     def release(self, h):
         self.lib.jcpp_free(h)

@@ -80,6 +80,19 @@ void *jref_open(const char *model, const char *run_dir) {
 
 void jref_close(void *h) { delete (JoinCascador *)h; }
 
+// Initial shift (data.cpp:225-236): shift_size as in config.json's face.random_shift, with the tick that seeds
+// RandomShape's RNG fixed so that every window -- and the test -- draws the same (x, y).  tick = 0: real ticks.
+// xy (may be NULL) receives the shift the reference's own RNG then produces.
+void jref_set_shift(double shift_size, long long tick, double *xy) {
+  Config::GetInstance().shift_size = shift_size;
+  cv::shim_fixed_tick() = (cv::int64)tick;
+  if (xy) {
+    cv::RNG rng = cv::RNG(cv::getTickCount());
+    xy[0] = rng.uniform(-shift_size, shift_size);
+    xy[1] = rng.uniform(-shift_size, shift_size);
+  }
+}
+
 void jref_dims(void *h, int *out6) {
   const JoinCascador *jc = (const JoinCascador *)h;
   out6[0] = jc->T; out6[1] = jc->K; out6[2] = jc->landmark_n; out6[3] = jc->tree_depth;
