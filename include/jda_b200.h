@@ -166,13 +166,12 @@ JDA_API int jdaB200DetectMixed(void *cascador, const jdaB200Frame *frames, int n
  * JoinCascador::Detect with fddb.method = 1 (src/jda/cascador.cpp:310-376, 431-477): fixed pixel step, window
  * ladder win = int(win * scale) from fddb.minimum_size, JoinCascador::Validate per window in double precision with
  * round()ed pixel coordinates (data.cpp:18-58), no final score threshold, multimap NMS (cascador.cpp:387-429),
- * results in pick order.  Scope: models whose nodes are all at scale 0 and face.similarity_transform = false (the
- * shipped model and config.json); anything else is refused with an error.  A handle created from a float-flavour
- * file runs the exactly widened values.
- * This is the DETERMINISTIC Validate: every window starts from mean_shape + 0, i.e. DataSet::RandomShape with
- * shift_size = 0 as src/test.cpp:17,75 (test, fddb) force it.  src/live.cpp leaves config.json's random_shift = 0.02
- * in place, a tick-count-seeded shift per window that no two runs of the reference share; that variant is not
- * reproduced. */
+ * results in pick order.  Scope: models whose nodes are all at scale 0 (the shipped model); anything else is refused
+ * with an error.  A handle created from a float-flavour file runs the exactly widened values.
+ * Validate is DETERMINISTIC here: every window starts from mean_shape + (shift_x, shift_y) of the parameters below --
+ * (0, 0) is DataSet::RandomShape with shift_size = 0 as src/test.cpp:17,75 (test, fddb) force it.  src/live.cpp leaves
+ * config.json's random_shift = 0.02 in place, a tick-count-seeded shift per window that no two runs of the reference
+ * share; a caller who wants that behaviour passes the shift of its choice, one per call. */
 typedef struct {
   int n;
   int landmark_n;
@@ -189,6 +188,14 @@ typedef struct {
   double overlap;   /* fddb.overlap      (0.3)                   */
   int nms;          /* fddb.nms          (true)                  */
   int flags;        /* 0, or JDA_B200_NO_STAGE0_SCAN: every window through the double-precision kernel */
+  int similarity_transform; /* face.similarity_transform (config.json: false): offsets and the regressed delta go through
+                               STParameter::Calc(shape, mean_shape) / Apply (data.cpp:64-126), recomputed per stage.
+                               Calc's cv::norm is taken as the square root of the squares summed in index order (the
+                               reference build this is pinned against uses that stand-in; OpenCV is not in the image). */
+  double shift_x, shift_y;  /* the shift DataSet::RandomShape adds to the mean shape (data.cpp:225-236).  The reference
+                               draws it per window from an RNG seeded with the tick count (face.random_shift; forced to 0
+                               by src/test.cpp:17,75): pass the values a run should use, the same for every window.
+                               Non-zero: every window runs through the double-precision kernel (no stage-0 prefilter). */
 } jdaB200CppParams;
 
 /* n_frames equally sized host frames (8-bit gray, stride == width, frame f at frames + f*width*height).

@@ -76,7 +76,8 @@ def run_fddb(c, a):
                    for b, s, p in c.detect_many(frames)]
         else:
             res = c.detect_cpp_many(frames, minimum_size=a.fddb_min, step=a.fddb_step, scale=a.fddb_scale,
-                                    overlap=a.overlap, nms=not a.no_nms)
+                                    overlap=a.overlap, nms=not a.no_nms, similarity=a.similarity_transform,
+                                    shift=tuple(a.shift))
         with open(os.path.join(a.fddb_dir, "result", "fold-%02d-out.txt" % i), "w") as out:
             for path, (rects, scores, _) in zip(names, res):
                 out.write("%s\n%d\n" % (path, len(scores)))                            # test.cpp:153
@@ -108,6 +109,10 @@ def main(argv=None):
     p.add_argument("--fddb-min", type=int, default=20); p.add_argument("--fddb-step", type=int, default=5)
     p.add_argument("--fddb-scale", type=float, default=1.2); p.add_argument("--overlap", type=float, default=0.3)
     p.add_argument("--no-nms", action="store_true")
+    p.add_argument("--similarity-transform", action="store_true", help="config.json face.similarity_transform (C++ detector)")
+    p.add_argument("--shift", type=float, nargs=2, default=(0.0, 0.0), metavar=("X", "Y"),
+                   help="initial shift added to the mean shape (face.random_shift draws one per window in the reference; "
+                        "src/test.cpp forces 0)")
     p = sub.add_parser("fddb")
     p.add_argument("model"); p.add_argument("fddb_dir"); p.add_argument("--float", action="store_true")
     p.add_argument("--c-api", action="store_true", help="jdaDetect semantics instead of JoinCascador::Detect")
@@ -115,6 +120,10 @@ def main(argv=None):
     p.add_argument("--fddb-min", type=int, default=20); p.add_argument("--fddb-step", type=int, default=5)
     p.add_argument("--fddb-scale", type=float, default=1.2); p.add_argument("--overlap", type=float, default=0.3)
     p.add_argument("--no-nms", action="store_true")
+    p.add_argument("--similarity-transform", action="store_true", help="config.json face.similarity_transform (C++ detector)")
+    p.add_argument("--shift", type=float, nargs=2, default=(0.0, 0.0), metavar=("X", "Y"),
+                   help="initial shift added to the mean shape (face.random_shift draws one per window in the reference; "
+                        "src/test.cpp forces 0)")
     a = ap.parse_args(argv)
 
     if a.cmd == "convert":
@@ -143,7 +152,7 @@ def main(argv=None):
     frames = [read_gray(p) for p in a.images]
     if a.cpp:
         res = c.detect_cpp_many(frames, minimum_size=a.fddb_min, step=a.fddb_step, scale=a.fddb_scale, overlap=a.overlap,
-                                nms=not a.no_nms)
+                                nms=not a.no_nms, similarity=a.similarity_transform, shift=tuple(a.shift))
     else:
         res = c.detect_many(frames, scale=a.scale, min_size=a.min_size, max_size=a.max_size, th=a.th)
     out = open(a.fddb_out, "w") if a.fddb_out else sys.stdout

@@ -55,7 +55,8 @@ class ResultF64(C.Structure):
 class CppParams(C.Structure):
     """the fddb.* keys JoinCascador::Detect reads (src/jda/common.cpp:178-188); defaults = model/config.json"""
     _fields_ = [("minimum_size", C.c_int), ("step", C.c_int), ("scale", C.c_double), ("overlap", C.c_double),
-                ("nms", C.c_int), ("flags", C.c_int)]
+                ("nms", C.c_int), ("flags", C.c_int), ("similarity_transform", C.c_int),
+                ("shift_x", C.c_double), ("shift_y", C.c_double)]
 
 
 class FlatResult(C.Structure):
@@ -420,7 +421,8 @@ class Cascador:
             raise RuntimeError("jdaB200DetectMixed failed: " + last_error())
         return self._unpack_results(res, n, unpack)
 
-    def detect_cpp(self, frames, minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True, flags=0):
+    def detect_cpp(self, frames, minimum_size=20, step=5, scale=1.2, overlap=0.3, nms=True, flags=0, similarity=False,
+                   shift=(0.0, 0.0)):
         """jdaB200JoinCascadorDetect: the reference's double-precision C++ detector (JoinCascador::Detect,
         fddb.method = 1).  frames: one [h,w] u8 image or a batch [n,h,w].  Returns (rects[k,4] i32 = x y w h,
         scores[k] f64, shapes[k,2L] f64 in image pixels) -- a list of those for a batch."""
@@ -429,7 +431,8 @@ class Cascador:
         if single:
             a = a[None]
         n, h, w = a.shape
-        prm = CppParams(minimum_size, step, scale, overlap, 1 if nms else 0, flags)
+        prm = CppParams(minimum_size, step, scale, overlap, 1 if nms else 0, flags, 1 if similarity else 0,
+                        float(shift[0]), float(shift[1]))
         res = (ResultF64 * max(n, 1))()
         st = Stats()
         rc = lib().jdaB200JoinCascadorDetect(self._h, C.c_void_p(a.ctypes.data), n, w, h, C.byref(prm), res, C.byref(st))
@@ -469,14 +472,14 @@ class Cascador:
                 out[i] = r
         return out
 
-    def trace_cpp(self, img, minimum_size=20, step=5, scale=1.2):
+    def trace_cpp(self, img, minimum_size=20, step=5, scale=1.2, similarity=False, shift=(0.0, 0.0)):
         """JoinCascador::Validate per window in scan order: (carts evaluated, exit score f64)"""
         a = np.ascontiguousarray(img, np.uint8)
         h, w = a.shape
         nwin = count_windows_cpp(w, h, minimum_size, step, scale)
         tn = np.zeros(max(nwin, 1), np.int32)
         ts = np.zeros(max(nwin, 1), np.float64)
-        prm = CppParams(minimum_size, step, scale, 0.3, 1, 0)
+        prm = CppParams(minimum_size, step, scale, 0.3, 1, 0, 1 if similarity else 0, float(shift[0]), float(shift[1]))
         n = lib().jdaB200JoinCascadorTrace(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, C.byref(prm),
                                            tn.ctypes.data_as(C.POINTER(C.c_int)), ts.ctypes.data_as(C.POINTER(C.c_double)))
         if n < 0:

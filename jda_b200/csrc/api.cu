@@ -1366,8 +1366,10 @@ bool ensure_model64_impl(Context *c) {
   CU_OK(cudaMemcpy(c->d_cart64, m.cart3.data(), m.cart3.size() * 8, cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(c->d_w64, m.w.data(), m.w.size() * 8, cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(c->d_mean64, m.mean_shape.data(), m.mean_shape.size() * 8, cudaMemcpyHostToDevice));
-  CU_OK(cudaFuncSetAttribute(k4_cascade_f64, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CU_OK(cudaFuncSetAttribute(k4_cascade_f64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(K4_WARPS * (kMaxDim * 8 + 4096))));  // largest K (see ctx_init: the attribute is per device)
+  CU_OK(cudaFuncSetAttribute(k4_cascade_f64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(K4_WARPS * (kMaxDim * 8 + 4096))));
   return true;
 }
 
@@ -1465,7 +1467,9 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
   R.leaf_pad = leaf_bytes(m.K);
   R.scan_K = m.K;  // (R.t_run stays 0: the prefilter's survivors are re-evaluated from cart 0, no leaf records needed)
   R.total_windows = st.windows;
-  R.use_scan = c->filter64_ok && !(prm.flags & JDA_B200_NO_STAGE0_SCAN) && !tracing;
+  // the prefilter's tables are built for the mean shape itself: a shifted initial shape goes through the double kernel
+  // from cart 0 (the similarity transform of stage 0 is the identity for shape == mean shape, bit for bit)
+  R.use_scan = c->filter64_ok && !(prm.flags & JDA_B200_NO_STAGE0_SCAN) && !tracing && prm.shift_x == 0.0 && prm.shift_y == 0.0;
   cudaStream_t s = R.s;
   if (timing) CU_OK(cudaEventRecord(c->sc->ev[0], s));
   if (!stage_frames(R, frames)) return false;
@@ -1507,7 +1511,9 @@ bool run_device64(Context *c, const unsigned char *frames, int n_frames, int wid
     Q.work_counter = c->sc->d_counters + kCntWork;
     Q.trace_n = tracing ? c->d_trace_n64.p : nullptr;
     Q.trace_s = tracing ? c->d_trace_s64.p : nullptr;
-    k4_cascade_f64<<<c->sm_count * 8, K4_WARPS * 32, K4_WARPS * (kMaxDim * 8 + ((m.K + 15) & ~15)), s>>>(Q);
+    Q.similarity = prm.similarity_transform ? 1 : 0; Q.shift_x = prm.shift_x; Q.shift_y = prm.shift_y;
+    if (Q.similarity) k4_cascade_f64<true><<<c->sm_count * 8, K4_WARPS * 32, K4_WARPS * (kMaxDim * 8 + ((m.K + 15) & ~15)), s>>>(Q);
+    else k4_cascade_f64<false><<<c->sm_count * 8, K4_WARPS * 32, K4_WARPS * (kMaxDim * 8 + ((m.K + 15) & ~15)), s>>>(Q);
     CU_OK(cudaGetLastError());
     st.cascade_launches++;
     if (timing) CU_OK(cudaEventRecord(c->sc->ev[4], s));

@@ -42,6 +42,14 @@ struct Cascade64Params {
   unsigned *work_counter;
   int *trace_n;     // dense mode, optional: carts evaluated per window
   double *trace_s;  //                       exit score per window
+  // face.similarity_transform (data.cpp:64-126) and the initial shift DataSet::RandomShape adds (data.cpp:225-236)
+  int similarity;
+  double shift_x, shift_y;
+};
+
+// STParameter (include/jda/data.hpp:18-50); the default is the identity
+struct STP64 {
+  double scale, r00, r01, r10, r11;
 };
 
 constexpr int kHit64Header = 4;
@@ -57,6 +65,50 @@ __device__ __forceinline__ int coord_f64(double s, double o, double fwin, int wi
   return min(max(c, 0), win - 1);
 }
 
+// STParameter::Apply (data.hpp:42-45)
+__device__ __forceinline__ void stp_apply(const STP64 &p, double x1, double y1, double &x2, double &y2) {
+  x2 = __dmul_rn(p.scale, __dadd_rn(__dmul_rn(p.r00, x1), __dmul_rn(p.r01, y1)));
+  y2 = __dmul_rn(p.scale, __dadd_rn(__dmul_rn(p.r10, x1), __dmul_rn(p.r11, y1)));
+}
+
+// STParameter::Calc(shape, mean_shape) (data.cpp:64-114), every lane of the warp for itself (the sums run over the
+// landmarks in index order: there is nothing to split).  The centred / normalised copies the reference keeps in two
+// temporaries are recomputed where they are used -- the same operations on the same values.  cv::norm = the square
+// root of the squares summed in index order (what the pinned reference build's stand-in does; OpenCV's own
+// accumulation order is third-party code that is not under /root/reference).
+__device__ __forceinline__ STP64 stp_calc(const double *s1, const double *s2, int L) {
+  double x1c = 0., y1c = 0., x2c = 0., y2c = 0.;
+  for (int i = 0; i < L; i++) {
+    x1c = __dadd_rn(x1c, s1[2 * i]); y1c = __dadd_rn(y1c, s1[2 * i + 1]);
+    x2c = __dadd_rn(x2c, __ldg(s2 + 2 * i)); y2c = __dadd_rn(y2c, __ldg(s2 + 2 * i + 1));
+  }
+  const double fl = (double)L;
+  x1c = __ddiv_rn(x1c, fl); y1c = __ddiv_rn(y1c, fl); x2c = __ddiv_rn(x2c, fl); y2c = __ddiv_rn(y2c, fl);
+  double q1 = 0., q2 = 0.;
+  for (int i = 0; i < L; i++) {
+    const double ax = __dsub_rn(s1[2 * i], x1c), ay = __dsub_rn(s1[2 * i + 1], y1c);
+    const double bx = __dsub_rn(__ldg(s2 + 2 * i), x2c), by = __dsub_rn(__ldg(s2 + 2 * i + 1), y2c);
+    q1 = __dadd_rn(q1, __dmul_rn(ax, ax)); q1 = __dadd_rn(q1, __dmul_rn(ay, ay));
+    q2 = __dadd_rn(q2, __dmul_rn(bx, bx)); q2 = __dadd_rn(q2, __dmul_rn(by, by));
+  }
+  const double scale1 = __dsqrt_rn(q1), scale2 = __dsqrt_rn(q2);
+  STP64 p;
+  p.scale = __ddiv_rn(scale1, scale2);
+  double num = 0., den = 0.;
+  for (int i = 0; i < L; i++) {
+    const double ax = __ddiv_rn(__dsub_rn(s1[2 * i], x1c), scale1), ay = __ddiv_rn(__dsub_rn(s1[2 * i + 1], y1c), scale1);
+    const double bx = __ddiv_rn(__dsub_rn(__ldg(s2 + 2 * i), x2c), scale2), by = __ddiv_rn(__dsub_rn(__ldg(s2 + 2 * i + 1), y2c), scale2);
+    num = __dadd_rn(num, __dsub_rn(__dmul_rn(ay, bx), __dmul_rn(ax, by)));
+    den = __dadd_rn(den, __dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)));
+  }
+  const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(num, num), __dmul_rn(den, den)));
+  const double sin_theta = __ddiv_rn(num, norm), cos_theta = __ddiv_rn(den, norm);
+  p.r00 = cos_theta; p.r01 = -sin_theta; p.r10 = sin_theta; p.r11 = cos_theta;
+  return p;
+}
+
+// SIM: face.similarity_transform (P.similarity); the shipped configuration runs the instantiation without it
+template <bool SIM>
 __global__ void __launch_bounds__(K4_WARPS * 32) k4_cascade_f64(const __grid_constant__ Cascade64Params P) {
   extern __shared__ __align__(16) uint8_t smem4[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -98,8 +150,11 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_cascade_f64(const __grid_con
     const uint8_t *po = P.frames + (size_t)frame * P.frame_stride + (size_t)y * P.pitch + x;
 
     __syncwarp();
-    for (int i = lane; i < D; i += 32) shape[i] = __dadd_rn(P.mean_shape[i], 0.0);  // RandomShape with a zero shift
+    // RandomShape: mean + (x, y); src/test.cpp:17,75 run with a zero shift
+    for (int i = lane; i < D; i += 32) shape[i] = __dadd_rn(P.mean_shape[i], (i & 1) ? P.shift_y : P.shift_x);
     __syncwarp();
+    [[maybe_unused]] STP64 stp;  // STParameter stp_mc; (cascador.cpp:176)
+    stp.scale = 1.0; stp.r00 = 1.0; stp.r01 = 0.0; stp.r10 = 0.0; stp.r11 = 1.0;
 
     double score = 0.0;
     int n_eval = 0;
@@ -109,6 +164,8 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_cascade_f64(const __grid_con
     for (int t = 0; t < n_pass && !rejected; t++) {
       const bool full = t < P.stage;
       const int kend = full ? P.K : P.cart_last + 1;
+      // cascador.cpp:180 -- the unfinished stage keeps the transform of the last finished one (cascador.cpp:199-202)
+      if (SIM && full) stp = stp_calc(shape, P.mean_shape, P.L);
       for (int kc = 0; kc < kend && !rejected; kc += 32 * K4_G) {
         double ls[K4_G], cth[K4_G], cmean[K4_G], cstd[K4_G];
         int idx[K4_G];
@@ -128,8 +185,12 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_cascade_f64(const __grid_con
           for (int g = 0; g < K4_G; g++) {
             const NodeRecD *n = nd[g] + idx[g];
             const int4 a = __ldg(reinterpret_cast<const int4 *>(n));            // scale, lm1, lm2, th
-            const double2 o1 = __ldg(reinterpret_cast<const double2 *>(n) + 1);  // o1x, o1y
-            const double2 o2 = __ldg(reinterpret_cast<const double2 *>(n) + 2);  // o2x, o2y
+            double2 o1 = __ldg(reinterpret_cast<const double2 *>(n) + 1);  // o1x, o1y
+            double2 o2 = __ldg(reinterpret_cast<const double2 *>(n) + 2);  // o2x, o2y
+            if (SIM) {  // stp_mc.Apply(offset), data.cpp:43-44 (the identity returns its input exactly)
+              stp_apply(stp, o1.x, o1.y, o1.x, o1.y);
+              stp_apply(stp, o2.x, o2.y, o2.x, o2.y);
+            }
             const int x1 = coord_f64(shape[a.y], o1.x, fwin, win), y1 = coord_f64(shape[a.y + 1], o1.y, fwin, win);
             const int x2 = coord_f64(shape[a.z], o2.x, fwin, win), y2 = coord_f64(shape[a.z + 1], o2.y, fwin, win);
             const int p1 = __ldg(po + (size_t)y1 * P.pitch + x1);
@@ -167,22 +228,25 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_cascade_f64(const __grid_con
       }
       if (rejected || !full) break;
       __syncwarp();
-      // btcart.cpp:407-424: delta = sum of the K selected rows, accumulated from zero in cart order; shape += delta
+      // btcart.cpp:407-424: delta = sum of the K selected rows, accumulated from zero in cart order; the transform is
+      // applied to it landmark by landmark; shape += delta.  A lane owns a landmark (both coordinates).
       const double *wt = P.w + (size_t)t * P.K * kLeaves * D;
-      for (int i = lane; i < D; i += 32) {
-        double delta = 0.0;
-        for (int k0 = 0; k0 < P.K; k0 += 8) {
-          double v[8];
+      for (int j = lane; j < P.L; j += 32) {
+        double dx = 0.0, dy = 0.0;
+        for (int k0 = 0; k0 < P.K; k0 += 4) {
+          double2 v[4];  // (four 16-byte row loads in flight: the bytes of round 1's eight 8-byte ones)
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
+          for (int u = 0; u < 4; u++) {
             const int k = min(k0 + u, P.K - 1);
-            v[u] = __ldg(wt + (size_t)(k * kLeaves + leafs[k]) * D + i);
+            v[u] = __ldg(reinterpret_cast<const double2 *>(wt + (size_t)(k * kLeaves + leafs[k]) * D) + j);
           }
 #pragma unroll
-          for (int u = 0; u < 8; u++)
-            if (k0 + u < P.K) delta = __dadd_rn(delta, v[u]);
+          for (int u = 0; u < 4; u++)
+            if (k0 + u < P.K) { dx = __dadd_rn(dx, v[u].x); dy = __dadd_rn(dy, v[u].y); }
         }
-        shape[i] = __dadd_rn(shape[i], delta);
+        if (SIM) stp_apply(stp, dx, dy, dx, dy);
+        shape[2 * j] = __dadd_rn(shape[2 * j], dx);
+        shape[2 * j + 1] = __dadd_rn(shape[2 * j + 1], dy);
       }
       __syncwarp();
     }

@@ -11,9 +11,10 @@
  * compares this file with that binary bit for bit: JoinCascador::Detect (faces, scores, landmarks,
  * patch / cart statistics, with and without NMS), Validate on every window (carts evaluated, exit
  * score), the shipped model, full-precision synthetic models and training snapshots.
- * Scope of the pin = scope of this file: fddb.method = 1, every node at scale == 0,
- * face.similarity_transform = false (both true for the shipped model and config), shift_size = 0
- * (src/test.cpp:17,75).  Models with scale != 0 nodes sample cv::resize'd planes
+ * Scope of the pin = scope of this file: fddb.method = 1, every node at scale == 0; face.similarity_transform on or
+ * off and any initial shift (jcpp_set_options; the reference build's RandomShape seed can be fixed for the
+ * comparison) -- with cv::norm inside STParameter::Calc being the stand-in's index-order sum of squares, OpenCV's own
+ * accumulation order is not pinned.  Models with scale != 0 nodes sample cv::resize'd planes
  * (cascador.cpp:330-331) -- OpenCV's arithmetic, third party, not under /root/reference: this file
  * refuses them, and the stand-in's resize is not OpenCV's.
  *
@@ -21,13 +22,14 @@
  *   model layout (double flavour)          src/jda/cascador.cpp:126-164, src/jda/cart.cpp:406-428
  *   window ladder / scan loops             src/jda/cascador.cpp:310-376   (detectMultiScale1)
  *   per-window cascade                     src/jda/cascador.cpp:166-211   (JoinCascador::Validate)
- *   initial shape                          src/jda/data.cpp:225-236       (RandomShape with shift_size = 0,
- *                                                                          as test.cpp:17,75 force it)
+ *   initial shape                          src/jda/data.cpp:225-236       (RandomShape: mean + (x, y); (0, 0) is what
+ *                                                                          test.cpp:17,75 force)
  *   tree walk                              src/jda/cart.cpp:392-404       (Cart::Forward, 1-based heap)
  *   pixel-difference feature               src/jda/data.cpp:18-58         (round(), per-view width, clamp:
  *                                                                          include/jda/common.hpp:227-232)
- *   similarity transform                   src/jda/data.cpp:64-70         (identity: config.json face.similarity_transform=false;
- *                                                                          Apply with the identity returns its input exactly)
+ *   similarity transform                   src/jda/data.cpp:64-126, include/jda/data.hpp:42-45   (STParameter::Calc / Apply;
+ *                                                                          config.json ships face.similarity_transform = false:
+ *                                                                          the identity, whose Apply returns its input exactly)
  *   global regression                      src/jda/btcart.cpp:407-424     (delta accumulated from 0, then shape += delta)
  *   nms                                    src/jda/cascador.cpp:387-429   (multimap by score, erase IoU > overlap)
  *   top level + relocation                 src/jda/cascador.cpp:431-477

@@ -235,3 +235,56 @@ def test_fddb_runner_layout(tmp_path, ocpp, ocpp_shipped):
     assert main(["fddb", SHIPPED_F32, str(root), "--float", "--folds", "1", "--c-api"]) == 0
     lines = (root / "result" / "fold-01-out.txt").read_text().split("\n")
     assert lines[0] == "2002/07/img_1" and int(lines[1]) >= 2 and len(lines[2].split()) == 5
+
+
+# ---- face.similarity_transform and the initial shift ------------------------------------
+
+@pytest.mark.parametrize("similarity,shift", [(True, (0.0, 0.0)), (False, (0.013, -0.0071)), (True, (-0.02, 0.0175))],
+                         ids=["similarity", "shift", "both"])
+def test_similarity_transform_and_initial_shift(casc, ocpp, ocpp_shipped, similarity, shift):
+    """STParameter::Calc / Apply per stage and mean_shape + (x, y) as the initial shape, CUDA path vs the restatement
+    (which tests/test_oracle_cpp.py pins to the reference binary): raw hits, NMS, a batch, the per-window trace.
+    With a zero shift the float32 prefilter stays on (the stage-0 transform of shape == mean shape is the identity, bit
+    for bit); a shifted initial shape sends every window through the double kernel."""
+    ocpp.set_options(similarity=similarity, shift=shift)
+    try:
+        kw = dict(similarity=similarity, shift=shift)
+        for img, okw in ((synth.face_canvas(), dict()), (synth.facemix_frame(11), dict(nms=False)),
+                         (synth.facemix_frame(12, 333, 251), dict(minimum_size=30, step=3, scale=1.3, overlap=0.5))):
+            _same(casc.detect_cpp(img, **okw, **kw), ocpp.detect(ocpp_shipped, img, **okw))
+            assert casc.last_stats["scan_launches"] == (1 if shift == (0.0, 0.0) else 0)
+        frames = synth.make_frames("facemix", 6, 320, 240, seed0=70)
+        for got, f in zip(casc.detect_cpp(frames, nms=False, **kw), frames):
+            _same(got, ocpp.detect(ocpp_shipped, f, nms=False))
+        img = synth.facemix_frame(21, 200, 150)
+        tn, ts = casc.trace_cpp(img, **kw)
+        on, os_ = ocpp.trace(ocpp_shipped, img)
+        np.testing.assert_array_equal(tn, on)
+        np.testing.assert_array_equal(_bits(ts), _bits(os_))
+        assert (on > 1080).any()                                  # windows that went through two regressions
+    finally:
+        ocpp.set_options()
+    # and the options do change the answer
+    a = casc.detect_cpp(synth.face_canvas(), nms=False)
+    b = casc.detect_cpp(synth.face_canvas(), nms=False, similarity=similarity, shift=shift)
+    assert len(a[1]) != len(b[1]) or not np.array_equal(a[2], b[2])
+
+
+def test_similarity_and_shift_against_the_reference_cpp_binary(casc, tmp_path):
+    """the same, CUDA path vs the reference's own binary with RandomShape's seed fixed (no restatement in between)"""
+    import os
+    from oracle import pyoracle
+    if not os.path.exists(pyoracle.REF_CPP_SO):
+        pytest.skip("oracle/_ref_cpp/libjda_ref_cpp.so not built")
+    ref = pyoracle.RefCpp()
+    hr = ref.load(synth.widen_f32_model(SHIPPED_F32, str(tmp_path / "wide.model")))
+    try:
+        xy = ref.set_shift(0.02, tick=987654321)
+        assert xy != (0.0, 0.0)
+        for img, kw in ((synth.face_canvas(), dict()), (synth.facemix_frame(3, 320, 240), dict(nms=False))):
+            _same(casc.detect_cpp(img, similarity=True, shift=xy, **kw), ref.detect(hr, img, similarity=True, **kw))
+        xy = ref.set_shift(0.0, 0)
+        _same(casc.detect_cpp(synth.face_canvas(), similarity=True), ref.detect(hr, synth.face_canvas(), similarity=True))
+    finally:
+        ref.set_shift(0.0, 0)
+        ref.release(hr)

@@ -8,8 +8,9 @@ JoinCascador::Detect (faces, scores, landmarks, patch and cart statistics), the 
 every window (carts evaluated, exit score) -- shipped model, full-precision synthetic models, training snapshots whose
 header stops inside a stage.  Also kept: the independent restatements of its pieces (multimap NMS, window ladder, a
 from-scratch Python Validate) and the error bound that lets the float32 scan kernel prefilter stage 0 of the double path.
-Scope of the pin: fddb.method = 1, models without scale != 0 nodes, face.similarity_transform = false, shift_size = 0
-(src/test.cpp:17,75) -- what runs through cv::resize is OpenCV's arithmetic, which the stand-in does not reproduce.
+Scope of the pin: fddb.method = 1, models without scale != 0 nodes; face.similarity_transform on and off, zero and
+seed-fixed non-zero initial shifts (the last test of this file) -- what runs through cv::resize is OpenCV's arithmetic,
+which the stand-in does not reproduce, and cv::norm inside STParameter::Calc is the stand-in's index-order sum.
 """
 import numpy as np
 import pytest
@@ -362,3 +363,47 @@ def test_second_independent_restatement_agrees(ocpp, ocpp_shipped):
         assert (x, y, win) == (r[0], r[1], r[2])
         want = shape.copy(); want[0::2] = x + shape[0::2] * win; want[1::2] = y + shape[1::2] * win
         np.testing.assert_array_equal(want.view(np.uint64), sh.view(np.uint64))
+
+
+# ---- face.similarity_transform and a non-zero initial shift -------------------------------
+
+@pytest.mark.parametrize("similarity,shift", [(True, 0.0), (False, 0.02), (True, 0.02)], ids=["similarity", "shift", "both"])
+def test_similarity_transform_and_shift_pinned_to_reference(ocpp, ocpp_shipped, refcpp, wide_shipped, similarity, shift):
+    """STParameter::Calc / Apply (data.cpp:64-126: offsets and the regressed delta go through the transform that maps
+    the current shape onto the mean shape) and DataSet::RandomShape's shift (data.cpp:225-236), restatement vs the
+    reference binary, bit for bit: Detect (raw + NMS) and Validate on every window.  The reference seeds the shift's RNG
+    with the tick count for every window; the stand-in's getTickCount can be fixed, and the restatement is given the
+    (x, y) the reference's own RNG then draws.  cv::norm inside Calc is the stand-in's (squares summed in index order):
+    OpenCV's own accumulation order is not pinned by this."""
+    hr = refcpp.load(wide_shipped)
+    xy = refcpp.set_shift(shift, tick=123456789 if shift else 0)
+    try:
+        assert (xy == (0.0, 0.0)) == (shift == 0.0) and all(abs(v) <= shift for v in xy)
+        ocpp.set_options(similarity=similarity, shift=xy)
+        plain = None
+        for name in ("faces", "facemix"):
+            img = PIN_FRAMES[name]()
+            for kw in (dict(), dict(minimum_size=30, step=7, scale=1.3, nms=False)):
+                rr, rs, rsh, st = refcpp.detect(hr, img, similarity=similarity, **kw)
+                orr, os_, osh, carts = ocpp.detect(ocpp_shipped, img, **kw)
+                np.testing.assert_array_equal(rr, orr)
+                _same64(rs, os_)
+                _same64(rsh, osh)
+                assert len(rs) > 0 or name != "faces"
+            if name == "faces":
+                plain = (rs, rsh)
+        img = synth.facemix_frame(11, 200, 150)
+        rn, rsc = refcpp.trace(hr, img, similarity=similarity)
+        on, osc = ocpp.trace(ocpp_shipped, img)
+        np.testing.assert_array_equal(rn, on)
+        _same64(rsc, osc)
+        assert (on > 540).any()
+        # the options do change the numbers: against the plain run of the same frame some landmark differs
+        ocpp.set_options()
+        refcpp.set_shift(0.0, 0)
+        _, s0, sh0, _ = ocpp.detect(ocpp_shipped, PIN_FRAMES["faces"](), minimum_size=30, step=7, scale=1.3, nms=False)
+        assert len(s0) != len(plain[0]) or not np.array_equal(sh0, plain[1])
+    finally:
+        ocpp.set_options()
+        refcpp.set_shift(0.0, 0)
+        refcpp.release(hr)
