@@ -8,8 +8,10 @@
 //   nms                                     src/jda/cascador.cpp:387-429 (multimap by score)
 //   relocation                              src/jda/cascador.cpp:462-474
 //
-// Scope: every node at scale == 0 and face.similarity_transform = false (the shipped model and config); other
-// models sample cv::resize'd planes whose arithmetic is OpenCV's (third party, unpinned) and are refused.
+// Scope: every node at scale == 0 (the shipped model); other models sample cv::resize'd planes whose arithmetic is
+// OpenCV's (third party, unpinned) and are refused.  face.similarity_transform and the initial shift live in the kernel
+// (kernels_f64.cuh); the stage-0 tables below are built for the mean shape and the identity transform, which is what
+// stage 0 sees whenever the shift is zero.
 #pragma once
 #include <algorithm>
 #include <cmath>
