@@ -28,7 +28,7 @@ except Exception as e:
 PY
 }
 # (GPU-minutes are charged per GPU of the box: CFG4_NS / CFG5_NS / VGA_NS trim the sweep)
-for n in ${CFG4_NS:-1 2 4 8}; do [ $n -le $maxn ] && run cfg4 $n --steps 3 --warmup 3; done
-for n in ${CFG5_NS:-8 4 2 1}; do [ $n -le $maxn ] && run cfg5 $n --steps 1 --warmup 3; done
-for n in ${VGA_NS:-$maxn 2}; do [ $n -le $maxn ] && run vga $n --steps 10 --warmup 3 --no-breakdown; done
+for n in ${CFG4_NS-1 2 4 8}; do [ $n -le $maxn ] && run cfg4 $n --steps 3 --warmup 3; done
+for n in ${CFG5_NS-8 4 2 1}; do [ $n -le $maxn ] && run cfg5 $n --steps 1 --warmup 3; done
+for n in ${VGA_NS-$maxn 2}; do [ $n -le $maxn ] && run vga $n --steps 10 --warmup 3 --no-breakdown; done
 true
