@@ -631,14 +631,15 @@ def main():
         nthr, nfr = 32, min(B, 512)
         ptrs = [fr[i].ctypes.data_as(C.POINTER(C.c_ubyte)) for i in range(nfr)]
 
-        def one(i):
-            L_.jdaResultRelease(L_.jdaDetect(c._h, ptrs[i], W, H, ARGS["scale"], 0.1, ARGS["min_size"], ARGS["max_size"], ARGS["th"]))
+        def worker(t):      # a host thread with its own share of the frames, one frame per call
+            for i in range(t, nfr, nthr):
+                L_.jdaResultRelease(L_.jdaDetect(c._h, ptrs[i], W, H, ARGS["scale"], 0.1, ARGS["min_size"], ARGS["max_size"], ARGS["th"]))
         with ThreadPoolExecutor(nthr) as ex:
-            list(ex.map(one, range(nfr)))          # warm-up
+            list(ex.map(worker, range(nthr)))      # warm-up
             c0 = c.coalescing_stats()
             t0 = time.perf_counter()
             for _ in range(3):
-                list(ex.map(one, range(nfr)))
+                list(ex.map(worker, range(nthr)))
             dt = time.perf_counter() - t0
             c1 = c.coalescing_stats()
         threads_fig = {"value": 3 * nfr * WINDOWS_PER_FRAME / dt, "unit": "windows/s", "host_threads": nthr,

@@ -707,6 +707,7 @@ struct Run {
   size_t hq_stride;
   size_t eager;        // hit records that travel with the counters (collect_start)
   bool async;          // submitted batch: its copies must not queue behind the batch before it
+  bool mixed_staged;   // mixed-size batch from pageable host memory: chunks are repacked into the pinned staging area first
   bool one_chunk;      // submitted while the batch before it is still running: the whole copy hides under that batch, so
                        // the scan is ONE launch (every chunk's launch ends in a tail of half-idle SMs)
   size_t cap_surv, cap_hit;  // queue capacities the kernels of this attempt were launched with
@@ -724,19 +725,46 @@ bool copy_mixed_chunk(Run &R, int ch) {
   if (ch >= R.nchunks || ch < R.chunks_copied) return true;
   const int f0 = chunk_begin(b.n_frames, ch, R.nchunks, c->tune.even_chunks), f1 = chunk_begin(b.n_frames, ch + 1, R.nchunks, c->tune.even_chunks);
   const UnpackFrame *tab = c->sc->h_unpack.data();
+  // runs of frames that are contiguous in host memory (and therefore in the staging area): {first frame, bytes}
+  std::vector<std::pair<int, size_t>> runs;
   int run0 = f0;
   for (int f = f0; f <= f1; f++) {
-    // [run0, f) is a run of frames that are contiguous in host memory (and therefore in the staging area)
     const bool extend = f < f1 && f > run0 && tab[f].src_off == tab[f - 1].src_off + frame_bytes(R.mixed[f - 1]) &&
                         R.mixed[f].data == R.mixed[f - 1].data + frame_bytes(R.mixed[f - 1]);
     if (extend) continue;
     if (f > run0) {
       const size_t bytes = tab[f - 1].src_off + frame_bytes(R.mixed[f - 1]) - tab[run0].src_off;
-      if (bytes > 0)
-        CU_OK(cudaMemcpyAsync(c->sc->d_packed.p + tab[run0].src_off, R.mixed[run0].data, bytes, cudaMemcpyHostToDevice,
-                              c->copy_stream));
+      if (bytes > 0) runs.push_back({run0, bytes});
     }
     run0 = f;
+  }
+  if (R.mixed_staged && !runs.empty()) {
+    // pageable frames (separately malloc'd images, numpy arrays): a few host threads copy the runs into the pinned
+    // staging area at their packed offsets, then the chunk goes across in ONE asynchronous copy -- the driver would
+    // stage every frame through its bounce buffer on the calling thread
+    uint8_t *hs = c->sc->h_stage;
+    const jdaB200Frame *mixed = R.mixed;
+    size_t total = 0;
+    for (const auto &r : runs) total += r.second;
+    auto work = [&runs, tab, hs, mixed](size_t i0, size_t i1) {
+      for (size_t i = i0; i < i1; i++) memcpy(hs + tab[runs[i].first].src_off, mixed[runs[i].first].data, runs[i].second);
+    };
+    const unsigned hc = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>(std::min<unsigned>(8u, hc ? hc / 2 : 1u), runs.size());
+    if (total < ((size_t)2 << 20) || nt < 2) {
+      work(0, runs.size());
+    } else {
+      std::vector<std::thread> th;
+      for (size_t i = 1; i < nt; i++) th.emplace_back(work, runs.size() * i / nt, runs.size() * (i + 1) / nt);
+      work(0, runs.size() / nt);
+      for (auto &t : th) t.join();
+    }
+    const size_t o0 = tab[runs.front().first].src_off, o1 = tab[runs.back().first].src_off + runs.back().second;
+    CU_OK(cudaMemcpyAsync(c->sc->d_packed.p + o0, hs + o0, o1 - o0, cudaMemcpyHostToDevice, c->copy_stream));
+  } else {
+    for (const auto &r : runs)
+      CU_OK(cudaMemcpyAsync(c->sc->d_packed.p + tab[r.first].src_off, R.mixed[r.first].data, r.second, cudaMemcpyHostToDevice,
+                            c->copy_stream));
   }
   if (f1 > f0) {
     dim3 grid((b.height + 7) / 8, f1 - f0);
@@ -822,6 +850,27 @@ bool stage_frames(Run &R, const unsigned char *frames) {
       off += frame_bytes(fr);
     }
     if (!c->sc->d_packed.ensure(off + 16) || !c->sc->d_unpack.ensure(b.n_frames)) return false;
+    {  // pageable sources (judged by the first frame that has data) go through the pinned staging area
+      R.mixed_staged = false;
+      const unsigned char *first = nullptr;
+      for (int f = 0; f < b.n_frames && !first; f++)
+        if (frame_bytes(R.mixed[f]) > 0) first = R.mixed[f].data;
+      cudaPointerAttributes pa;
+      const bool pageable = first && (cudaPointerGetAttributes(&pa, first) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered);
+      cudaGetLastError();
+      if (pageable && off + 16 > c->sc->h_stage_cap) {
+        uint8_t *bigger = nullptr;
+        const size_t want = off + 16 + (off >> 3);
+        if (cudaMallocHost(&bigger, want) == cudaSuccess) {
+          host_free(c->sc->h_stage);
+          c->sc->h_stage = bigger;
+          c->sc->h_stage_cap = want;
+        } else {
+          cudaGetLastError();
+        }
+      }
+      R.mixed_staged = pageable && off + 16 <= c->sc->h_stage_cap;
+    }
     CU_OK(cudaMemcpyAsync(c->sc->d_unpack.p, c->sc->h_unpack.data(), (size_t)b.n_frames * sizeof(UnpackFrame), cudaMemcpyHostToDevice,
                           c->copy_stream));
     R.chunks_copied = 0;
