@@ -119,6 +119,10 @@ struct Tuning {
   bool no_chunks = false;         // JDA_B200_NO_CHUNKS (test hook)
   bool tiny_queues = false;       // JDA_B200_TINY_QUEUES (test hook: start with queues that overflow)
   bool old_regress = false;       // JDA_B200_OLD_REGRESS: the regression gather through k3_stage0 (round 1 kernel) instead of k3_regress (A/B)
+  long long stage_min_windows = 60000000;  // JDA_B200_STAGE_MIN_WINDOWS: batches with fewer candidate windows take k3_cascade
+                                  // for stages >= 1 (ten small launches are pure latency on a small survivor list:
+                                  // 16 VGA frames 0.73 vs 0.37 ms, 256 frames 1.50 vs 1.41, 512 frames 2.26 vs 2.47;
+                                  // profiles/r3d_small_batch.txt)
   bool no_stage_kernels = false;  // JDA_B200_NO_STAGE_KERNELS: stages >= 1 through k3_cascade (one warp per survivor) as in round 1 (A/B)
   double level_weight_exp = 1.0;  // JDA_B200_LEVEL_WEIGHT_EXP (r1q: scan -1.7 % against flat weights)
   std::string sched;              // JDA_B200_SCHED="4,8,16,...": phase ends of k2_scan
@@ -145,6 +149,7 @@ Tuning read_tuning() {
   if (const char *e = getenv("JDA_B200_PITCH_EXTRA")) t.pitch_extra = e;
   t.even_chunks = getenv("JDA_B200_EVEN_CHUNKS") != nullptr;
   t.no_stage_kernels = getenv("JDA_B200_NO_STAGE_KERNELS") != nullptr;
+  if (const char *e = getenv("JDA_B200_STAGE_MIN_WINDOWS")) t.stage_min_windows = atoll(e);
   t.old_regress = getenv("JDA_B200_OLD_REGRESS") != nullptr;
   t.no_chunks = getenv("JDA_B200_NO_CHUNKS") != nullptr;
   if (const char *e = getenv("JDA_B200_TINY_QUEUES")) t.tiny_queues = atoi(e) != 0;
@@ -1114,10 +1119,12 @@ bool launch_cascade(Run &R) {
     Q.trace_leaf = (R.trace->leaf && R.trace->w1 > R.trace->w0) ? c->d_trace_leaf.p : nullptr;
     Q.leaf_w0 = R.trace->w0; Q.leaf_w1 = R.trace->w1; Q.leaf_stride = R.leaf_stride;
   }
-  // Batches: stages >= 1 one at a time (kernels_stages.cuh) -- the stage's tables in shared memory, the running scores
-  // replayed with lane = survivor.  One frame / dense mode / other tree depths: one warp per window through k3_cascade.
+  // Large batches: stages >= 1 one at a time (kernels_stages.cuh) -- the stage's tables in shared memory, the running
+  // scores replayed with lane = survivor.  Small batches / one frame / dense mode / other tree depths: one warp per
+  // window through k3_cascade.
   const int walk_warps = k3w_warps(m.K, R.tracing);
-  if (R.staged0 && m.depth == kDepth && walk_warps > 0 && !c->tune.no_stage_kernels) {
+  if (R.staged0 && m.depth == kDepth && walk_warps > 0 && !c->tune.no_stage_kernels &&
+      R.total_windows >= c->tune.stage_min_windows) {
     if (!c->sc->d_stage_list[0].ensure(c->surv_cap) || !c->sc->d_stage_list[1].ensure(c->surv_cap)) return false;
     WalkParams W;
     memset(&W, 0, sizeof W);

@@ -36,6 +36,27 @@ def casc():
     c.close()
 
 
+def _with_env(*names, **values):
+    """A handle created under A/B knobs / test hooks (a handle reads them from the environment once, when it is created)."""
+    env = {n: "1" for n in names}
+    env.update({k: str(v) for k, v in values.items()})
+    os.environ.update(env)
+    try:
+        return api.Cascador(SHIPPED_F32, double=False)
+    finally:
+        for k in env:
+            del os.environ[k]
+
+
+@pytest.fixture(scope="module")
+def casc_stages():
+    """stages >= 1 through k3_walk / k3_regress / k3_emit whatever the batch size (by default batches under 6e7 candidate
+    windows -- about 350 VGA frames -- take k3_cascade: ten small launches are pure latency on a short survivor list)"""
+    c = _with_env(JDA_B200_STAGE_MIN_WINDOWS=0)
+    yield c
+    c.close()
+
+
 # ---- the reference's own outputs -------------------------------------------------------------
 
 @pytest.mark.parametrize("case", [c[0] for c in CASES])
@@ -87,11 +108,7 @@ def test_trace_throughput_plan(oracle, oracle_shipped, frame, flags):
     """The batch (throughput) tile plan on one frame: pooled tiles, 512-window lists, global-memory levels -- every
     window's reject cart, exit score and leaves.  JDA_B200_FORCE_PLAN is a test hook: a one-frame call (the trace entry
     point) would otherwise only ever take the latency plan."""
-    os.environ["JDA_B200_FORCE_PLAN"] = "throughput"
-    try:
-        c = api.Cascador(SHIPPED_F32, double=False)
-    finally:
-        del os.environ["JDA_B200_FORCE_PLAN"]
+    c = _with_env(JDA_B200_FORCE_PLAN="throughput", JDA_B200_STAGE_MIN_WINDOWS=0)   # (and the traced stage kernels)
     img = TRACE_FRAMES[frame]()
     nwin = api.count_windows(img.shape[1], img.shape[0])
     for rng in [(max(nwin - 9000, 0), nwin), (nwin // 2, nwin // 2 + 2000), (0, 2000)]:
@@ -219,19 +236,27 @@ def test_synthetic_models(oracle, tmp_path, cfg):
     c.close(); oracle.release(ho)
 
 
+@pytest.mark.parametrize("stage_kernels", [False, True], ids=["k3_cascade", "stage_kernels"])
 @pytest.mark.parametrize("n_frames", [9, 130])
-def test_scan_plus_planes_batches(oracle, tmp_path, n_frames):
+def test_scan_plus_planes_batches(oracle, tmp_path, n_frames, stage_kernels):
     """Stage 0 from the LUT scan, stages >= 1 sampling the h / q planes, in batch mode (cohort-staged stage 0; 130
     frames: the size at which a scale-0 model would be copied in chunks -- a model with planes must not be).
     c/jda.c:340-354, 385-394."""
     path = synth.write_model(str(tmp_path / "syn.model"), seed=6, mode="reject", scales=(0, 1, 2), coord_max=0.45,
                              scales_by_stage={0: (0,)})
-    c = api.Cascador(path, double=True)
+    # (small frames: such a batch takes k3_cascade for the stages >= 1 unless the stage kernels -- here their h / q
+    # instantiation, k3_walk<., true> -- are forced)
+    os.environ["JDA_B200_STAGE_MIN_WINDOWS"] = "0" if stage_kernels else "1000000000000"
+    try:
+        c = api.Cascador(path, double=True)
+    finally:
+        del os.environ["JDA_B200_STAGE_MIN_WINDOWS"]
     ho = oracle.load(path, True)
     frames = synth.make_frames("facemix", n_frames, 112, 90, seed0=300)
     res = c.detect_batch(frames, th=-1e30, flags=api.RAW_HITS)
     st = c.last_stats
     assert st["scan_launches"] >= 1 and st["resize_launches"] == 1, st
+    assert (st["cascade_launches"] > 2) == stage_kernels, st
     hits = 0
     for f in range(n_frames):
         ob, osc, osh, ost = oracle.detect_raw(ho, frames[f], th=-1e30)
@@ -512,13 +537,18 @@ def test_mining_mode_truncated_cascade(casc, oracle, oracle_shipped, t_limit):
 
 @pytest.mark.parametrize("tk", [(0, 18), (0, 540), (2, 101), (1, 1), (4, 270)], ids=lambda tk: "t%d_k%d" % tk)
 @pytest.mark.parametrize("n_frames", [1, 6])
-def test_mining_mode_cart_granular(casc, oracle, oracle_shipped, tk, n_frames):
+def test_mining_mode_cart_granular(casc, casc_stages, oracle, oracle_shipped, tk, n_frames):
     """Validate() while a stage is being trained (src/jda/cascador.cpp:178-209, caller btcart.cpp:146-152):
     t full stages, then carts [0, k) of stage t, no regression after them.  1 frame: latency plan (k3_cascade
-    redoes stage 0); 6 frames: throughput plan (k2_scan -> k3_stage0 -> k3_cascade)."""
+    redoes stage 0); 6 frames: throughput plan, once with k3_cascade for the stages >= 1 (what a batch this small takes)
+    and once with the stage kernels (k2_scan -> k3_regress -> k3_walk ... -> k3_emit)."""
     t, k = tk
     frames = np.stack([synth.face_canvas()] + [synth.facemix_frame(90 + i) for i in range(n_frames - 1)])
     got = casc.detect_batch(frames, t_limit=t, k_limit=k, flags=api.RAW_HITS | api.NO_FINAL_TH)
+    if n_frames > 1:
+        forced = casc_stages.detect_batch(frames, t_limit=t, k_limit=k, flags=api.RAW_HITS | api.NO_FINAL_TH)
+        for a, b in zip(got, forced):
+            _same(a, b)
     total = 0
     for f in range(n_frames):
         ob, osc, osh, st = oracle.detect_raw(oracle_shipped, frames[f], t_limit=t, k_limit=k, use_th=False)
@@ -704,19 +734,10 @@ def test_queue_overflow_grows_and_retries(oracle, oracle_shipped):
 # ---- stages >= 1: the stage-synchronous kernels (k3_walk / k3_regress / k3_emit) against the one-warp-per-window
 # ---- kernel (k3_cascade) and the round-1 regression kernel (k3_stage0)
 
-def _with_env(name, **kw):
-    """(a handle reads its A/B knobs and test hooks from the environment once, when it is created)"""
-    os.environ[name] = "1"
-    try:
-        return api.Cascador(SHIPPED_F32, double=False, **kw)
-    finally:
-        del os.environ[name]
-
-
 @pytest.mark.parametrize("mode", ["full", "t2_k101", "t3"])
-def test_stage_kernels_equal_one_warp_per_window(casc, oracle, oracle_shipped, mode):
+def test_stage_kernels_equal_one_warp_per_window(casc_stages, oracle, oracle_shipped, mode):
     """A 40-frame batch (throughput plan) with many deep survivors: faces pass all five stages, blurred frames die in
-    stages 1-3.  Default = k3_walk + k3_regress + k3_emit; JDA_B200_NO_STAGE_KERNELS = k3_cascade for stages >= 1;
+    stages 1-3.  Stage kernels (forced: a batch this small takes k3_cascade by default) = k3_walk + k3_regress + k3_emit; JDA_B200_NO_STAGE_KERNELS = k3_cascade for stages >= 1;
     JDA_B200_OLD_REGRESS = k3_stage0 for every regression.  All three give the same bits, and frames 0 / 1 / 21 equal
     the oracle's."""
     frames = np.stack([synth.face_canvas()] + [synth.facemix_frame(300 + i) for i in range(19)] +
@@ -727,10 +748,10 @@ def test_stage_kernels_equal_one_warp_per_window(casc, oracle, oracle_shipped, m
         kw.update(t_limit=2, k_limit=101); okw.update(t_limit=2, k_limit=101)
     elif mode == "t3":
         kw.update(t_limit=3); okw.update(t_limit=3)
-    got = casc.detect_batch(frames, **kw)
-    launches = casc.last_stats["cascade_launches"]
+    got = casc_stages.detect_batch(frames, **kw)
+    launches = casc_stages.last_stats["cascade_launches"]
     c1 = _with_env("JDA_B200_NO_STAGE_KERNELS")
-    c2 = _with_env("JDA_B200_OLD_REGRESS")
+    c2 = _with_env("JDA_B200_OLD_REGRESS", JDA_B200_STAGE_MIN_WINDOWS=0)
     try:
         old = c1.detect_batch(frames, **kw)
         assert c1.last_stats["cascade_launches"] == 2 < launches   # (k3_stage0 + k3_cascade) against one pair per stage + emit
