@@ -269,6 +269,23 @@ struct Context {
 
 constexpr size_t kEagerHits = 64;
 constexpr int kLatencyFrames = 4;  // batches this small use the latency tile plan
+// ... and so do batches of more, smaller frames up to this many candidate windows (12 VGA 3-octave frames): measured per
+// call, latency / throughput plan -- 5 frames 0.85 / 1.35 ms, 8: 1.03 / 1.39, 12: 1.30 / 1.42, 16: 1.55 / 1.49
+// (profiles/r3f_small_batch.txt)
+constexpr long long kLatencyWindows = 2100000;
+
+// which tile plan a batch takes (plan_level; the latency plan also skips the cohort-staged stage 0)
+static bool batch_is_small(const jdaB200Batch &b, const jdaB200Frame *mixed) {
+  if (b.n_frames <= kLatencyFrames) return true;
+  long long w = 0;
+  if (mixed) {
+    for (int f = 0; f < b.n_frames && w <= kLatencyWindows; f++)
+      w += count_windows(mixed[f].width, mixed[f].height, b.scale, b.min_size, b.max_size);
+  } else {
+    w = count_windows(b.width, b.height, b.scale, b.min_size, b.max_size) * b.n_frames;
+  }
+  return w <= kLatencyWindows;
+}
 // First frame of chunk `ch` when a host batch is copied and scanned in `nchunks` pieces.  The pieces grow
 // (1/8, 2/8, 2/8, 3/8 of the batch): the first scan can only start when the first piece has landed, so it is small.
 int chunk_begin(int n_frames, int ch, int nchunks, bool even = false) {
@@ -1261,7 +1278,7 @@ bool run_prepare(Context *c, Run &R, const unsigned char *frames, const jdaB200B
     return false;
   }
   R.c = c; R.b = &b; R.mixed = mixed; R.trace = trace; R.timing = timing; R.tracing = trace != nullptr;
-  R.latency_plan = b.n_frames <= kLatencyFrames;
+  R.latency_plan = batch_is_small(b, mixed);
   if (c->tune.force_plan) R.latency_plan = c->tune.force_plan == 1;
   if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, R.latency_plan)) return false;
   const Geometry &g = c->geo;
@@ -2103,7 +2120,7 @@ static bool same_geometry(const Context *c, const jdaB200Batch &b, bool latency)
 }
 
 static bool plan_is_latency(const Context *c, const jdaB200Batch &b) {
-  return c->tune.force_plan ? c->tune.force_plan == 1 : b.n_frames <= kLatencyFrames;
+  return c->tune.force_plan ? c->tune.force_plan == 1 : batch_is_small(b, nullptr);
 }
 
 int jdaB200Submit(void *cascador, const unsigned char *frames, const jdaB200Batch *batch) {

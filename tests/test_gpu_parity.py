@@ -50,9 +50,10 @@ def _with_env(*names, **values):
 
 @pytest.fixture(scope="module")
 def casc_stages():
-    """stages >= 1 through k3_walk / k3_regress / k3_emit whatever the batch size (by default batches under 6e7 candidate
-    windows -- about 350 VGA frames -- take k3_cascade: ten small launches are pure latency on a short survivor list)"""
-    c = _with_env(JDA_B200_STAGE_MIN_WINDOWS=0)
+    """throughput tile plan and stages >= 1 through k3_walk / k3_regress / k3_emit whatever the batch size (by default
+    batches under 2.1e6 candidate windows take the latency plan, and batches under 6e7 -- about 350 VGA frames -- take
+    k3_cascade: ten small launches are pure latency on a short survivor list)"""
+    c = _with_env(JDA_B200_STAGE_MIN_WINDOWS=0, JDA_B200_FORCE_PLAN="throughput")
     yield c
     c.close()
 
@@ -247,10 +248,11 @@ def test_scan_plus_planes_batches(oracle, tmp_path, n_frames, stage_kernels):
     # (small frames: such a batch takes k3_cascade for the stages >= 1 unless the stage kernels -- here their h / q
     # instantiation, k3_walk<., true> -- are forced)
     os.environ["JDA_B200_STAGE_MIN_WINDOWS"] = "0" if stage_kernels else "1000000000000"
+    os.environ["JDA_B200_FORCE_PLAN"] = "throughput"   # (9 small frames would otherwise take the latency plan)
     try:
         c = api.Cascador(path, double=True)
     finally:
-        del os.environ["JDA_B200_STAGE_MIN_WINDOWS"]
+        del os.environ["JDA_B200_STAGE_MIN_WINDOWS"], os.environ["JDA_B200_FORCE_PLAN"]
     ho = oracle.load(path, True)
     frames = synth.make_frames("facemix", n_frames, 112, 90, seed0=300)
     res = c.detect_batch(frames, th=-1e30, flags=api.RAW_HITS)

@@ -1,4 +1,4 @@
-"""Cascade kernels on small batches (what coalesced jdaDetect calls and small jdaB200DetectBatch calls run):
+"""Tile plan and cascade kernels on small batches (what coalesced jdaDetect calls and small jdaB200DetectBatch calls run):
 stage kernels (k3_walk / k3_regress / k3_emit) against k3_cascade for stages >= 1, resident frames, steady state."""
 import os, sys, time
 import numpy as np
@@ -9,18 +9,20 @@ from jda_b200 import api, synth
 
 def handle(env=None):
     if env:
-        os.environ[env] = "1"
+        os.environ[env[0]] = env[1]
     try:
         return api.Cascador("tests/golden/jda_shipped_f32.model", double=False)
     finally:
         if env:
-            del os.environ[env]
+            del os.environ[env[0]]
 
 
 pool = synth.make_frames("mix", 64, 640, 480, seed0=100000)
-for name, env in (("stage kernels", None), ("k3_cascade for stages >= 1", "JDA_B200_NO_STAGE_KERNELS")):
+for name, env in (("default", None), ("stage kernels", ("JDA_B200_STAGE_MIN_WINDOWS", "0")),
+                  ("k3_cascade for stages >= 1", ("JDA_B200_NO_STAGE_KERNELS", "1")),
+                  ("latency tile plan", ("JDA_B200_FORCE_PLAN", "latency"))):
     c = handle(env)
-    for n in (5, 8, 16, 32, 64, 128, 256):
+    for n in ((1, 2, 4, 5, 8, 12, 16, 24, 32, 64) if name in ("default", "latency tile plan") else (5, 16, 64, 256)):
         fr = np.ascontiguousarray(pool[np.arange(n) % 64])
         d = torch.from_numpy(fr).cuda()
         torch.cuda.synchronize()
