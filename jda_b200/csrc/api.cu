@@ -79,7 +79,7 @@ struct DevBuf {
 struct Geometry {
   int w = 0, h = 0, min_size = 0, max_size = 0;
   float scale = 0.f;
-  bool latency = false;  // which tile plan (see plan_level)
+  int plan = 0;          // which tile plan (see plan_level): 0 throughput, 1 latency, 2 throughput with short global-memory tiles
   int step64 = 0;        // double-precision detector: fixed step and double scale factor (0 = the C path's ladder)
   double factor64 = 0.;
   int n_levels = 0;
@@ -274,17 +274,23 @@ constexpr int kLatencyFrames = 4;  // batches this small use the latency tile pl
 // (profiles/r3f_small_batch.txt)
 constexpr long long kLatencyWindows = 2100000;
 
-// which tile plan a batch takes (plan_level; the latency plan also skips the cohort-staged stage 0)
-static bool batch_is_small(const jdaB200Batch &b, const jdaB200Frame *mixed) {
-  if (b.n_frames <= kLatencyFrames) return true;
+// ... and batches up to this many (47 VGA frames) keep the throughput plan but read the global-memory levels in
+// 128-window virtual tiles instead of 512-window ones (plan 2): scan of 16 frames 1.03 -> 0.86 ms, 24: 1.39 -> 1.23,
+// 32: 1.63 -> 1.59, 64: 2.99 -> 3.01 (profiles/r3h_small_batch_default.txt against r3g_)
+constexpr long long kMediumWindows = 8000000;
+
+// which tile plan a batch takes (plan_level): 0 throughput, 1 latency (also skips the cohort-staged stage 0), 2 medium
+static int batch_plan(const Tuning &tn, const jdaB200Batch &b, const jdaB200Frame *mixed) {
+  if (tn.force_plan) return tn.force_plan == 1 ? 1 : 0;
+  if (b.n_frames <= kLatencyFrames) return 1;
   long long w = 0;
   if (mixed) {
-    for (int f = 0; f < b.n_frames && w <= kLatencyWindows; f++)
+    for (int f = 0; f < b.n_frames && w <= kMediumWindows; f++)
       w += count_windows(mixed[f].width, mixed[f].height, b.scale, b.min_size, b.max_size);
   } else {
     w = count_windows(b.width, b.height, b.scale, b.min_size, b.max_size) * b.n_frames;
   }
-  return w <= kLatencyWindows;
+  return w <= kLatencyWindows ? 1 : w <= kMediumWindows ? 2 : 0;
 }
 // First frame of chunk `ch` when a host batch is copied and scanned in `nchunks` pieces.  The pieces grow
 // (1/8, 2/8, 2/8, 3/8 of the batch): the first scan can only start when the first piece has landed, so it is small.
@@ -598,7 +604,8 @@ int plan_tile(const Tuning &tn, LevelInfo &L, int tile_bytes, int min_tl = 3, in
 // (with its 16-byte-granular pixel box) fits a warp's 8 KB buffer -- or, for coarser levels, the
 // buffers of 2 or 4 neighbouring warps (only every 2nd / 4th warp then works on that level).  Levels
 // that fit neither read pixels from global memory in "virtual" tiles of 32 x 16 windows.
-void plan_level(const Tuning &tn, LevelInfo &L, bool latency) {
+void plan_level(const Tuning &tn, LevelInfo &L, int plan) {
+  const bool latency = plan == 1;
   // Two plans.  Throughput (many frames in flight): coarse levels pool at most 4 warps' buffers, what is
   // left reads global memory in 512-window virtual tiles -- measured fastest on 128+ frame batches.
   // Latency (a handful of frames): the coarsest levels pool the whole block's buffers and go straight to
@@ -628,7 +635,9 @@ void plan_level(const Tuning &tn, LevelInfo &L, bool latency) {
     L = pick;
   }
   if (!L.use_smem) {  // global-memory virtual tiles
-    L.tw_log2 = 5; L.th = latency ? 4 : K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0;
+    // (medium batches, plan 2: 128-window virtual tiles -- a 512-window tile read from global memory is a ~1 ms chain of
+    // dependent loads, the floor of every scan under ~100 frames; at 512 frames the short tiles cost 0.6 %)
+    L.tw_log2 = 5; L.th = (latency || plan == 2) ? 4 : K2_LIST_CAP / 32; L.box_w = 0; L.box_h = 0;
     if (tn.global_tile_rows > 0) L.th = tn.global_tile_rows;
   }
   const int tw = 1 << L.tw_log2;
@@ -636,13 +645,13 @@ void plan_level(const Tuning &tn, LevelInfo &L, bool latency) {
   L.nty = (L.ny + L.th - 1) / L.th;
 }
 
-bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int max_size, bool latency) {
+bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int max_size, int plan) {
   Geometry &g = c->geo;
   if (g.valid && g.w == w && g.h == h && g.scale == scale && g.min_size == min_size && g.max_size == max_size &&
-      g.latency == latency)
+      g.plan == plan)
     return true;
   g.valid = false;
-  g.w = w; g.h = h; g.scale = scale; g.min_size = min_size; g.max_size = max_size; g.latency = latency;
+  g.w = w; g.h = h; g.scale = scale; g.min_size = min_size; g.max_size = max_size; g.plan = plan;
   int wins[kMaxLevels + 1];
   int n = (w < 24 || h < 24) ? 0 : enumerate_levels(w, h, scale, min_size, max_size, wins, kMaxLevels + 1);
   if (n > kMaxLevels) {
@@ -661,7 +670,7 @@ bool ensure_geometry(Context *c, int w, int h, float scale, int min_size, int ma
     L.nx = (w - L.win) / L.step + 1;
     L.ny = (h - L.win) / L.step + 1;
     if (L.nx > 8191 || L.ny > 8191) { set_err("frame too large for 13-bit window indices"); return false; }
-    plan_level(c->tune, L, latency);
+    plan_level(c->tune, L, plan);
     L.table_off = i * g.table_bytes;
     L.win_base = base;
     base += (long long)L.nx * L.ny;
@@ -1278,9 +1287,9 @@ bool run_prepare(Context *c, Run &R, const unsigned char *frames, const jdaB200B
     return false;
   }
   R.c = c; R.b = &b; R.mixed = mixed; R.trace = trace; R.timing = timing; R.tracing = trace != nullptr;
-  R.latency_plan = batch_is_small(b, mixed);
-  if (c->tune.force_plan) R.latency_plan = c->tune.force_plan == 1;
-  if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, R.latency_plan)) return false;
+  const int plan = batch_plan(c->tune, b, mixed);
+  R.latency_plan = plan == 1;
+  if (!ensure_geometry(c, b.width, b.height, b.scale, b.min_size, b.max_size, plan)) return false;
   const Geometry &g = c->geo;
   R.geo = &c->geo; R.tables = c->d_tables.p; R.norms = c->d_norms;
   st.n_levels = g.n_levels;
@@ -1464,11 +1473,11 @@ bool ensure_model64(Context *c) {
 bool ensure_geometry64(Context *c, int w, int h, int minimum_size, int step, double factor, bool latency) {
   Geometry &g = c->geo64;
   if (g.valid && g.w == w && g.h == h && g.min_size == minimum_size && g.step64 == step && g.factor64 == factor &&
-      g.latency == latency)
+      g.plan == (latency ? 1 : 0))
     return true;
   g.valid = false;
   g.w = w; g.h = h; g.min_size = minimum_size; g.max_size = 0; g.scale = 0.f; g.step64 = step; g.factor64 = factor;
-  g.latency = latency;
+  g.plan = latency ? 1 : 0;
   int wins[kMaxLevels + 1];
   const int n = enumerate_levels_f64(w, h, minimum_size, factor, wins, kMaxLevels + 1);
   if (n > kMaxLevels) { set_err("more than %d pyramid levels (scale too close to 1)", kMaxLevels); return false; }
@@ -1484,7 +1493,7 @@ bool ensure_geometry64(Context *c, int w, int h, int minimum_size, int step, dou
     L.nx = (w - L.win) / step + 1;
     L.ny = (h - L.win) / step + 1;
     if (L.nx > 8191 || L.ny > 8191) { set_err("frame too large for 13-bit window indices"); return false; }
-    plan_level(c->tune, L, latency);
+    plan_level(c->tune, L, latency ? 1 : 0);
     L.table_off = i * g.table_bytes;
     L.win_base = base;
     base += (long long)L.nx * L.ny;
@@ -2113,14 +2122,10 @@ int jdaB200JoinCascadorLevels(int width, int height, int minimum_size, double sc
 // ---- submit / collect: two batches in flight ----------------------------------------------------------------
 // While batch i is scanned, batch i + 1 is already being copied in; while batch i + 1 is scanned, the host sorts,
 // suppresses and relocates the hits of batch i.  Set t & 1 of the handle's two scratch sets serves ticket t.
-static bool same_geometry(const Context *c, const jdaB200Batch &b, bool latency) {
+static bool same_geometry(const Context *c, const jdaB200Batch &b, int plan) {
   const Geometry &g = c->geo;
   return g.valid && g.w == b.width && g.h == b.height && g.scale == b.scale && g.min_size == b.min_size &&
-         g.max_size == b.max_size && g.latency == latency;
-}
-
-static bool plan_is_latency(const Context *c, const jdaB200Batch &b) {
-  return c->tune.force_plan ? c->tune.force_plan == 1 : batch_is_small(b, nullptr);
+         g.max_size == b.max_size && g.plan == plan;
 }
 
 int jdaB200Submit(void *cascador, const unsigned char *frames, const jdaB200Batch *batch) {
@@ -2143,7 +2148,7 @@ int jdaB200Submit(void *cascador, const unsigned char *frames, const jdaB200Batc
   if (!slot_init(sl)) return done(-1);
   // the stage-0 tables belong to a geometry: a batch of another size or pyramid may only rebuild them once the
   // batch that is still using them has finished
-  if (other.busy && !same_geometry(c, *batch, plan_is_latency(c, *batch))) cudaEventSynchronize(other.ev_done);
+  if (other.busy && !same_geometry(c, *batch, batch_plan(c->tune, *batch, nullptr))) cudaEventSynchronize(other.ev_done);
   c->sc = &sl;
   sl.batch = *batch;
   sl.frames = frames;
@@ -2289,7 +2294,7 @@ int jdaB200DescribePlan(int width, int height, float scale, int min_size, int ma
     memset(&L, 0, sizeof L);
     L.win = wins[i]; L.step = level_step(L.win);
     L.nx = (width - L.win) / L.step + 1; L.ny = (height - L.win) / L.step + 1;
-    plan_level(tn, L, latency);
+    plan_level(tn, L, latency ? 1 : 0);
     if (buf && o < cap)
       o += snprintf(buf + o, cap - o, "%d %d %d %d %d %d %d %d %d %d %d\n", L.win, L.step, L.nx, L.ny, 1 << L.tw_log2,
                     L.th, L.box_w, L.box_h, L.use_smem, (1 << L.tw_log2) * L.th, L.span);
