@@ -23,12 +23,12 @@ if [ "${NCU:-1}" = "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $O/${tag}_ncu_bench.log 2>&1
 grep -c k2_scan $O/${tag}_launches.csv
-# full capture: the kernels of ONE 256-frame step (k2_scan, k3_regress, 4 x (k3_walk, k3_regress), k3_emit), resident frames;
+# full capture: the kernels of ONE 512-frame step (the stage kernels run from 6e7 candidate windows up) (k2_scan, k3_regress, 4 x (k3_walk, k3_regress), k3_emit), resident frames;
 # the traced instantiations the bench uses for its cart statistics are left out by name
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
   -k regex:'k2_scan<\(int\)4, \(bool\)0, \(bool\)0>|k3_walk<\(bool\)0|k3_regress|k3_emit<\(bool\)0' -s 11 -c 11 -f -o /tmp/${tag}_full \
-  python bench.py --batch 256 --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $O/${tag}_ncu_full.log 2>&1
-python tools/ncu_digest.py /tmp/${tag}_full.ncu-rep $O/${tag}_full 256 >> $O/${tag}_ncu_full.log 2>&1
+  python bench.py --batch 512 --steps 2 --warmup 1 --no-cpu-baseline --no-breakdown > $O/${tag}_ncu_full.log 2>&1
+python tools/ncu_digest.py /tmp/${tag}_full.ncu-rep $O/${tag}_full 512 >> $O/${tag}_ncu_full.log 2>&1
 cp $O/${tag}_full_k2_capture.json $O/k2_capture.json 2>/dev/null   # -> profiles/k2_capture.json (bench.py reads it)
 ls -la /tmp/${tag}_full.ncu-rep >> $O/${tag}_ncu_full.log 2>&1
 fi
