@@ -91,3 +91,14 @@ def test_all_gather_detections_world2(oracle, oracle_shipped, tmp_path):
     np.testing.assert_array_equal(t0.view(np.uint32), want.view(np.uint32))  # = the single-process answer
     fid = shard.unpack_records(t0)[0]
     assert (np.diff(fid) >= 0).all() and len(fid) >= 4
+
+
+def test_record_gather_block_capacity_rule():
+    """detections (hundreds per batch): twice the largest count, a power of two; mining (tens of thousands per batch):
+    a quarter above it, rounded to 4096 -- every padded row crosses NVLink and PCIe to every rank"""
+    from jda_b200.shard import RecordGather
+    assert RecordGather._next_cap(0) == 1 and RecordGather._next_cap(3) == 8 and RecordGather._next_cap(200) == 512
+    assert RecordGather._next_cap(4095) == 8192
+    for n in (4096, 27785, 100000):
+        cap = RecordGather._next_cap(n)
+        assert cap % 4096 == 0 and 1.25 * n <= cap < 1.25 * n + 4096
