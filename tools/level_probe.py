@@ -4,6 +4,8 @@ import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jda_b200 import api, synth
+# one level of 256 frames can be under the small-batch thresholds: the probe is about the throughput tile plan
+os.environ.setdefault("JDA_B200_FORCE_PLAN", "throughput")
 c = api.Cascador("tests/golden/jda_shipped_f32.model", double=False)
 pool = synth.make_frames("mix", 64, 640, 480, seed0=100000)
 fr = np.ascontiguousarray(pool[np.arange(256) % 64])
