@@ -226,3 +226,29 @@ def test_our_header_is_plain_c(tmp_path):
     for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
         subprocess.run(["gcc", "-x", lang, std, "-Wall", "-Werror", "-fsyntax-only", "-I", inc,
                         os.path.join(inc, "jda_b200.h")], check=True)
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The structs of include/jda_b200.h as the C compiler lays them out against their ctypes mirrors in jda_b200/api.py
+    (tests and bench call through those): size and the offset of every field."""
+    import ctypes
+    import subprocess
+    pairs = {"jdaB200CppParams": api.CppParams, "jdaB200Stats": api.Stats, "jdaB200FlatResult": api.FlatResult,
+             "jdaB200ResultF64": api.ResultF64, "jdaB200Batch": api.Batch, "jdaB200Frame": api.Frame, "jdaResult": api._Result}
+    lines = []
+    for cname, cls in pairs.items():
+        lines.append('printf("%s size %%d\\n", (int)sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%d\\n", (int)offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "jda_b200.h"\nint main(void) {\n' + "\n".join(lines) +
+                   "\nreturn 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
