@@ -141,7 +141,8 @@ def main(argv=None):
         print("T=%d K=%d landmarks=%d depth=%d" % (c.T, c.K, c.L, c.depth))
         print("%dx%d, max_size %d: %d candidate windows" % (w, h, a.max_size, api.count_windows(w, h, 1.25, 24, a.max_size)))
         for lat in (False, True):
-            print("scan plan (%s):" % ("<= 4 frames per call" if lat else "batches"))
+            print("scan plan (%s):" % ("calls of <= 4 frames or <= 2.1e6 candidate windows" if lat else
+                                       "batches; up to 8e6 candidate windows the global-memory levels use 32 x 4 tiles"))
             for q in api.describe_plan(w, h, 1.25, 24, a.max_size, latency=lat):
                 print("   win %3d step %2d  %4d x %-4d windows  tile %2d x %-2d  box %3d x %-3d  %s" %
                       (q["win"], q["step"], q["nx"], q["ny"], q["tw"], q["th"], q["box_w"], q["box_h"],
