@@ -19,7 +19,8 @@ from oracle import pyoracle
 from jda_b200 import synth, api
 
 MODEL = "tests/golden/jda_shipped_f32.model"
-SCHED = [4, 8, 12, 16, 24, 32, 48, 64, 96, 128, 160, 192, 256, 320, 384, 448, 540]
+SCHED = [8, 16, 24, 32, 40, 48, 64, 80, 96, 128, 160, 192, 256, 320, 384, 448, 540]   # api.cu: ctx_init (round-2 default)
+STRAG_MAX = 32                                                                        # kernels.cuh: K2_STRAG_MAX
 K = 540
 
 
@@ -79,7 +80,7 @@ def wavefronts(addr):
 
 
 def simulate(img, deaths, win, step, tw, th_rows, pitch, xy, n1, n2, nx, ny, nw=4, order="row", max_tiles=None, rng=None,
-             planes=False):
+             planes=False, bank_order=False):
     """returns dict depth -> [sum wavefronts, loads] and per-phase totals.
     planes=True: the de-interleaved tile layout (round 2): pixel (x, y) of the tile lives in plane (y % step, x % step) at
     (y // step, x // step), so a window's base is wy * bx + wx and neighbouring windows are ONE byte apart; `pitch` is bx."""
@@ -117,8 +118,17 @@ def simulate(img, deaths, win, step, tw, th_rows, pitch, xy, n1, n2, nx, ny, nw=
             n = len(alive)
             if n == 0:
                 break
-            if ph > 0 and n <= 15:
+            if ph > 0 and n <= STRAG_MAX:
                 break                                   # straggler mode from here (not modelled)
+            if ph > 0 and bank_order:
+                # what-if: the compacted list ordered so that every packet of 32 holds windows of distinct bank classes
+                # as far as the classes' sizes allow (round-robin over the 32 classes of the windows' base words)
+                cls = (tbase[alive] >> 2) & 31
+                srt = np.argsort(cls, kind="stable")
+                rank = np.empty(n, np.int64)
+                starts = np.r_[0, np.cumsum(np.bincount(cls, minlength=32))[:-1]]
+                rank[srt] = np.arange(n) - starts[cls[srt]]
+                alive = alive[np.lexsort((cls, rank))]
             lst = alive
             npk = (n + 31) // 32
             W_ = np.full(npk * 32, -1, np.int64)
@@ -189,9 +199,10 @@ def main():
         if planes and step * step * pitch * (thr + halo) > 8192:
             print("(planes tw %d th %d bx %d: %d bytes, does not fit 8 KB)" % (tw, thr, pitch, step * step * pitch * (thr + halo)))
             continue
+        bo = os.environ.get("SIM_BANK_ORDER") == "1"
         tot, per = simulate(img, deaths, win, step, tw, thr, pitch, xy, n1, n2, nx, ny, max_tiles=40, planes=planes,
-                            order=os.environ.get("SIM_ORDER", "row"))
-        s = "%s tw %2d th %2d pitch %3d: " % ("PLANES" if planes else "raw   ", tw, thr, pitch)
+                            order=os.environ.get("SIM_ORDER", "row"), bank_order=bo)
+        s = "%s%s tw %2d th %2d pitch %3d: " % ("PLANES" if planes else "raw   ", " bank-ordered packets" if bo else "", tw, thr, pitch)
         s += "  ".join("%s %.2f" % (nm, tot[i, 0] / tot[i, 1]) for i, nm in enumerate(("root", "L1", "L2")))
         s += "  all %.3f wavefronts / LDS.U8" % (tot[:, 0].sum() / tot[:, 1].sum())
         print(s)
